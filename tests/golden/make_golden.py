@@ -1,0 +1,156 @@
+"""Generate tests/golden/*.npz by running the REAL reference from /root/reference on CPU.
+
+Run in the build container only:   python tests/golden/make_golden.py
+The reference cannot travel to the GPU box, so its outputs on seeded inputs are committed
+here as small (sub-sampled) fixtures; tests/test_oracle_golden.py pins oracle/restate.py
+against them, and the GPU parity tests then use the oracle as the travelling checker.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import fixtures, ref_import, weights  # noqa: E402
+from oracle.restate import DEFAULT_TEST_CFG  # noqa: E402
+
+torch.set_grad_enabled(False)
+
+
+def sub(t, *steps):
+    sl = tuple(slice(None, None, s) for s in steps)
+    return np.ascontiguousarray(t[sl].numpy() if isinstance(t, torch.Tensor) else t[sl])
+
+
+def model_case(name, sam_arch, dino_arch):
+    """Encoder / DINOv2 / decoder / predict_torch outputs of the real modules."""
+    sam_sd = weights.make_sam_state(sam_arch)
+    dino_sd = weights.make_dino_state(dino_arch)
+    sam = ref_import.build_sam(sam_sd, sam_arch)
+    dino = ref_import.build_dino(dino_sd, dino_arch)
+    sacs, _, _ = ref_import.load()
+    pred = sacs.SamPredictor(sam, dino)
+    out = {}
+    # ---- square image: set_image + decoder on 6 prompts
+    img = weights.synthetic_image(0)
+    pred.set_image(img)
+    out["features"] = sub(pred.features, 1, 8, 2, 2)
+    out["dino_feats"] = sub(pred.dino_feats, 1, 6, 6, 8)
+    out["fg_map"] = sub(pred.predict_fg_map(), 1, 1, 4, 4)
+    pts = np.array([[10, 20], [512, 512], [1000, 30], [333, 777], [64, 960], [800, 801]])
+    coords = torch.as_tensor(pred.transform.apply_coords(pts, pred.original_size))[:, None, :]
+    labels = torch.ones(len(pts), dtype=torch.int)[:, None]
+    masks, iou, cls, low = pred.predict_torch(coords, labels, multimask_output=True, return_logits=True)
+    out["points"] = pts
+    out["low_res"] = sub(low, 1, 1, 8, 8)
+    out["masks"] = sub(masks, 1, 1, 32, 32)
+    out["iou_pred"] = iou.numpy()
+    out["cls"] = cls.numpy()
+    out["dense_pe"] = sub(sam.prompt_encoder.get_dense_pe(), 1, 4, 4, 4)
+    # ---- non-square image (exercises pad + both postprocess resizes)
+    img2 = weights.synthetic_image(1, 600, 900)
+    pred.set_image(img2)
+    pts2 = np.array([[5, 5], [450, 300], [880, 590]])
+    coords2 = torch.as_tensor(pred.transform.apply_coords(pts2, pred.original_size))[:, None, :]
+    masks2, iou2, cls2, low2 = pred.predict_torch(coords2, labels[:3], multimask_output=True, return_logits=True)
+    out["ns_points"] = pts2
+    out["ns_features"] = sub(pred.features, 1, 8, 2, 2)
+    out["ns_low_res"] = sub(low2, 1, 1, 8, 8)
+    out["ns_masks"] = sub(masks2, 1, 1, 24, 36)
+    out["ns_iou_pred"] = iou2.numpy()
+    out["ns_cls"] = cls2.numpy()
+    np.savez_compressed(os.path.join(HERE, f"model_{name}.npz"), **out)
+    print("wrote", name, {k: v.shape for k, v in out.items()})
+    return sam, dino
+
+
+def pipeline_case(name, sam, dino, overrides, image_index=0, hw=(1024, 1024)):
+    """CrowdSAM.generate end to end through the real crowdsam/model.py."""
+    cfg = dict(DEFAULT_TEST_CFG)
+    cfg.update(overrides)
+    m = ref_import.build_crowdsam(sam, dino, cfg)
+    img = weights.synthetic_image(image_index, *hw)
+    np.random.seed(42)
+    res = m.generate(img)
+    out = {"cfg_keys": np.array(sorted(overrides.keys())),
+           "cfg_vals": np.array([str(overrides[k]) for k in sorted(overrides.keys())]),
+           "image_index": np.array(image_index), "hw": np.array(hw)}
+    for k, v in res.items():
+        if k == "rles":
+            out["rle_counts"] = np.array([r["counts"] for r in v])
+            out["rle_sizes"] = np.array([r["size"] for r in v]).reshape(-1, 2)
+        elif k == "rles_info":
+            out["rles_info"] = np.array([list(v[0]), list(v[1]) + [0, 0]])
+        else:
+            out[k] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, f"pipeline_{name}.npz"), **out)
+    print("wrote pipeline", name, {k: (v.shape, v.dtype) for k, v in out.items()})
+
+
+def stage_case():
+    """Post-processing + NMS + RLE through the reference's own utility functions on seeded
+    blob logits (the stage-level fixture of SURVEY.md §8d)."""
+    ref_import.load()
+    from segment_anything_cs.utils import amg
+    from segment_anything_cs.modeling.sam import Sam
+    from torchvision.ops import nms as tv_nms
+    from torchvision.ops.boxes import batched_nms
+
+    out = {}
+    P = 48
+    low, iou, cls = fixtures.blob_logits(P, seed=0)
+
+    class _Enc:
+        img_size = 1024
+
+    class _S:
+        image_encoder = _Enc()
+
+    for tag, (inp, orig) in {"sq": ((1024, 1024), (1024, 1024)), "ns": ((683, 1024), (600, 900))}.items():
+        full = Sam.postprocess_masks(_S(), low, inp, orig)
+        score = torch.clamp(iou, 0.0) * cls.squeeze(2).sigmoid()
+        sel = score.max(dim=-1)[1]
+        m = full[torch.arange(P), sel]
+        stab = amg.calculate_stability_score(m, 0.0, 1.0)
+        binm = m > 0.0
+        boxes = amg.batched_mask_to_box(binm)
+        out[f"{tag}_score"] = score[torch.arange(P), sel].numpy()
+        out[f"{tag}_sel"] = sel.numpy()
+        out[f"{tag}_stability"] = stab.numpy()
+        out[f"{tag}_boxes"] = boxes.numpy()
+        out[f"{tag}_area"] = binm.flatten(1).sum(1).numpy()
+        keep = batched_nms(boxes.float(), score[torch.arange(P), sel], torch.zeros_like(boxes[:, 0]), 0.65)
+        out[f"{tag}_nms_keep"] = keep.numpy()
+        if tag == "sq":
+            rles = amg.mask_to_rle_pytorch(binm[:4])
+            out["sq_rle_counts0"] = np.array(rles[0]["counts"])
+            out["sq_rle_counts3"] = np.array(rles[3]["counts"])
+            out["sq_rle_str0"] = np.array(amg.coco_encode_rle(rles[0])["counts"])
+    # plain NMS goldens (torchvision.ops.nms, CPU = stable order)
+    for n, seed, binary in ((257, 0, False), (3000, 1, False), (3000, 2, True), (1, 3, False)):
+        b, s = fixtures.random_boxes(n, seed, binary_scores=binary)
+        for thr in (0.65, 0.7):
+            keep = tv_nms(torch.as_tensor(b), torch.as_tensor(s), thr)
+            out[f"nms_{n}_{seed}_{thr}"] = keep.numpy()
+    np.savez_compressed(os.path.join(HERE, "stage_post_nms.npz"), **out)
+    print("wrote stage", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    assert ref_import.available(), "needs /root/reference"
+    torch.manual_seed(0)
+    stage_case()
+    sam, dino = model_case("tiny", "tiny", "tiny")
+    pipeline_case("tiny_grid8", sam, dino,
+                  dict(grid_size=8, pos_sim_thresh=-1, max_prompts=64, points_per_batch=16,
+                       filter_thresh=2.0, min_mask_region_area=0))
+    pipeline_case("tiny_eps", sam, dino,
+                  dict(grid_size=16, pos_sim_thresh=0.5, max_prompts=48, points_per_batch=8,
+                       filter_thresh=0.3, min_mask_region_area=100, pred_iou_thresh=0.05,
+                       stability_score_thresh=0.5), image_index=2, hw=(768, 1024))
+    model_case("tiny_l", "tiny_l", "tiny")
