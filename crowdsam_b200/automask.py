@@ -1,0 +1,77 @@
+"""SamAutomaticMaskGenerator on the B200 kernels.
+
+The reference copy cannot be constructed (`SamPredictor(model)` lacks `dino_model`,
+automatic_mask_generator.py:123) nor unpack predict_torch's 4 returns (:279), so there is no runnable
+reference behaviour to match; this class provides the upstream-SAM semantics (32x32 grid, 64 points per
+batch, all 4 masks per point, pred_iou 0.88 / stability 0.95 / box NMS 0.7) on the same kernels.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import amg, ops
+from .predictor import SamPredictor
+
+
+class SamAutomaticMaskGenerator:
+    def __init__(self, model, dino_model=None, points_per_side: Optional[int] = 32, points_per_batch: int = 64,
+                 pred_iou_thresh: float = 0.88, stability_score_thresh: float = 0.95,
+                 stability_score_offset: float = 1.0, box_nms_thresh: float = 0.7, crop_n_layers: int = 0,
+                 min_mask_region_area: int = 0, output_mode: str = "binary_mask", **unused) -> None:
+        assert output_mode in ("binary_mask", "uncompressed_rle", "coco_rle")
+        if crop_n_layers != 0:
+            raise NotImplementedError("multi-crop AMG is outside the B200 hot path")
+        if dino_model is None:
+            raise TypeError("SamAutomaticMaskGenerator needs dino_model (PWD-Net features feed the mask decoder)")
+        self.predictor = SamPredictor(model, dino_model)
+        self.point_grid = amg.build_point_grid(points_per_side)
+        self.points_per_batch = points_per_batch
+        self.pred_iou_thresh = pred_iou_thresh
+        self.stability_score_thresh = stability_score_thresh
+        self.stability_score_offset = stability_score_offset
+        self.box_nms_thresh = box_nms_thresh
+        self.output_mode = output_mode
+
+    @torch.no_grad()
+    def generate(self, image: np.ndarray) -> List[Dict[str, Any]]:
+        pr = self.predictor
+        pr.set_image(image)
+        h, w = image.shape[:2]
+        pts = self.point_grid * np.array([[w, h]])
+        thr = float(pr.model.mask_threshold)
+        all_masks, all_iou, all_stab, all_boxes, all_pts = [], [], [], [], []
+        for (chunk,) in amg.batch_iterator(self.points_per_batch, pts):
+            coords = torch.as_tensor(pr.transform.apply_coords(chunk, (h, w)))[:, None, :]
+            labels = torch.ones(coords.shape[0], dtype=torch.int)[:, None]
+            low, iou, _ = pr.decode_low_res(coords, labels)
+            flat = low.reshape(-1, 256, 256)
+            counts, boxes = ops.mask_post_stats(flat, None, pr.input_size, pr.original_size, thr, self.stability_score_offset)
+            stab = counts[:, 0] / counts[:, 1]
+            iou_f = iou.reshape(-1)
+            keep = (iou_f > self.pred_iou_thresh) & (stab >= self.stability_score_thresh)
+            idx = keep.nonzero()[:, 0]
+            masks, _ = ops.mask_post_write(flat, None, idx.to(torch.int32), pr.input_size, pr.original_size, thr)
+            all_masks.append(masks); all_iou.append(iou_f[idx]); all_stab.append(stab[idx]); all_boxes.append(boxes[idx])
+            all_pts.append(torch.as_tensor(chunk).repeat_interleave(4, dim=0)[idx.cpu()])
+        pr.reset_image()
+        masks = torch.cat(all_masks); iou = torch.cat(all_iou); stab = torch.cat(all_stab)
+        boxes = torch.cat(all_boxes); ptsk = torch.cat(all_pts)
+        keep = ops.box_nms(boxes.float(), iou, self.box_nms_thresh)
+        masks, iou, stab, boxes, ptsk = masks[keep], iou[keep], stab[keep], boxes[keep], ptsk[keep.cpu()]
+        if self.output_mode == "binary_mask":
+            segs = [m for m in masks.cpu().numpy()]
+        else:
+            rles = amg.mask_to_rle_pytorch(masks)
+            segs = [amg.coco_encode_rle(r) for r in rles] if self.output_mode == "coco_rle" else rles
+        areas = masks.flatten(1).sum(1).tolist()
+        out = []
+        for i in range(len(segs)):
+            b = boxes[i].tolist()
+            out.append({"segmentation": segs[i], "area": int(areas[i]),
+                        "bbox": [b[0], b[1], b[2] - b[0], b[3] - b[1]], "predicted_iou": float(iou[i]),
+                        "point_coords": [ptsk[i].tolist()], "stability_score": float(stab[i]),
+                        "crop_box": [0, 0, w, h]})
+        return out

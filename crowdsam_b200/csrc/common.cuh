@@ -1,0 +1,198 @@
+// common.cuh — shared helpers for libcsam_sm100 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+
+#include "../../include/csam.h"
+
+namespace csam {
+
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+inline int fail(const char* fmt, const char* a = "", long long b = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return 1;
+}
+inline int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+#define CSAM_REQUIRE(cond, msg)                                   \
+  do {                                                            \
+    if (!(cond)) return ::csam::fail("%s (%lld)", msg, __LINE__); \
+  } while (0)
+
+// ---- h16 pair (hi + lo split) ---------------------------------------------------------
+__device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+
+__device__ __forceinline__ void split_h(float v, __half& hi, __half& lo) {
+  v = clamp_h(v);
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+__device__ __forceinline__ void store_pair(__half* hi, __half* lo, size_t i, float v) {
+  __half h, l;
+  split_h(v, h, l);
+  hi[i] = h;
+  if (lo) lo[i] = l;
+}
+__device__ __forceinline__ float load_pair(const __half* hi, const __half* lo, size_t i) {
+  float v = __half2float(hi[i]);
+  if (lo) v += __half2float(lo[i]);
+  return v;
+}
+// 8 consecutive values -> two 16-byte stores
+__device__ __forceinline__ void store_pair8(__half* hi, __half* lo, size_t i, const float* v) {
+  __align__(16) __half h[8];
+  __align__(16) __half l[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) split_h(v[j], h[j], l[j]);
+  *reinterpret_cast<uint4*>(hi + i) = *reinterpret_cast<const uint4*>(h);
+  if (lo) *reinterpret_cast<uint4*>(lo + i) = *reinterpret_cast<const uint4*>(l);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == CSAM_ACT_GELU) return gelu_erf(v);
+  if (act == CSAM_ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- PTX wrappers: mbarrier / TMA / tcgen05 -------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Spin on the phase parity; a watchdog turns a lost arrival into a trap instead of a hang.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+      printf("csam: mbarrier watchdog block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16, issued by ONE thread.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all tcgen05 ops previously issued by this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives lane (base+i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major or MN-major operand stored as rows of 128 bytes with
+// the 128B swizzle (what TMA SWIZZLE_128B writes): 8-row atoms of 1024 B, SBO = 1024.
+// (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+//  version=1 [46,48), layout_type [61,64) with SWIZZLE_128B = 2.)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor for kind::f16, fp16 A/B, fp32 accumulate (InstrDescriptor bit layout).
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4)                          // c_format = F32
+         | (0u << 7) | (0u << 10)           // a/b format = F16
+         | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16)
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- host: TMA descriptor creation through the driver entry point (no -lcuda at build time)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled();
+// 2-D fp16 tensor [rows, cols] with row stride ld (elements); box = [box_rows, box_cols]; 128B swizzle.
+int make_tmap_2d_f16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                     uint32_t box_rows, uint32_t box_cols);
+
+}  // namespace csam

@@ -1,0 +1,388 @@
+// gemm.cu — K-GEMM: out = epilogue(A[M,K] * W[N,K]^T) on the 5th-gen tensor cores.
+//
+// Persistent, warp-specialised sm_100a kernel:
+//   warp 0      TMA producer   (cp.async.bulk.tensor 2D, 128B swizzle, mbarrier complete_tx)
+//   warp 1      MMA issuer     (one lane issues tcgen05.mma kind::f16, accumulators in TMEM)
+//   warp 2      TMEM allocator
+//   warps 4..7  epilogue       (tcgen05.ld 32x32b -> bias/act/LayerScale/residual -> global)
+// Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
+// "h16 pair" operands (hi + lo) turn every k-step into 3 MMAs (hi*hi + lo*hi + hi*lo) for
+// fp32-level accuracy; with lo == NULL it is a plain single-pass fp16 GEMM.
+//
+// Replaces the nn.Linear / conv call sites listed in include/csam.h (K-GEMM).
+#include "common.cuh"
+
+namespace csam {
+
+struct GemmEpi {
+  int M, N;
+  const float* bias; const float* row_scale; const float* col_scale; int act;
+  const float* residual; int ldr; int res_mod;
+  const int* row_map;
+  float* out_f32; int ldo;
+  __half* out_hi; __half* out_lo; int ldh;
+  int vec_ok;   // all strides / bases allow 16-byte vector access
+};
+
+// v[0..NV) are the raw accumulators of row r, columns [c0, c0+NV)
+template <int NV>
+__device__ __forceinline__ void epi_store(const GemmEpi& e, int r, int c0, float* v) {
+  if (r >= e.M || c0 >= e.N) return;
+  const int orow = e.row_map ? e.row_map[r] : r;
+  if (orow < 0) return;
+  const float rs = e.row_scale ? e.row_scale[r] : 1.f;
+  const int rr = e.res_mod > 0 ? (orow % e.res_mod) : orow;
+  const bool full = (c0 + NV <= e.N) && e.vec_ok;
+  const float* res = e.residual ? e.residual + (size_t)rr * e.ldr : nullptr;
+  if (full) {
+#pragma unroll
+    for (int j = 0; j < NV; j += 4) {
+      float4 b = e.bias ? *reinterpret_cast<const float4*>(e.bias + c0 + j) : make_float4(0, 0, 0, 0);
+      float4 cs = e.col_scale ? *reinterpret_cast<const float4*>(e.col_scale + c0 + j) : make_float4(1, 1, 1, 1);
+      float4 rv = res ? *reinterpret_cast<const float4*>(res + c0 + j) : make_float4(0, 0, 0, 0);
+      v[j + 0] = apply_act(v[j + 0] * rs + b.x, e.act) * cs.x + rv.x;
+      v[j + 1] = apply_act(v[j + 1] * rs + b.y, e.act) * cs.y + rv.y;
+      v[j + 2] = apply_act(v[j + 2] * rs + b.z, e.act) * cs.z + rv.z;
+      v[j + 3] = apply_act(v[j + 3] * rs + b.w, e.act) * cs.w + rv.w;
+    }
+    if (e.out_f32) {
+      float* o = e.out_f32 + (size_t)orow * e.ldo + c0;
+#pragma unroll
+      for (int j = 0; j < NV; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    if (e.out_hi) {
+      const size_t base = (size_t)orow * e.ldh + c0;
+      if constexpr (NV % 8 == 0) {
+#pragma unroll
+        for (int j = 0; j < NV; j += 8) store_pair8(e.out_hi, e.out_lo, base + j, v + j);
+      } else {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) store_pair(e.out_hi, e.out_lo, base + j, v[j]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = c0 + j;
+      if (c < e.N) {
+        float x = v[j] * rs + (e.bias ? e.bias[c] : 0.f);
+        x = apply_act(x, e.act);
+        if (e.col_scale) x *= e.col_scale[c];
+        if (res) x += res[c];
+        if (e.out_f32) e.out_f32[(size_t)orow * e.ldo + c] = x;
+        if (e.out_hi) store_pair(e.out_hi, e.out_lo, (size_t)orow * e.ldh + c, x);
+      }
+    }
+  }
+}
+
+// =========================================================================================
+// tcgen05 kernel
+// =========================================================================================
+constexpr int BM = 128;
+constexpr int BK = 64;           // 64 fp16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+
+template <int BN, int SPLIT>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
+  static constexpr int W_BYTES = BN * BK * 2;
+  static constexpr int NOPS = (SPLIT == 3) ? 2 : 1;           // hi (+ lo) per operand
+  static constexpr int STAGE_BYTES = NOPS * (A_BYTES + W_BYTES);
+  static constexpr int STAGES = (SPLIT == 3) ? (BN >= 256 ? 2 : 3) : (BN >= 256 ? 4 : 6);
+  static constexpr int TMEM_COLS = 2 * BN;                    // two accumulator buffers
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, int SPLIT, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant__ CUtensorMap ta_lo,
+               const __grid_constant__ CUtensorMap tw_hi, const __grid_constant__ CUtensorMap tw_lo,
+               GemmEpi e, int K, int tiles_m, int tiles_n) {
+  using Cfg = GemmCfg<BN, SPLIT>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&ta_hi);
+    tma_prefetch_desc(&tw_hi);
+    if (SPLIT == 3) { tma_prefetch_desc(&ta_lo); tma_prefetch_desc(&tw_lo); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t % tiles_m) * BM;
+        const int n0 = (t / tiles_m) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sw = sa + Cfg::NOPS * Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const int k0 = kb * BK;
+          tma_load_2d(sa, &ta_hi, &full_bar[stage], k0, m0);
+          if (SPLIT == 3) tma_load_2d(sa + Cfg::A_BYTES, &ta_lo, &full_bar[stage], k0, m0);
+          if (!B_MN) {
+            tma_load_2d(sw, &tw_hi, &full_bar[stage], k0, n0);
+            if (SPLIT == 3) tma_load_2d(sw + Cfg::W_BYTES, &tw_lo, &full_bar[stage], k0, n0);
+          } else {
+            // W is [K,N] row-major: boxes of [64 k][64 n], one per 64-wide N atom
+#pragma unroll
+            for (int a = 0; a < BN / 64; ++a) {
+              tma_load_2d(sw + a * 8192, &tw_hi, &full_bar[stage], n0 + a * 64, k0);
+              if (SPLIT == 3) tma_load_2d(sw + Cfg::W_BYTES + a * 8192, &tw_lo, &full_bar[stage], n0 + a * 64, k0);
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, B_MN ? 1 : 0);
+      int stage = 0; uint32_t phase = 0;
+      int local = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
+        const int buf = local & 1;
+        const uint32_t bphase = (local >> 1) & 1;
+        mbar_wait(&tempty_bar[buf], bphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sw = sa + Cfg::NOPS * Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t a_hi = umma_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t w_hi = B_MN ? umma_desc_sw128(sw + k * 2048, 8192, 1024)
+                                       : umma_desc_sw128(sw + k * 32, 16, 1024);
+            umma_f16(d_addr, a_hi, w_hi, idesc, (kb | k) ? 1u : 0u);
+            if (SPLIT == 3) {
+              const uint64_t a_lo = umma_desc_sw128(sa + Cfg::A_BYTES + k * 32, 16, 1024);
+              const uint64_t w_lo = B_MN ? umma_desc_sw128(sw + Cfg::W_BYTES + k * 2048, 8192, 1024)
+                                         : umma_desc_sw128(sw + Cfg::W_BYTES + k * 32, 16, 1024);
+              umma_f16(d_addr, a_lo, w_hi, idesc, 1u);
+              umma_f16(d_addr, a_hi, w_lo, idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);            // smem slot reusable once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[buf]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp - 4;                      // TMEM lane quadrant == warp % 4
+    int local = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
+      const int buf = local & 1;
+      const uint32_t bphase = (local >> 1) & 1;
+      const int m0 = (t % tiles_m) * BM;
+      const int n0 = (t / tiles_m) * BN;
+      mbar_wait(&tfull_bar[buf], bphase);
+      tc_fence_after();
+      const int r = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c, raw);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        epi_store<32>(e, r, n0 + c, v);
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// =========================================================================================
+// SIMT validation kernel (same operands, same epilogue); slow, used to cross-check tcgen05.
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo,
+                 int K, int lda, int ldw, int b_mn, GemmEpi e) {
+  __shared__ float sa[16][64 + 1];
+  __shared__ float sw[16][64 + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int kk = i & 15, rr = i >> 4;
+      const int k = k0 + kk;
+      float av = 0.f, wv = 0.f;
+      if (k < K) {
+        if (m0 + rr < e.M) av = load_pair(a_hi, a_lo, (size_t)(m0 + rr) * lda + k);
+        if (n0 + rr < e.N) wv = b_mn ? load_pair(w_hi, w_lo, (size_t)k * ldw + n0 + rr)
+                                      : load_pair(w_hi, w_lo, (size_t)(n0 + rr) * ldw + k);
+      }
+      sa[kk][rr] = av;
+      sw[kk][rr] = wv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sa[kk][ty * 4 + i]; w[i] = sw[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) epi_store<4>(e, m0 + ty * 4 + i, n0 + tx * 4, acc[i]);
+}
+
+// =========================================================================================
+// host
+// =========================================================================================
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_2d_f16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                     uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return fail("%s", "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed %s(%lld)", "", (long long)r);
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, int SPLIT, bool B_MN>
+static int launch_tc(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, SPLIT>;
+  CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+  if (make_tmap_2d_f16(&ta_hi, a->a_hi, a->M, a->K, a->lda, BM, BK)) return 1;
+  ta_lo = ta_hi;
+  if (SPLIT == 3 && make_tmap_2d_f16(&ta_lo, a->a_lo, a->M, a->K, a->lda, BM, BK)) return 1;
+  if (!B_MN) {
+    if (make_tmap_2d_f16(&tw_hi, a->w_hi, a->N, a->K, a->ldw, BN, BK)) return 1;
+    tw_lo = tw_hi;
+    if (SPLIT == 3 && make_tmap_2d_f16(&tw_lo, a->w_lo, a->N, a->K, a->ldw, BN, BK)) return 1;
+  } else {
+    if (make_tmap_2d_f16(&tw_hi, a->w_hi, a->K, a->N, a->ldw, BK, 64)) return 1;
+    tw_lo = tw_hi;
+    if (SPLIT == 3 && make_tmap_2d_f16(&tw_lo, a->w_lo, a->K, a->N, a->ldw, BK, 64)) return 1;
+  }
+  auto kern = gemm_tc_kernel<BN, SPLIT, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+      return fail("%s", "cudaFuncSetAttribute(smem) failed for gemm_tc_kernel");
+    attr_set = true;
+  }
+  const int tiles_m = (a->M + BM - 1) / BM;
+  const int tiles_n = (a->N + BN - 1) / BN;
+  const int grid = min(tiles_m * tiles_n, num_sms());
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, e, a->K, tiles_m, tiles_n);
+  return check_launch("gemm_tc_kernel");
+}
+
+}  // namespace csam
+
+using namespace csam;
+
+extern "C" int csam_gemm(const csam_gemm_args* a, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CSAM_REQUIRE(a && a->a_hi && a->w_hi, "csam_gemm: null operand");
+  CSAM_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "csam_gemm: empty problem");
+  CSAM_REQUIRE((a->a_lo == nullptr) == (a->w_lo == nullptr), "csam_gemm: both operands must be split or neither");
+  CSAM_REQUIRE(a->out_f32 || a->out_hi, "csam_gemm: no output");
+  GemmEpi e;
+  e.M = a->M; e.N = a->N;
+  e.bias = a->bias; e.row_scale = a->row_scale; e.col_scale = a->col_scale; e.act = a->act;
+  e.residual = a->residual; e.ldr = a->ldr; e.res_mod = a->res_mod; e.row_map = a->row_map;
+  e.out_f32 = a->out_f32; e.ldo = a->ldo;
+  e.out_hi = static_cast<__half*>(a->out_hi); e.out_lo = static_cast<__half*>(a->out_lo); e.ldh = a->ldh;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  e.vec_ok = 1;
+  if (a->bias && !al16(a->bias)) e.vec_ok = 0;
+  if (a->col_scale && !al16(a->col_scale)) e.vec_ok = 0;
+  if (a->residual && (!al16(a->residual) || (a->ldr & 3))) e.vec_ok = 0;
+  if (a->out_f32 && (!al16(a->out_f32) || (a->ldo & 3))) e.vec_ok = 0;
+  if (a->out_hi && (!al16(a->out_hi) || (a->ldh & 7) || (a->out_lo && !al16(a->out_lo)))) e.vec_ok = 0;
+
+  if (a->impl == CSAM_GEMM_SIMT) {
+    dim3 grid((a->M + 63) / 64, (a->N + 63) / 64);
+    gemm_simt_kernel<<<grid, 256, 0, st>>>(static_cast<const __half*>(a->a_hi), static_cast<const __half*>(a->a_lo),
+                                           static_cast<const __half*>(a->w_hi), static_cast<const __half*>(a->w_lo),
+                                           a->K, a->lda, a->ldw, a->b_mn_major, e);
+    return check_launch("gemm_simt_kernel");
+  }
+  // TMA constraints: 16-byte aligned bases and row strides
+  CSAM_REQUIRE(al16(a->a_hi) && al16(a->w_hi) && (!a->a_lo || (al16(a->a_lo) && al16(a->w_lo))),
+               "csam_gemm: operands must be 16-byte aligned");
+  CSAM_REQUIRE((a->lda % 8) == 0 && (a->ldw % 8) == 0, "csam_gemm: lda/ldw must be multiples of 8");
+  const bool split = a->a_lo != nullptr;
+  const bool small_n = a->N <= 64;
+  if (a->b_mn_major) {
+    CSAM_REQUIRE(!small_n, "csam_gemm: b_mn_major needs N > 64");
+    return split ? launch_tc<128, 3, true>(a, e, st) : launch_tc<128, 1, true>(a, e, st);
+  }
+  if (small_n) return split ? launch_tc<64, 3, false>(a, e, st) : launch_tc<64, 1, false>(a, e, st);
+  return split ? launch_tc<128, 3, false>(a, e, st) : launch_tc<128, 1, false>(a, e, st);
+}

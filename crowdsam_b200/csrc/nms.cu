@@ -1,0 +1,265 @@
+// nms.cu — K-NMS (bit-exact torchvision.ops.nms), K-MIOU, EPS occupancy test, RLE encoding.
+// Call sites replaced: model.py:171-176,257-263,429-434 (batched_nms with all-zero category ids,
+// so the coordinate offset trick is a no-op), crowdsam/utils.py:422-479 (mask overlap, dead code),
+// model.py:229-246 (occupancy), amg.py:107-135 (RLE).
+#include "common.cuh"
+
+namespace csam {
+
+// stable descending order by rank counting: rank_i = #{j : s_j > s_i or (s_j == s_i and j < i)}
+__global__ void nms_rank_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, int n,
+                                int* __restrict__ order, float4* __restrict__ sorted) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float sh[256];
+  const float si = i < n ? scores[i] : 0.f;
+  int rank = 0;
+  for (int j0 = 0; j0 < n; j0 += 256) {
+    __syncthreads();
+    if (j0 + threadIdx.x < n) sh[threadIdx.x] = scores[j0 + threadIdx.x];
+    __syncthreads();
+    const int lim = min(256, n - j0);
+    for (int t = 0; t < lim; ++t) {
+      const float sj = sh[t];
+      rank += (sj > si) || (sj == si && (j0 + t) < i);
+    }
+  }
+  if (i < n) {
+    order[rank] = i;
+    sorted[rank] = make_float4(boxes[i * 4 + 0], boxes[i * 4 + 1], boxes[i * 4 + 2], boxes[i * 4 + 3]);
+  }
+}
+
+// torchvision arithmetic, no FMA contraction anywhere (explicit round-to-nearest ops)
+__device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr) {
+  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  const float w = fmaxf(__fsub_rn(right, left), 0.f), h = fmaxf(__fsub_rn(bottom, top), 0.f);
+  const float inter = __fmul_rn(w, h);
+  const float sa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  const float sb = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter)) > thr;   // NaN compares false
+}
+
+// mask[i][w] bit b set <=> sorted box j = 64 w + b (j > i) overlaps sorted box i above thr
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__ sorted, int n, float thr,
+                                                      unsigned long long* __restrict__ mask, int nw) {
+  const int rb = blockIdx.y, cb = blockIdx.x;
+  if (cb < rb) return;   // only the upper triangle is ever read
+  __shared__ float4 cbx[64];
+  const int j = cb * 64 + threadIdx.x;
+  if (j < n) cbx[threadIdx.x] = sorted[j];
+  __syncthreads();
+  const int i = rb * 64 + threadIdx.x;
+  if (i >= n) return;
+  const float4 bi = sorted[i];
+  unsigned long long bits = 0;
+  const int lim = min(64, n - cb * 64);
+  const int start = (rb == cb) ? threadIdx.x + 1 : 0;
+  for (int t = start; t < lim; ++t)
+    if (iou_gt(bi, cbx[t], thr)) bits |= 1ULL << t;
+  mask[(size_t)i * nw + cb] = bits;
+}
+
+// greedy scan in sorted order (one block; thread w owns word w of the removed bitmap)
+__global__ void nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ order, int n, int nw,
+                                int* __restrict__ keep, int* __restrict__ n_keep) {
+  extern __shared__ unsigned long long remv[];
+  __shared__ int s_cnt;
+  for (int w = threadIdx.x; w < nw; w += blockDim.x) remv[w] = 0;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  for (int i = 0; i < n; ++i) {
+    const int wi = i >> 6, bi = i & 63;
+    const bool alive = !((remv[wi] >> bi) & 1ULL);
+    __syncthreads();
+    if (alive) {
+      if (threadIdx.x == 0) keep[s_cnt++] = order[i];
+      for (int w = wi + threadIdx.x; w < nw; w += blockDim.x) remv[w] |= mask[(size_t)i * nw + w];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_keep = s_cnt;
+}
+
+// ---- K-MIOU ------------------------------------------------------------------------------------
+constexpr int MO_SIDE = 150, MO_BITS = MO_SIDE * MO_SIDE, MO_WORDS = (MO_BITS + 31) / 32;   // 704
+
+__global__ void mo_pack_kernel(const uint8_t* __restrict__ masks, int h, int w, uint32_t* __restrict__ packed) {
+  const int i = blockIdx.y;
+  const int word = blockIdx.x * blockDim.x + threadIdx.x;
+  if (word >= MO_WORDS) return;
+  const float sh = (float)h / MO_SIDE, sw = (float)w / MO_SIDE;   // F.interpolate nearest (utils.py:431)
+  uint32_t bits = 0;
+  for (int b = 0; b < 32; ++b) {
+    const int t = word * 32 + b;
+    if (t < MO_BITS) {
+      const int y = min((int)floorf((t / MO_SIDE) * sh), h - 1), x = min((int)floorf((t % MO_SIDE) * sw), w - 1);
+      if (masks[((size_t)i * h + y) * w + x]) bits |= 1u << b;
+    }
+  }
+  packed[(size_t)i * MO_WORDS + word] = bits;
+}
+__global__ void mo_inter_kernel(const uint32_t* __restrict__ packed, int n, int* __restrict__ inter, int* __restrict__ area) {
+  const int i = blockIdx.y, j = blockIdx.x;   // one warp per pair
+  const uint32_t* a = packed + (size_t)i * MO_WORDS;
+  const uint32_t* b = packed + (size_t)j * MO_WORDS;
+  int c = 0;
+  for (int w = threadIdx.x; w < MO_WORDS; w += 32) c += __popc(a[w] & b[w]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (threadIdx.x == 0) {
+    inter[(size_t)i * n + j] = c;
+    if (i == j) area[i] = c;
+  }
+}
+
+// ---- EPS occupancy ------------------------------------------------------------------------------
+__global__ void points_occupied_kernel(const uint8_t* __restrict__ masks, int n_masks, int h, int w,
+                                       const uint8_t* __restrict__ flag, const int* __restrict__ pts, int n_pts,
+                                       uint8_t* __restrict__ occ) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pts) return;
+  const int x = pts[i * 2], y = pts[i * 2 + 1];
+  uint8_t o = 0;
+  if (x >= 0 && x < w && y >= 0 && y < h)
+    for (int m = 0; m < n_masks && !o; ++m)
+      if (flag[m] && masks[((size_t)m * h + y) * w + x]) o = 1;
+  occ[i] = o;
+}
+
+// ---- RLE (column-major) -----------------------------------------------------------------------
+// element t of the Fortran-order flattening is mask[t % h][t / h]
+__device__ __forceinline__ uint8_t fval(const uint8_t* m, int h, int w, int t) { return m[(size_t)(t % h) * w + t / h]; }
+
+// changes[t] (t >= 1) = flat[t] != flat[t-1]; block handles one mask; thread handles a contiguous chunk
+__global__ void __launch_bounds__(1024) rle_kernel(const uint8_t* __restrict__ masks, int h, int w,
+                                                   const long long* __restrict__ offsets, int* __restrict__ runs,
+                                                   int* __restrict__ n_runs) {
+  __shared__ int s_cnt[1024];
+  const uint8_t* m = masks + (size_t)blockIdx.x * h * w;
+  const int total = h * w;
+  const int chunk = (total + 1023) / 1024;
+  const int t0 = threadIdx.x * chunk, t1 = min(t0 + chunk, total);
+  int cnt = 0;
+  if (t0 < t1) {
+    uint8_t prev = t0 > 0 ? fval(m, h, w, t0 - 1) : fval(m, h, w, 0);
+    for (int t = t0; t < t1; ++t) {
+      const uint8_t v = fval(m, h, w, t);
+      cnt += (v != prev);
+      prev = v;
+    }
+  }
+  s_cnt[threadIdx.x] = cnt;
+  __syncthreads();
+  // exclusive scan (Hillis-Steele on 1024 entries)
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = threadIdx.x >= o ? s_cnt[threadIdx.x - o] : 0;
+    __syncthreads();
+    s_cnt[threadIdx.x] += v;
+    __syncthreads();
+  }
+  const int changes = s_cnt[1023];
+  const int first_one = m[0] ? 1 : 0;              // counts start with the number of zeros
+  const int nr = changes + 1 + first_one;
+  if (!runs) {                                     // counting pass
+    if (threadIdx.x == 0) n_runs[blockIdx.x] = nr;
+    return;
+  }
+  // second pass: write change positions, then turn them into run lengths in place
+  int* out = runs + offsets[blockIdx.x];
+  int k = s_cnt[threadIdx.x] - cnt + first_one;    // index of this thread's first change position
+  if (threadIdx.x == 0 && first_one) out[0] = 0;
+  if (t0 < t1) {
+    uint8_t prev = t0 > 0 ? fval(m, h, w, t0 - 1) : fval(m, h, w, 0);
+    for (int t = t0; t < t1; ++t) {
+      const uint8_t v = fval(m, h, w, t);
+      if (v != prev) out[k++ + 1] = t;             // slot j+1 holds the start of run j+1
+      prev = v;
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  // out[first_one + 1 + c] = position of change c; run lengths = successive differences
+  // work backwards-safe: each thread computes its lengths into registers first
+  const int base = first_one;                      // runs[base + r] for r = 0..changes
+  for (int r0 = 0; r0 <= changes; r0 += 1024) {
+    const int r = r0 + threadIdx.x;
+    int len = 0;
+    if (r <= changes) {
+      const int start = r == 0 ? 0 : out[base + r];
+      const int end = r == changes ? total : out[base + r + 1];
+      len = end - start;
+    }
+    __syncthreads();
+    if (r <= changes) out[base + r] = len;
+    __syncthreads();
+  }
+}
+
+}  // namespace csam
+
+using namespace csam;
+
+extern "C" long long csam_box_nms_scratch_bytes(int n) {
+  const long long nw = (n + 63) / 64;
+  return (long long)n * 4 + (long long)n * 16 + (long long)n * nw * 8 + 256;
+}
+
+extern "C" int csam_box_nms(const float* boxes, const float* scores, int n, float thr, int* keep_out, int* n_keep,
+                            void* scratch, long long scratch_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  CSAM_REQUIRE(keep_out && n_keep && n >= 0, "csam_box_nms: bad args");
+  if (n == 0) {
+    cudaMemsetAsync(n_keep, 0, sizeof(int), st);
+    return 0;
+  }
+  CSAM_REQUIRE(boxes && scores && scratch && scratch_bytes >= csam_box_nms_scratch_bytes(n), "csam_box_nms: scratch too small");
+  CSAM_REQUIRE(n <= 65536, "csam_box_nms: n <= 65536");
+  const int nw = (n + 63) / 64;
+  uint8_t* s = static_cast<uint8_t*>(scratch);
+  float4* sorted = reinterpret_cast<float4*>(s);                                  // 16-byte aligned first
+  unsigned long long* mask = reinterpret_cast<unsigned long long*>(s + (size_t)n * 16);
+  int* order = reinterpret_cast<int*>(s + (size_t)n * 16 + (size_t)n * nw * 8);
+  nms_rank_kernel<<<(n + 255) / 256, 256, 0, st>>>(scores, boxes, n, order, sorted);
+  if (check_launch("nms_rank_kernel")) return 1;
+  nms_mask_kernel<<<dim3(nw, nw), 64, 0, st>>>(sorted, n, thr, mask, nw);
+  if (check_launch("nms_mask_kernel")) return 1;
+  const int threads = min(1024, ((nw + 31) / 32) * 32);
+  nms_scan_kernel<<<1, threads, nw * sizeof(unsigned long long), st>>>(mask, order, n, nw, keep_out, n_keep);
+  return check_launch("nms_scan_kernel");
+}
+
+extern "C" long long csam_mask_overlap_scratch_bytes(int n) { return (long long)n * MO_WORDS * 4; }
+
+extern "C" int csam_mask_overlap(const uint8_t* masks, int n, int h, int w, int* inter, int* area, void* scratch,
+                                 long long scratch_bytes, void* stream) {
+  CSAM_REQUIRE(masks && inter && area && n > 0 && n <= 65535, "csam_mask_overlap: bad args");
+  CSAM_REQUIRE(scratch && scratch_bytes >= csam_mask_overlap_scratch_bytes(n), "csam_mask_overlap: scratch too small");
+  uint32_t* packed = static_cast<uint32_t*>(scratch);
+  mo_pack_kernel<<<dim3((MO_WORDS + 127) / 128, n), 128, 0, (cudaStream_t)stream>>>(masks, h, w, packed);
+  if (check_launch("mo_pack_kernel")) return 1;
+  mo_inter_kernel<<<dim3(n, n), 32, 0, (cudaStream_t)stream>>>(packed, n, inter, area);
+  return check_launch("mo_inter_kernel");
+}
+
+extern "C" int csam_points_occupied(const uint8_t* masks, int n_masks, int h, int w, const uint8_t* flag,
+                                    const int* pts_xy, int n_pts, uint8_t* occ, void* stream) {
+  CSAM_REQUIRE(occ && n_pts >= 0, "csam_points_occupied: bad args");
+  if (n_pts == 0) return 0;
+  CSAM_REQUIRE(pts_xy && (n_masks == 0 || (masks && flag)), "csam_points_occupied: bad args");
+  points_occupied_kernel<<<(n_pts + 127) / 128, 128, 0, (cudaStream_t)stream>>>(masks, n_masks, h, w, flag, pts_xy, n_pts, occ);
+  return check_launch("points_occupied_kernel");
+}
+
+extern "C" int csam_rle_count(const uint8_t* masks, int n, int h, int w, int* n_runs, void* stream) {
+  CSAM_REQUIRE(masks && n_runs && n > 0 && h > 0 && w > 0, "csam_rle_count: bad args");
+  rle_kernel<<<n, 1024, 0, (cudaStream_t)stream>>>(masks, h, w, nullptr, nullptr, n_runs);
+  return check_launch("rle_kernel(count)");
+}
+
+extern "C" int csam_rle_fill(const uint8_t* masks, int n, int h, int w, const long long* offsets, int* runs,
+                             void* stream) {
+  CSAM_REQUIRE(masks && offsets && runs && n > 0 && h > 0 && w > 0, "csam_rle_fill: bad args");
+  rle_kernel<<<n, 1024, 0, (cudaStream_t)stream>>>(masks, h, w, offsets, runs, nullptr);
+  return check_launch("rle_kernel(fill)");
+}

@@ -1,0 +1,172 @@
+// post.cu — K-POST: per-prompt mask upsample + threshold + stability counts + box (HBM-bound).
+// Replaces sam.py:132-161 (two bilinear resizes), model.py:372-384, amg.py:156-176 (stability),
+// amg.py:303-346 (boxes).  The reference materialises [P,4,H,W] fp32 twice (~95 MB / prompt);
+// here the logits are re-evaluated on the fly from the selected 256x256 plane (256 KB, L2
+// resident) and only the bool mask (1 B / pixel) of surviving prompts is written.
+#include "common.cuh"
+#include <limits.h>
+
+namespace csam {
+
+struct PostGeom {
+  int in_h, in_w, out_h, out_w;
+  int identity;          // stage-2 resize is the identity (always true on the CrowdSAM path)
+  float s2h, s2w;        // in/out scales of stage 2 (ATen: float(in)/out)
+};
+
+// stage 1: 256 -> 1024, align_corners=False (scale 0.25)
+__device__ __forceinline__ void coord256(int d, int& i0, int& i1, float& l1) {
+  const float s = fmaxf(0.25f * (d + 0.5f) - 0.5f, 0.f);
+  i0 = (int)s;
+  i1 = i0 + (i0 < 255 ? 1 : 0);
+  l1 = s - i0;
+}
+__device__ __forceinline__ float stage1(const float* __restrict__ L, int y, int x) {
+  int y0, y1, x0, x1; float ly, lx;
+  coord256(y, y0, y1, ly);
+  coord256(x, x0, x1, lx);
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  return hy * (hx * L[y0 * 256 + x0] + lx * L[y0 * 256 + x1]) + ly * (hx * L[y1 * 256 + x0] + lx * L[y1 * 256 + x1]);
+}
+__device__ __forceinline__ float eval_logit(const float* __restrict__ L, const PostGeom& g, int Y, int X) {
+  if (g.identity) return stage1(L, Y, X);
+  // stage 2: crop to (in_h,in_w) then bilinear to (out_h,out_w)
+  float sy = fmaxf(g.s2h * (Y + 0.5f) - 0.5f, 0.f), sx = fmaxf(g.s2w * (X + 0.5f) - 0.5f, 0.f);
+  const int y0 = min((int)sy, g.in_h - 1), x0 = min((int)sx, g.in_w - 1);
+  const int y1 = y0 + (y0 < g.in_h - 1 ? 1 : 0), x1 = x0 + (x0 < g.in_w - 1 ? 1 : 0);
+  const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+  return hy * (hx * stage1(L, y0, x0) + lx * stage1(L, y0, x1)) + ly * (hx * stage1(L, y1, x0) + lx * stage1(L, y1, x1));
+}
+
+__device__ __forceinline__ const float* plane_of(const csam_post_args& a, int p) {
+  const int l = a.sel ? a.sel[p] : 0;
+  return a.low + ((size_t)p * a.planes + l) * 65536;
+}
+
+constexpr int POST_ROWS = 8;   // output rows per block
+
+__global__ void post_init_kernel(int* counts, int* boxes, int P) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  counts[p * 3 + 0] = counts[p * 3 + 1] = counts[p * 3 + 2] = 0;
+  boxes[p * 4 + 0] = INT_MAX; boxes[p * 4 + 1] = INT_MAX; boxes[p * 4 + 2] = -1; boxes[p * 4 + 3] = -1;
+}
+__global__ void post_finalize_kernel(int* boxes, int P) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  // amg.py:333-338: empty mask (right < left or bottom < top) -> [0,0,0,0]
+  if (boxes[p * 4 + 2] < boxes[p * 4 + 0] || boxes[p * 4 + 3] < boxes[p * 4 + 1]) {
+    boxes[p * 4 + 0] = boxes[p * 4 + 1] = boxes[p * 4 + 2] = boxes[p * 4 + 3] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) post_stats_kernel(csam_post_args a, PostGeom g) {
+  const int p = blockIdx.y;
+  const float* L = plane_of(a, p);
+  const int y_begin = blockIdx.x * POST_ROWS;
+  const int y_end = min(y_begin + POST_ROWS, g.out_h);
+  const float t_hi = a.thr + a.off, t_lo = a.thr - a.off;
+  int c_hi = 0, c_lo = 0, c_mid = 0;
+  int xmin = INT_MAX, xmax = -1, ymin = INT_MAX, ymax = -1;
+  const int n = (y_end - y_begin) * g.out_w;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int Y = y_begin + i / g.out_w, X = i % g.out_w;
+    const float v = eval_logit(L, g, Y, X);
+    c_hi += v > t_hi;
+    c_lo += v > t_lo;
+    if (v > a.thr) {
+      ++c_mid;
+      xmin = min(xmin, X); xmax = max(xmax, X); ymin = min(ymin, Y); ymax = max(ymax, Y);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    c_hi += __shfl_xor_sync(0xffffffffu, c_hi, o);
+    c_lo += __shfl_xor_sync(0xffffffffu, c_lo, o);
+    c_mid += __shfl_xor_sync(0xffffffffu, c_mid, o);
+    xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+    ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+    xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+    ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (c_hi) atomicAdd(&a.counts[p * 3 + 0], c_hi);
+    if (c_lo) atomicAdd(&a.counts[p * 3 + 1], c_lo);
+    if (c_mid) {
+      atomicAdd(&a.counts[p * 3 + 2], c_mid);
+      atomicMin(&a.boxes[p * 4 + 0], xmin); atomicMin(&a.boxes[p * 4 + 1], ymin);
+      atomicMax(&a.boxes[p * 4 + 2], xmax); atomicMax(&a.boxes[p * 4 + 3], ymax);
+    }
+  }
+}
+
+// one thread = 16 consecutive output pixels of one row -> one 16-byte store
+__global__ void __launch_bounds__(256) post_write_kernel(csam_post_args a, PostGeom g, int segs_per_row) {
+  const int i = blockIdx.y;
+  const int p = a.keep ? a.keep[i] : i;
+  const float* L = plane_of(a, p);
+  const int total = g.out_h * segs_per_row;
+  uint8_t* mo = a.masks ? a.masks + (size_t)i * g.out_h * g.out_w : nullptr;
+  float* lo = a.logits ? a.logits + (size_t)i * g.out_h * g.out_w : nullptr;
+  const bool vec = (g.out_w & 15) == 0;
+  for (int s = blockIdx.x * 256 + threadIdx.x; s < total; s += gridDim.x * 256) {
+    const int Y = s / segs_per_row, X0 = (s % segs_per_row) * 16;
+    const int nx = min(16, g.out_w - X0);
+    __align__(16) uint8_t b[16];
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      v[j] = (j < nx) ? eval_logit(L, g, Y, X0 + j) : 0.f;
+      b[j] = v[j] > a.thr ? 1 : 0;
+    }
+    const size_t o = (size_t)Y * g.out_w + X0;
+    if (mo) {
+      if (vec) *reinterpret_cast<uint4*>(mo + o) = *reinterpret_cast<const uint4*>(b);
+      else for (int j = 0; j < nx; ++j) mo[o + j] = b[j];
+    }
+    if (lo) for (int j = 0; j < nx; ++j) lo[o + j] = v[j];
+  }
+}
+
+static int make_geom(const csam_post_args* a, PostGeom& g) {
+  CSAM_REQUIRE(a && a->low && a->P > 0, "csam_mask_post: bad args");
+  CSAM_REQUIRE(a->in_h > 0 && a->in_h <= 1024 && a->in_w > 0 && a->in_w <= 1024 && a->out_h > 0 && a->out_w > 0,
+               "csam_mask_post: bad sizes");
+  CSAM_REQUIRE(a->planes == 4 || (a->planes == 1 && !a->sel), "csam_mask_post: planes must be 4 (with sel) or 1");
+  g.in_h = a->in_h; g.in_w = a->in_w; g.out_h = a->out_h; g.out_w = a->out_w;
+  g.identity = (a->in_h == a->out_h && a->in_w == a->out_w);
+  g.s2h = (float)a->in_h / (float)a->out_h;
+  g.s2w = (float)a->in_w / (float)a->out_w;
+  return 0;
+}
+
+}  // namespace csam
+
+using namespace csam;
+
+extern "C" int csam_mask_post_stats(const csam_post_args* a, void* stream) {
+  PostGeom g;
+  if (make_geom(a, g)) return 1;
+  CSAM_REQUIRE(a->counts && a->boxes && a->P <= 65535, "csam_mask_post_stats: need counts/boxes, P <= 65535");
+  cudaStream_t st = (cudaStream_t)stream;
+  post_init_kernel<<<(a->P + 255) / 256, 256, 0, st>>>(a->counts, a->boxes, a->P);
+  if (check_launch("post_init_kernel")) return 1;
+  dim3 grid((g.out_h + POST_ROWS - 1) / POST_ROWS, a->P);
+  post_stats_kernel<<<grid, 256, 0, st>>>(*a, g);
+  if (check_launch("post_stats_kernel")) return 1;
+  post_finalize_kernel<<<(a->P + 255) / 256, 256, 0, st>>>(a->boxes, a->P);
+  return check_launch("post_finalize_kernel");
+}
+
+extern "C" int csam_mask_post_write(const csam_post_args* a, void* stream) {
+  PostGeom g;
+  if (make_geom(a, g)) return 1;
+  const int n = a->keep ? a->n_keep : a->P;
+  if (n == 0) return 0;
+  CSAM_REQUIRE((a->masks || a->logits) && n > 0 && n <= 65535, "csam_mask_post_write: need an output, n <= 65535");
+  const int segs = (g.out_w + 15) / 16;
+  const int total = g.out_h * segs;
+  dim3 grid(min((total + 255) / 256, 64), n);
+  post_write_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a, g, segs);
+  return check_launch("post_write_kernel");
+}

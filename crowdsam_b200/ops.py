@@ -1,0 +1,350 @@
+"""Torch-tensor front end of the C-ABI kernels.  PyTorch is used here for device memory and
+streams only; every computation is a libcsam_sm100 kernel."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+from . import lib as L
+
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+
+# GEMM / attention implementation switches (validation only): 0 = tcgen05, 1 = SIMT
+GEMM_IMPL = int(os.environ.get("CSAM_GEMM_IMPL", "0"))
+ATTN_IMPL = int(os.environ.get("CSAM_ATTN_IMPL", "1"))   # tcgen05 attention pending
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class H16:
+    """fp16 hi (+ optional lo) pair: value = hi + lo (see include/csam.h)."""
+
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi: torch.Tensor, lo: Optional[torch.Tensor]):
+        self.hi, self.lo = hi, lo
+
+    @staticmethod
+    def empty(shape, split: bool, device="cuda") -> "H16":
+        hi = torch.empty(shape, dtype=torch.float16, device=device)
+        lo = torch.empty(shape, dtype=torch.float16, device=device) if split else None
+        return H16(hi, lo)
+
+    @staticmethod
+    def from_f32(t: torch.Tensor, split: bool) -> "H16":
+        """Weight preparation at load time (host-side plumbing, not on the hot path)."""
+        t = t.detach().float().clamp(-65504.0, 65504.0)
+        hi = t.half()
+        lo = (t - hi.float()).half() if split else None
+        return H16(hi.contiguous(), None if lo is None else lo.contiguous())
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    def view(self, *shape) -> "H16":
+        return H16(self.hi.view(*shape), None if self.lo is None else self.lo.view(*shape))
+
+    def rows(self, a: int, b: int) -> "H16":
+        return H16(self.hi[a:b], None if self.lo is None else self.lo[a:b])
+
+    def float(self) -> torch.Tensor:
+        return self.hi.float() if self.lo is None else self.hi.float() + self.lo.float()
+
+
+def gemm(a: H16, w: H16, *, bias=None, act=ACT_NONE, residual=None, res_mod=0, row_map=None,
+         row_scale=None, col_scale=None, out_f32=None, out_h16: Optional[H16] = None,
+         want_f32=False, want_h16=False, impl=None, b_mn_major=False, M=None):
+    """out = epilogue(a[M,K] @ w[N,K]^T); returns (fp32 or None, H16 or None)."""
+    assert a.hi.dim() == 2 and w.hi.dim() == 2
+    M = a.hi.shape[0] if M is None else M
+    K = a.hi.shape[1]
+    N = w.hi.shape[1] if b_mn_major else w.hi.shape[0]
+    split = a.lo is not None and w.lo is not None
+    dev = a.hi.device
+    if row_map is not None:
+        assert not (want_f32 and out_f32 is None) and not (want_h16 and out_h16 is None), \
+            "row_map GEMMs need caller-provided outputs"
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty((M, N), dtype=torch.float32, device=dev)
+    if want_h16 and out_h16 is None:
+        out_h16 = H16.empty((M, N), a.lo is not None, dev)
+    g = L.GemmArgs()
+    g.a_hi, g.a_lo = _p(a.hi), _p(a.lo if split else None)
+    g.w_hi, g.w_lo = _p(w.hi), _p(w.lo if split else None)
+    g.M, g.N, g.K = M, N, K
+    g.lda, g.ldw = a.hi.stride(0), w.hi.stride(0)
+    g.bias, g.row_scale, g.col_scale, g.act = _p(bias), _p(row_scale), _p(col_scale), act
+    g.residual, g.ldr, g.res_mod = _p(residual), (residual.stride(0) if residual is not None else 0), res_mod
+    g.row_map = _p(row_map)
+    g.out_f32, g.ldo = _p(out_f32), (out_f32.stride(0) if out_f32 is not None else 0)
+    if out_h16 is not None:
+        g.out_hi, g.out_lo, g.ldh = _p(out_h16.hi), _p(out_h16.lo), out_h16.hi.stride(0)
+    g.impl = GEMM_IMPL if impl is None else impl
+    g.b_mn_major = 1 if b_mn_major else 0
+    L.check(L.load().csam_gemm(C.byref(g), _stream()), "csam_gemm")
+    return out_f32, out_h16
+
+
+def patchify(img_u8_chw: torch.Tensor, patch: int, n_side: int, resize_to: int, kpad: int, split: bool) -> H16:
+    _, h, w = img_u8_chw.shape
+    out = H16.empty((n_side * n_side, kpad), split, img_u8_chw.device)
+    L.check(L.load().csam_patchify(_p(img_u8_chw), h, w, patch, n_side, resize_to, _p(out.hi), _p(out.lo), kpad,
+                                   _stream()), "csam_patchify")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma=None, beta=None, eps=1e-6, *, add=None, add_mod=0, row_map=None,
+              rows_out=None, normalize=True, out_f32=None, want_f32=False, out_h16: Optional[H16] = None,
+              want_h16=False, split=False, pe=None, pe_mod=0, out2: Optional[H16] = None, want_out2=False,
+              act=ACT_NONE):
+    assert x.dim() == 2 and x.dtype == torch.float32
+    rows_in, cols = x.shape
+    rows_out = (rows_in if row_map is None else row_map.numel()) if rows_out is None else rows_out
+    dev = x.device
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty((rows_out, cols), dtype=torch.float32, device=dev)
+    if want_h16 and out_h16 is None:
+        out_h16 = H16.empty((rows_out, cols), split, dev)
+    if want_out2 and out2 is None:
+        out2 = H16.empty((rows_out, cols), split, dev)
+    a = L.LnArgs()
+    a.x, a.ldx, a.rows_in = _p(x), x.stride(0), rows_in
+    a.add, a.ldadd, a.add_mod = _p(add), (add.stride(0) if add is not None else 0), add_mod
+    a.row_map, a.rows_out, a.cols = _p(row_map), rows_out, cols
+    a.gamma, a.beta, a.eps, a.normalize = _p(gamma), _p(beta), eps, 1 if normalize else 0
+    a.out_f32, a.ldo = _p(out_f32), (out_f32.stride(0) if out_f32 is not None else 0)
+    if out_h16 is not None:
+        a.out_hi, a.out_lo, a.ldh = _p(out_h16.hi), _p(out_h16.lo), out_h16.hi.stride(0)
+    if out2 is not None:
+        assert pe is not None
+        a.out2_hi, a.out2_lo = _p(out2.hi), _p(out2.lo)
+        if out_h16 is not None:
+            assert out2.hi.stride(0) == out_h16.hi.stride(0)
+        a.ldh = out2.hi.stride(0)
+    a.pe, a.ldpe, a.pe_mod = _p(pe), (pe.stride(0) if pe is not None else 0), pe_mod
+    a.act = act
+    L.check(L.load().csam_layernorm(C.byref(a), _stream()), "csam_layernorm")
+    return out_f32, out_h16, out2
+
+
+_attn_scratch = {}
+
+
+def vit_attention(qkv: H16, groups: int, tokens: int, heads: int, hd: int, scale: float, rel_h=None, rel_w=None,
+                  S=0, impl=None) -> H16:
+    dev = qkv.hi.device
+    out = H16.empty((groups * tokens, heads * hd), qkv.lo is not None, dev)
+    a = L.AttnArgs()
+    a.qkv_hi, a.qkv_lo, a.ld_qkv = _p(qkv.hi), _p(qkv.lo), qkv.hi.stride(0)
+    a.groups, a.tokens, a.heads, a.hd, a.scale = groups, tokens, heads, hd, scale
+    a.rel_h, a.rel_w, a.S = _p(rel_h), _p(rel_w), S
+    a.out_hi, a.out_lo, a.ld_out = _p(out.hi), _p(out.lo), out.hi.stride(0)
+    if rel_h is not None:
+        need = L.load().csam_vit_attention_scratch_bytes(groups, tokens, heads, hd, S)
+        key = (dev, need)
+        if key not in _attn_scratch:
+            _attn_scratch[key] = torch.empty(need, dtype=torch.uint8, device=dev)
+        a.scratch, a.scratch_bytes = _p(_attn_scratch[key]), need
+    a.impl = ATTN_IMPL if impl is None else impl
+    L.check(L.load().csam_vit_attention(C.byref(a), _stream()), "csam_vit_attention")
+    return out
+
+
+def im2col3x3(x: H16, side: int, Cc: int) -> H16:
+    out = H16.empty((side * side, 9 * Cc), x.lo is not None, x.hi.device)
+    L.check(L.load().csam_im2col3x3(_p(x.hi), _p(x.lo), side, Cc, _p(out.hi), _p(out.lo), _stream()), "csam_im2col3x3")
+    return out
+
+
+def transpose_f32(x: torch.Tensor) -> torch.Tensor:
+    rows, cols = x.shape
+    out = torch.empty((cols, rows), dtype=torch.float32, device=x.device)
+    L.check(L.load().csam_transpose_f32(_p(x), rows, cols, _p(out), _stream()), "csam_transpose_f32")
+    return out
+
+
+def bilinear(x: torch.Tensor, hout: int, wout: int, chlast: bool) -> torch.Tensor:
+    """planes [n,h,w] -> [n,hout,wout]  or channels-last [h,w,n] -> [hout,wout,n]."""
+    x = x.contiguous()
+    if chlast:
+        hin, win, n = x.shape
+        out = torch.empty((hout, wout, n), dtype=torch.float32, device=x.device)
+    else:
+        n, hin, win = x.shape
+        out = torch.empty((n, hout, wout), dtype=torch.float32, device=x.device)
+    L.check(L.load().csam_bilinear(_p(x), n, hin, win, _p(out), hout, wout, 1 if chlast else 0, _stream()),
+            "csam_bilinear")
+    return out
+
+
+def prompt_tokens(coords01, labels, gauss, tok5, point_emb, nap) -> torch.Tensor:
+    P = coords01.shape[0]
+    out = torch.empty((P, 7, 256), dtype=torch.float32, device=coords01.device)
+    L.check(L.load().csam_prompt_tokens(_p(coords01), _p(labels), P, _p(gauss), _p(tok5), _p(point_emb), _p(nap),
+                                        _p(out), _stream()), "csam_prompt_tokens")
+    return out
+
+
+def _dec_attn(fn_name, q, k, v, B, nq, nk, heads, hd, want_f32, want_h16, split):
+    dev = q.device
+    Cc = heads * hd
+    a = L.DecAttnArgs()
+    a.q, a.Bq = _p(q), (1 if q.shape[0] == 1 and B > 1 else B)
+    a.k, a.v, a.Bk = _p(k), _p(v), (1 if k.shape[0] == 1 and B > 1 else B)
+    a.B, a.nq, a.nk, a.heads, a.hd = B, nq, nk, heads, hd
+    of = torch.empty((B, nq, Cc), dtype=torch.float32, device=dev) if want_f32 else None
+    oh = H16.empty((B, nq, Cc), split, dev) if want_h16 else None
+    a.out_f32 = _p(of)
+    if oh is not None:
+        a.out_hi, a.out_lo = _p(oh.hi), _p(oh.lo)
+    L.check(getattr(L.load(), fn_name)(C.byref(a), _stream()), fn_name)
+    return of, oh
+
+
+def attn_few_keys(q, k, v, B, nq, nk, heads, hd, want_f32=False, want_h16=False, split=False):
+    return _dec_attn("csam_attn_few_keys", q, k, v, B, nq, nk, heads, hd, want_f32, want_h16, split)
+
+
+def attn_few_queries(q, k, v, B, nq, nk, heads, hd, want_f32=False, want_h16=False, split=False):
+    return _dec_attn("csam_attn_few_queries", q, k, v, B, nq, nk, heads, hd, want_f32, want_h16, split)
+
+
+def upscale_shuffle_ln_gelu(y1: torch.Tensor, P: int, gamma, beta, eps: float, split: bool) -> H16:
+    out = H16.empty((P * 16384, 64), split, y1.device)
+    L.check(L.load().csam_upscale_shuffle_ln_gelu(_p(y1), P, _p(gamma), _p(beta), eps, _p(out.hi), _p(out.lo),
+                                                  _stream()), "csam_upscale_shuffle_ln_gelu")
+    return out
+
+
+def upscale_hyper_masks(y2: torch.Tensor, P: int, hyper_in: torch.Tensor, out=None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty((P, 4, 256, 256), dtype=torch.float32, device=y2.device)
+    L.check(L.load().csam_upscale_hyper_masks(_p(y2), P, _p(hyper_in), _p(out), _stream()), "csam_upscale_hyper_masks")
+    return out
+
+
+def softmax_weights(x: torch.Tensor, split: bool):
+    R, n = x.shape
+    e = H16.empty((R, n), split, x.device)
+    inv = torch.empty((R,), dtype=torch.float32, device=x.device)
+    L.check(L.load().csam_softmax_weights(_p(x), R, n, _p(e.hi), _p(e.lo), _p(inv), _stream()), "csam_softmax_weights")
+    return e, inv
+
+
+def select_candidates(iou: torch.Tensor, cls: torch.Tensor):
+    P, ncls = iou.shape[0], cls.shape[-1]
+    dev = iou.device
+    score = torch.empty((P,), dtype=torch.float32, device=dev)
+    sel = torch.empty((P,), dtype=torch.int32, device=dev)
+    cat = torch.empty((P,), dtype=torch.int32, device=dev)
+    L.check(L.load().csam_select_candidates(_p(iou), _p(cls), P, ncls, _p(score), _p(sel), _p(cat), _stream()),
+            "csam_select_candidates")
+    return score, sel, cat
+
+
+def _post_args(low, sel, in_size, out_size, thr, off):
+    a = L.PostArgs()
+    low = low.contiguous()
+    a.low, a.P, a.sel = _p(low), low.shape[0], _p(sel)
+    a.planes = 4 if sel is not None else 1
+    a.in_h, a.in_w = int(in_size[0]), int(in_size[1])
+    a.out_h, a.out_w = int(out_size[0]), int(out_size[1])
+    a.thr, a.off = float(thr), float(off)
+    return a, low
+
+
+def mask_post_stats(low, sel, in_size, out_size, thr=0.0, off=1.0):
+    """-> counts int32 [P,3] (#>thr+off, #>thr-off, #>thr), boxes int32 [P,4]."""
+    a, low = _post_args(low, sel, in_size, out_size, thr, off)
+    P = low.shape[0]
+    counts = torch.empty((P, 3), dtype=torch.int32, device=low.device)
+    boxes = torch.empty((P, 4), dtype=torch.int32, device=low.device)
+    a.counts, a.boxes = _p(counts), _p(boxes)
+    L.check(L.load().csam_mask_post_stats(C.byref(a), _stream()), "csam_mask_post_stats")
+    return counts, boxes
+
+
+def mask_post_write(low, sel, keep, in_size, out_size, thr=0.0, want_masks=True, want_logits=False):
+    a, low = _post_args(low, sel, in_size, out_size, thr, 0.0)
+    n = low.shape[0] if keep is None else int(keep.numel())
+    dev = low.device
+    masks = torch.empty((n, a.out_h, a.out_w), dtype=torch.bool, device=dev) if want_masks else None
+    logits = torch.empty((n, a.out_h, a.out_w), dtype=torch.float32, device=dev) if want_logits else None
+    if n == 0:
+        return masks, logits
+    a.keep, a.n_keep = _p(keep), n
+    a.masks, a.logits = _p(masks), _p(logits)
+    L.check(L.load().csam_mask_post_write(C.byref(a), _stream()), "csam_mask_post_write")
+    return masks, logits
+
+
+def box_nms(boxes: torch.Tensor, scores: torch.Tensor, thr: float) -> torch.Tensor:
+    """torchvision.ops.nms semantics; returns kept indices (int64) in stable descending-score order."""
+    n = boxes.shape[0]
+    dev = boxes.device
+    if n == 0:
+        return torch.zeros((0,), dtype=torch.int64, device=dev)
+    boxes = boxes.contiguous().float()
+    scores = scores.contiguous().float()
+    keep = torch.empty((n,), dtype=torch.int32, device=dev)
+    nk = torch.zeros((1,), dtype=torch.int32, device=dev)
+    need = L.load().csam_box_nms_scratch_bytes(n)
+    scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+    L.check(L.load().csam_box_nms(_p(boxes), _p(scores), n, float(thr), _p(keep), _p(nk), _p(scratch), need, _stream()),
+            "csam_box_nms")
+    k = int(nk.item())
+    return keep[:k].long()
+
+
+def mask_overlap(masks: torch.Tensor):
+    n, h, w = masks.shape
+    dev = masks.device
+    inter = torch.empty((n, n), dtype=torch.int32, device=dev)
+    area = torch.empty((n,), dtype=torch.int32, device=dev)
+    need = L.load().csam_mask_overlap_scratch_bytes(n)
+    scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+    L.check(L.load().csam_mask_overlap(_p(masks.contiguous()), n, h, w, _p(inter), _p(area), _p(scratch), need,
+                                       _stream()), "csam_mask_overlap")
+    return inter, area
+
+
+def points_occupied(masks: torch.Tensor, flag: torch.Tensor, pts_xy: torch.Tensor) -> torch.Tensor:
+    n_pts = pts_xy.shape[0]
+    occ = torch.zeros((n_pts,), dtype=torch.uint8, device=pts_xy.device)
+    if n_pts == 0 or masks.shape[0] == 0:
+        return occ
+    n, h, w = masks.shape
+    L.check(L.load().csam_points_occupied(_p(masks.contiguous()), n, h, w, _p(flag.contiguous()), _p(pts_xy.contiguous()),
+                                          n_pts, _p(occ), _stream()), "csam_points_occupied")
+    return occ
+
+
+def rle_encode(masks: torch.Tensor):
+    """Column-major uncompressed RLE of bool masks [n,h,w] -> list of python int lists."""
+    n, h, w = masks.shape
+    if n == 0:
+        return []
+    masks = masks.contiguous()
+    dev = masks.device
+    cnt = torch.empty((n,), dtype=torch.int32, device=dev)
+    L.check(L.load().csam_rle_count(_p(masks), n, h, w, _p(cnt), _stream()), "csam_rle_count")
+    cnt_h = cnt.cpu().long()
+    offs = torch.zeros((n + 1,), dtype=torch.int64)
+    offs[1:] = torch.cumsum(cnt_h, 0)
+    total = int(offs[-1])
+    runs = torch.empty((total,), dtype=torch.int32, device=dev)
+    offs_d = offs[:-1].to(dev)
+    L.check(L.load().csam_rle_fill(_p(masks), n, h, w, _p(offs_d), _p(runs), _stream()), "csam_rle_fill")
+    runs_h = runs.cpu().numpy()
+    o = offs.numpy()
+    return [runs_h[o[i]:o[i + 1]] for i in range(n)]

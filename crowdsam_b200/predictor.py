@@ -1,0 +1,163 @@
+"""SamPredictor over the B200 engines — the drop-in boundary.
+
+Mirrors segment_anything_cs/predictor.py: `set_image :32`, `set_torch_image :72`,
+`predict_fg_map :113`, `predict :133`, `predict_torch :214`, `get_image_embedding :294`,
+`reset_image :311`, `.device :308`, assignable `.features / .dino_feats / .original_size /
+.input_size / .is_image_set / .model`.  Same error behaviour (RuntimeError before set_image,
+AssertionError on bad format/shape).  Everything runs under no_grad on the CUDA kernels.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from .ops import H16
+from .transforms import ResizeLongestSide
+
+
+class SamPredictor:
+    def __init__(self, sam_model, dino_model) -> None:
+        self.model = sam_model
+        self.dino_model = dino_model
+        self.transform = ResizeLongestSide(sam_model.image_encoder.img_size)
+        self.reset_image()
+
+    # ------------------------------------------------------------------ image
+    def set_image(self, image: np.ndarray, mask: np.ndarray = None, image_format: str = "RGB", cal_image=True):
+        assert image_format in ["RGB", "BGR"], f"image_format must be in ['RGB', 'BGR'], is {image_format}."
+        if image_format != self.model.image_format:
+            image = image[..., ::-1]
+        resized = self.transform.apply_image(np.ascontiguousarray(image))
+        t = torch.as_tensor(resized).permute(2, 0, 1).contiguous()[None]      # pageable -> pinned -> device
+        t = t.to(self.device, non_blocking=False)
+        mask_t = None
+        if mask is not None:
+            mask_t = torch.as_tensor(self.transform.apply_image(mask), device=self.device).permute(2, 0, 1).contiguous()[None]
+        return self.set_torch_image(t, image.shape[:2], transformed_mask=mask_t, cal_image=cal_image)
+
+    @torch.no_grad()
+    def set_torch_image(self, transformed_image: torch.Tensor, original_image_size: Tuple[int, ...],
+                        transformed_mask: torch.Tensor = None, cal_image=True):
+        size = self.model.image_encoder.img_size
+        assert (len(transformed_image.shape) == 4 and transformed_image.shape[1] == 3
+                and max(*transformed_image.shape[2:]) == size), \
+            f"set_torch_image input must be BCHW with long side {size}."
+        if cal_image:
+            self.reset_image()
+            self.original_size = tuple(original_image_size)
+            self.input_size = tuple(transformed_image.shape[-2:])
+            img = transformed_image[0]
+            if img.dtype != torch.uint8:
+                r = img.round()
+                if not torch.equal(r, img) or r.min() < 0 or r.max() > 255:
+                    raise NotImplementedError("the B200 path takes 8-bit images (as SamPredictor.set_image produces)")
+                img = r.to(torch.uint8)
+            img = img.to(self.device).contiguous()
+            feats, feat_tok = self.model.image_encoder.forward_u8(img)
+            dino_f32, dino_h = self.dino_model.forward_features_u8(img)
+            self.features = feats
+            self.dino_feats = dino_f32.view(1, 73, 73, -1)
+            self._bind(feats, self.dino_feats, feat_tok, dino_h)
+            self.is_image_set = True
+        if transformed_mask is not None:
+            h, w = transformed_mask.shape[-2:]
+            return torch.nn.functional.pad(transformed_mask, (0, size - w, 0, size - h))
+
+    def _bind(self, feats, dino_feats, feat_tok=None, dino_h=None):
+        """Run the prompt-independent decoder work for (features, dino_feats).  When a caller assigned the
+        two tensors directly (tools/train.py caches them), derive the engine inputs from them."""
+        eng = self.model.mask_decoder.engine()
+        if feat_tok is None:
+            feat_tok = ops.transpose_f32(feats.reshape(256, 4096).float().contiguous())
+        if dino_h is None:
+            d = dino_feats.reshape(-1, dino_feats.shape[-1]).float().contiguous()
+            _, dino_h, _ = ops.layernorm(d, normalize=False, want_h16=True, split=eng.split)
+        eng.set_image(feat_tok, dino_h)
+        self._bound = (feats, dino_feats, eng)
+
+    def _engine(self):
+        if not self.is_image_set:
+            raise RuntimeError("An image must be set with .set_image(...) before mask prediction.")
+        eng = self.model.mask_decoder.engine()
+        b = self._bound
+        if b is None or b[0] is not self.features or b[1] is not self.dino_feats or b[2] is not eng:
+            self._bind(self.features, self.dino_feats)
+        return self._bound[2]
+
+    # ------------------------------------------------------------------ prompts
+    @torch.no_grad()
+    def predict_fg_map(self, img_size=None) -> torch.Tensor:
+        return self._engine().fg_logits()
+
+    def _coords01(self, point_coords: torch.Tensor, point_labels: torch.Tensor, boxes, mask_input):
+        if boxes is not None or mask_input is not None or point_coords is None:
+            raise NotImplementedError("only point prompts are on the B200 hot path (boxes / mask inputs are not)")
+        if point_coords.dim() != 3 or point_coords.shape[1] != 1:
+            raise NotImplementedError("one point per prompt on the B200 hot path")
+        # (pt + 0.5) / 1024 in the incoming dtype (float64 from apply_coords), then fp32
+        # (prompt_encoder.py:82,215-218)
+        c = (point_coords[:, 0, :] + 0.5) / float(self.model.image_encoder.img_size)
+        c01 = c.to(torch.float32).contiguous().to(self.device)
+        lab = point_labels[:, 0].to(torch.int32).contiguous().to(self.device)
+        return c01, lab
+
+    @torch.no_grad()
+    def decode_low_res(self, point_coords, point_labels, boxes=None, mask_input=None):
+        """low-res logits [P,4,256,256], iou [P,4], cls [P,4,n_class] without the full-size upsample."""
+        eng = self._engine()
+        c01, lab = self._coords01(point_coords, point_labels, boxes, mask_input)
+        return eng.decode(c01, lab)
+
+    @torch.no_grad()
+    def predict_torch(self, point_coords: Optional[torch.Tensor], point_labels: Optional[torch.Tensor],
+                      boxes: Optional[torch.Tensor] = None, mask_input: Optional[torch.Tensor] = None,
+                      multimask_output: bool = True, return_logits: bool = False, attn_sim=None,
+                      target_embedding=None):
+        if not self.is_image_set:
+            raise RuntimeError("An image must be set with .set_image(...) before mask prediction.")
+        low, iou, cls = self.decode_low_res(point_coords, point_labels, boxes, mask_input)
+        if not multimask_output:                         # mask_decoder.py:128-134
+            low, iou, cls = low[:, :1].contiguous(), iou[:, :1], cls[:, :1]
+        P, Cn = low.shape[:2]
+        flat = low.reshape(P * Cn, 256, 256)
+        thr = float(self.model.mask_threshold)
+        m, lg = ops.mask_post_write(flat, None, None, self.input_size, self.original_size, thr,
+                                    want_masks=not return_logits, want_logits=return_logits)
+        out = lg if return_logits else m
+        H, W = self.original_size
+        return out.view(P, Cn, H, W), iou, cls, low
+
+    def predict(self, point_coords=None, point_labels=None, box=None, mask_input=None, multimask_output=True,
+                return_logits=False, attn_sim=None, target_embedding=None):
+        """numpy front end of predict_torch (predictor.py:133-212) for a single prompt."""
+        if not self.is_image_set:
+            raise RuntimeError("An image must be set with .set_image(...) before mask prediction.")
+        assert point_coords is not None and point_labels is not None, "point_labels must be supplied with point_coords."
+        pc = self.transform.apply_coords(point_coords, self.original_size)
+        ct = torch.as_tensor(pc, dtype=torch.float)[None]
+        lt = torch.as_tensor(point_labels, dtype=torch.int)[None]
+        if box is not None or mask_input is not None:
+            raise NotImplementedError("only point prompts are on the B200 hot path")
+        masks, iou, _, low = self.predict_torch(ct, lt, None, None, multimask_output, return_logits=return_logits)
+        return masks[0].cpu().numpy(), iou[0].cpu().numpy(), low[0].cpu().numpy()
+
+    # ------------------------------------------------------------------ state
+    def get_image_embedding(self) -> torch.Tensor:
+        if not self.is_image_set:
+            raise RuntimeError("An image must be set with .set_image(...) to generate an embedding.")
+        assert self.features is not None, "Features must exist if an image has been set."
+        return self.features
+
+    @property
+    def device(self) -> torch.device:
+        return self.model.device
+
+    def reset_image(self) -> None:
+        self.is_image_set = False
+        self.features = None
+        self.dino_feats = None
+        self._bound = None
+        self.orig_h = self.orig_w = self.input_h = self.input_w = None

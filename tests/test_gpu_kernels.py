@@ -1,0 +1,415 @@
+"""GPU parity tests of the individual kernels, called through the C-ABI (crowdsam_b200.ops -> ctypes).
+
+Oracle: plain PyTorch fp32 on the CPU of the same op (oracle/restate.py where the op is a stage of
+the reference path).  Tolerances are written per test; integer / index outputs are bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import fixtures, restate  # noqa: E402
+
+DEV = "cuda"
+# which GEMM / attention implementations to exercise: 0 = tcgen05, 1 = SIMT validation kernels
+IMPLS = [int(x) for x in os.environ.get("CSAM_TEST_IMPLS", "1,0").split(",")]
+ATTN_IMPLS = [int(x) for x in os.environ.get("CSAM_TEST_ATTN_IMPLS", "1").split(",")]
+
+
+def ops():
+    from crowdsam_b200 import ops as o
+
+    return o
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def _h16(t, split):
+    return ops().H16.from_f32(t.to(DEV), split)
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+GEMM_SHAPES = [(128, 128, 64), (256, 384, 1024), (4900, 3072, 1024), (6, 32, 256), (42, 2048, 256),
+               (5330, 1024, 592), (130, 1, 256), (4096, 256, 2304), (300, 4, 256), (200, 64, 64)]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_plain(M, N, K, split, impl):
+    o = ops()
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    ah, wh = _h16(a, split), _h16(w, split)
+    ref = ah.float().cpu().double() @ wh.float().cpu().double().T + bias.double()
+    out, outh = o.gemm(ah, wh, bias=bias.to(DEV), want_f32=True, want_h16=True, impl=impl)
+    torch.cuda.synchronize()
+    # operands are exactly representable, so only accumulation order / the dropped lo*lo term differ
+    tol = 2e-5 if split else 2e-5
+    assert _rel(out, ref) < tol, (M, N, K, split, impl, _rel(out, ref))
+    assert _rel(outh.float(), ref) < (1e-5 + tol if split else 1e-3)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_gemm_x3_accuracy_vs_fp32(impl):
+    """The hi/lo split keeps fp32-level accuracy on fp32 inputs (no pre-rounding of the reference)."""
+    o = ops()
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(512, 1024, generator=g)
+    w = torch.randn(768, 1024, generator=g) * 0.03
+    ref = a.double() @ w.double().T
+    o3, _ = o.gemm(_h16(a, True), _h16(w, True), want_f32=True, impl=impl)
+    o1, _ = o.gemm(_h16(a, False), _h16(w, False), want_f32=True, impl=impl)
+    e3, e1 = _rel(o3, ref), _rel(o1, ref)
+    assert e3 < 5e-6, e3
+    assert e1 < 2e-3 and e1 > e3 * 10, (e1, e3)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_gemm_epilogue(impl):
+    """bias + GELU + LayerScale + residual with row scatter map (window un-partition) + row_scale."""
+    o = ops()
+    g = torch.Generator().manual_seed(11)
+    M, N, K, R = 300, 256, 128, 280
+    a, w = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.1
+    bias, cs, rs = torch.randn(N, generator=g), torch.rand(N, generator=g) + 0.5, torch.rand(M, generator=g) + 0.5
+    res = torch.randn(R, N, generator=g)
+    perm = torch.randperm(M, generator=g)
+    row_map = torch.full((M,), -1, dtype=torch.int32)
+    row_map[perm[:R]] = torch.arange(R, dtype=torch.int32)
+    ah, wh = _h16(a, True), _h16(w, True)
+    acc = ah.float().cpu().double() @ wh.float().cpu().double().T
+    v = torch.nn.functional.gelu((acc * rs[:, None].double() + bias.double())) * cs.double()
+    ref = res.double().clone()
+    for r in range(M):
+        if row_map[r] >= 0:
+            ref[row_map[r]] = v[r] + res[row_map[r]].double()
+    out = res.clone().to(DEV)
+    outh = o.H16.empty((R, N), True, DEV)
+    o.gemm(ah, wh, bias=bias.to(DEV), act=o.ACT_GELU, col_scale=cs.to(DEV), row_scale=rs.to(DEV), residual=out,
+           row_map=row_map.to(DEV), out_f32=out, out_h16=outh, impl=impl)
+    assert _rel(out, ref) < 1e-5
+    sel = row_map[row_map >= 0].long()
+    assert _rel(outh.float().cpu()[sel], ref[sel]) < 1e-5
+    # residual broadcast with res_mod + ReLU, odd N (scalar epilogue path)
+    res2 = torch.randn(50, 30, generator=g)
+    w2 = torch.randn(30, K, generator=g)
+    ref2 = torch.relu(ah.float().cpu().double() @ _h16(w2, True).float().cpu().double().T) + res2.double()[torch.arange(M) % 50]
+    out2, _ = o.gemm(ah, _h16(w2, True), act=o.ACT_RELU, residual=res2.to(DEV), res_mod=50, want_f32=True, impl=impl)
+    assert _rel(out2, ref2) < 1e-5
+
+
+@pytest.mark.skipif(0 not in IMPLS, reason="tcgen05 only")
+@pytest.mark.parametrize("split", [False, True])
+def test_gemm_b_mn_major(split):
+    """W given as [K,N] row-major (MN-major UMMA operand) — the layout the attention PV product uses."""
+    o = ops()
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 256, 256, 192
+    a, wkn = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g)
+    ah, wh = _h16(a, split), _h16(wkn, split)
+    ref = ah.float().cpu().double() @ wh.float().cpu().double()
+    out, _ = o.gemm(ah, wh, want_f32=True, b_mn_major=True, impl=0)
+    assert _rel(out, ref) < 2e-5
+
+
+def test_gemm_strided_views():
+    o = ops()
+    g = torch.Generator().manual_seed(4)
+    P = 37
+    hs = torch.randn(P, 7 * 256, generator=g)
+    w = torch.randn(32, 256, generator=g)
+    hh = _h16(hs, True)
+    a = o.H16(hh.hi[:, 512:768], hh.lo[:, 512:768])
+    out = torch.zeros(P, 4, 32, device=DEV)
+    o.gemm(a, _h16(w, True), out_f32=out[:, 2, :])
+    ref = hh.float().cpu()[:, 512:768].double() @ _h16(w, True).float().cpu().double().T
+    assert _rel(out[:, 2, :], ref) < 1e-5
+    assert float(out[:, [0, 1, 3], :].abs().max()) == 0.0
+
+
+# --------------------------------------------------------------------------------- LayerNorm etc.
+@pytest.mark.parametrize("cols", [64, 256, 768, 1024, 1280])
+def test_layernorm(cols):
+    o = ops()
+    g = torch.Generator().manual_seed(cols)
+    x = torch.randn(333, cols, generator=g) * 3 + 1
+    gam, bet = torch.randn(cols, generator=g), torch.randn(cols, generator=g)
+    ref = torch.nn.functional.layer_norm(x, (cols,), gam, bet, 1e-6)
+    f, h, _ = o.layernorm(x.to(DEV), gam.to(DEV), bet.to(DEV), 1e-6, want_f32=True, want_h16=True, split=True)
+    assert _rel(f, ref) < 2e-6
+    assert _rel(h.float(), ref) < 2e-6
+    _, h1, _ = o.layernorm(x.to(DEV), gam.to(DEV), bet.to(DEV), 1e-6, want_h16=True, split=False)
+    assert _rel(h1.float(), ref) < 1e-3
+
+
+def test_layernorm_gather_add_pe():
+    o = ops()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(100, 256, generator=g)
+    add = torch.randn(10, 256, generator=g)
+    pe = torch.randn(7, 256, generator=g)
+    rm = torch.tensor([5, -1, 99, 0, -1, 42, 42], dtype=torch.int32)
+    gam, bet = torch.randn(256, generator=g), torch.randn(256, generator=g)
+    f, h, h2 = o.layernorm(x.to(DEV), gam.to(DEV), bet.to(DEV), 1e-5, add=add.to(DEV), add_mod=10, row_map=rm.to(DEV),
+                           want_f32=True, want_h16=True, split=True, pe=pe.to(DEV), want_out2=True, act=o.ACT_GELU)
+    ref = torch.zeros(7, 256)
+    for r, s in enumerate(rm.tolist()):
+        if s >= 0:
+            ref[r] = torch.nn.functional.gelu(torch.nn.functional.layer_norm(x[s] + add[s % 10], (256,), gam, bet, 1e-5))
+    assert _rel(f, ref) < 2e-6
+    assert _rel(h.float(), ref) < 2e-6
+    valid = rm >= 0
+    assert _rel(h2.float().cpu()[valid], (ref + pe)[valid]) < 2e-6
+    # pure cast
+    _, hc, _ = o.layernorm(x.to(DEV), normalize=False, want_h16=True, split=True)
+    assert _rel(hc.float(), x) < 1e-6
+
+
+def test_patchify_sam_and_dino():
+    o = ops()
+    img = torch.as_tensor(np.random.default_rng(0).integers(0, 256, (3, 683, 1024), dtype=np.uint8))
+    x = restate.preprocess(img[None])                                        # [1,3,1024,1024]
+    ref = torch.nn.functional.unfold(x, 16, stride=16)[0].T                  # [4096, 768]
+    p = o.patchify(img.to(DEV), 16, 64, 0, 768, True)
+    assert _rel(p.float(), ref) < 1e-6
+    x2 = torch.nn.functional.interpolate(x, (1022, 1022), mode="bilinear")
+    ref2 = torch.nn.functional.unfold(x2, 14, stride=14)[0].T                # [5329, 588]
+    p2 = o.patchify(img.to(DEV), 14, 73, 1022, 592, True).float().cpu()
+    assert float(p2[:, 588:].abs().max()) == 0.0
+    assert (p2[:, :588] - ref2).abs().max() < 2e-5
+
+
+def test_im2col_transpose_bilinear():
+    o = ops()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(1, 256, 64, 64, generator=g)
+    xh = _h16(x[0].permute(1, 2, 0).reshape(4096, 256).contiguous(), True)
+    cols = o.im2col3x3(xh, 64, 256).float().cpu()
+    ref = torch.nn.functional.unfold(xh.float().cpu().T.reshape(1, 256, 64, 64), 3, padding=1)[0]   # [256*9, 4096], (c,ky,kx)
+    ref = ref.view(256, 9, 4096).permute(2, 1, 0).reshape(4096, 9 * 256)
+    assert torch.equal(cols, ref)
+    t = torch.randn(100, 37, generator=g)
+    assert torch.equal(o.transpose_f32(t.to(DEV)).cpu(), t.T.contiguous())
+    d = torch.randn(5, 73, 73, generator=g)
+    ref = torch.nn.functional.interpolate(d[None], (256, 256), mode="bilinear")[0]
+    assert (o.bilinear(d.to(DEV), 256, 256, False).cpu() - ref).abs().max() < 2e-6
+    refd = torch.nn.functional.interpolate(d[None], (40, 61), mode="bilinear")[0]
+    assert (o.bilinear(d.to(DEV), 40, 61, False).cpu() - refd).abs().max() < 2e-6
+    dl = d.permute(1, 2, 0).contiguous()
+    assert (o.bilinear(dl.to(DEV), 256, 256, True).cpu() - ref.permute(1, 2, 0)).abs().max() < 2e-6
+
+
+# ------------------------------------------------------------------------------------ attention
+def _attn_ref(qkv, groups, tokens, heads, hd, rel_h=None, rel_w=None, S=0):
+    D = heads * hd
+    x = qkv.double().view(groups, tokens, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = x[0], x[1], x[2]
+    attn = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    if rel_h is not None:
+        Rh, Rw = restate._rel_table(rel_h.double(), S), restate._rel_table(rel_w.double(), S)
+        rq = q.reshape(groups, heads, S, S, hd)
+        bh = torch.einsum("ghywc,ykc->ghywk", rq, Rh)
+        bw = torch.einsum("ghywc,wkc->ghywk", rq, Rw)
+        attn = (attn.view(groups, heads, S, S, S, S) + bh[..., :, None] + bw[..., None, :]).view(groups, heads, tokens, tokens)
+    o = attn.softmax(-1) @ v
+    return o.permute(0, 2, 1, 3).reshape(groups * tokens, D)
+
+
+@pytest.mark.parametrize("impl", ATTN_IMPLS)
+@pytest.mark.parametrize("groups,S,heads,hd", [(3, 14, 2, 64), (1, 32, 2, 64), (2, 14, 2, 80)])
+def test_vit_attention_relpos(groups, S, heads, hd, impl):
+    o = ops()
+    g = torch.Generator().manual_seed(S)
+    tokens = S * S
+    qkv = torch.randn(groups * tokens, 3 * heads * hd, generator=g)
+    rel_h, rel_w = torch.randn(2 * S - 1, hd, generator=g) * 0.3, torch.randn(2 * S - 1, hd, generator=g) * 0.3
+    qh = _h16(qkv, True)
+    ref = _attn_ref(qh.float().cpu(), groups, tokens, heads, hd, rel_h, rel_w, S)
+    out = o.vit_attention(qh, groups, tokens, heads, hd, hd ** -0.5, rel_h.to(DEV), rel_w.to(DEV), S, impl=impl)
+    assert _rel(out.float(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("impl", ATTN_IMPLS)
+def test_vit_attention_plain_ragged(impl):
+    o = ops()
+    g = torch.Generator().manual_seed(9)
+    tokens, heads, hd = 333, 3, 64
+    qkv = torch.randn(tokens, 3 * heads * hd, generator=g)
+    qh = _h16(qkv, True)
+    ref = _attn_ref(qh.float().cpu(), 1, tokens, heads, hd)
+    out = o.vit_attention(qh, 1, tokens, heads, hd, hd ** -0.5, impl=impl)
+    assert _rel(out.float(), ref) < 1e-5
+
+
+def test_decoder_attentions():
+    o = ops()
+    g = torch.Generator().manual_seed(12)
+
+    def ref(q, k, v, heads):
+        B, nq, C = q.shape
+        hd = C // heads
+        sp = lambda t: t.double().view(t.shape[0], t.shape[1], heads, hd).transpose(1, 2)
+        a = torch.softmax(sp(q) @ sp(k).transpose(-1, -2) / hd ** 0.5, -1) @ sp(v)
+        return a.transpose(1, 2).reshape(-1, nq, C)
+
+    P = 5
+    q, k, v = (torch.randn(P, 7, 256, generator=g) for _ in range(3))
+    f, h = o.attn_few_keys(q.to(DEV), k.to(DEV), v.to(DEV), P, 7, 7, 8, 32, want_f32=True, want_h16=True, split=True)
+    assert _rel(f, ref(q, k, v, 8)) < 1e-5 and _rel(h.float(), ref(q, k, v, 8)) < 1e-5
+    q1 = torch.randn(1, 4096, 128, generator=g)
+    k7, v7 = torch.randn(P, 7, 128, generator=g), torch.randn(P, 7, 128, generator=g)
+    f, _ = o.attn_few_keys(q1.to(DEV), k7.to(DEV), v7.to(DEV), P, 4096, 7, 8, 16, want_f32=True)
+    assert _rel(f, ref(q1.expand(P, -1, -1), k7, v7, 8)) < 1e-5
+    qq = torch.randn(P, 7, 128, generator=g)
+    kk, vv = torch.randn(1, 4096, 128, generator=g), torch.randn(1, 4096, 128, generator=g)
+    f, _ = o.attn_few_queries(qq.to(DEV), kk.to(DEV), vv.to(DEV), P, 7, 4096, 8, 16, want_f32=True)
+    assert _rel(f, ref(qq, kk.expand(P, -1, -1), vv.expand(P, -1, -1), 8)) < 1e-5
+    kp, vp = torch.randn(P, 4096, 128, generator=g), torch.randn(P, 4096, 128, generator=g)
+    f, _ = o.attn_few_queries(qq.to(DEV), kp.to(DEV), vp.to(DEV), P, 7, 4096, 8, 16, want_f32=True)
+    assert _rel(f, ref(qq, kp, vp, 8)) < 1e-5
+
+
+def test_prompt_tokens_and_small_kernels():
+    o = ops()
+    from oracle import weights
+
+    sd = weights.make_sam_state("tiny")
+    pts = np.array([[10, 20], [512, 512], [1000, 30], [0, 0], [1023, 1023]], dtype=float)
+    coords = torch.as_tensor(pts)[:, None, :]
+    labels = torch.ones(5, dtype=torch.int)[:, None]
+    labels[3, 0] = 0
+    sparse = restate.embed_points(sd, coords, labels)
+    c01 = ((coords[:, 0, :] + 0.5) / 1024.0).float()
+    tok5 = torch.cat([sd["mask_decoder.iou_token.weight"], sd["mask_decoder.mask_tokens.weight"]], 0)
+    pe = torch.cat([sd["prompt_encoder.point_embeddings.0.weight"], sd["prompt_encoder.point_embeddings.1.weight"]], 0)
+    t = o.prompt_tokens(c01.to(DEV), labels[:, 0].to(torch.int32).to(DEV),
+                        sd["prompt_encoder.pe_layer.positional_encoding_gaussian_matrix"].to(DEV), tok5.contiguous().to(DEV),
+                        pe.contiguous().to(DEV), sd["prompt_encoder.not_a_point_embed.weight"].reshape(256).to(DEV)).cpu()
+    assert torch.equal(t[:, :5], tok5[None].expand(5, -1, -1))
+    assert (t[:, 5:] - sparse).abs().max() < 2e-5
+    # softmax weights
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(6, 65536, generator=g) * 8
+    e, inv = o.softmax_weights(x.to(DEV), True)
+    w = e.float().cpu().double() * inv.cpu().double()[:, None]
+    assert (w - x.double().softmax(-1)).abs().max() / x.double().softmax(-1).max() < 1e-5
+    # select
+    iou, cls = torch.randn(50, 4, generator=g), torch.randn(50, 4, 1, generator=g)
+    iou[3] = 0.5
+    cls[3] = 0.1
+    s, sel, cat = o.select_candidates(iou.to(DEV), cls.to(DEV))
+    ref = torch.clamp(iou, 0.0) * cls.squeeze(2).sigmoid()
+    assert torch.equal(sel.cpu().long(), ref.max(-1)[1]) and (s.cpu() - ref.max(-1)[0]).abs().max() < 1e-6
+    assert int(cat.abs().max()) == 0
+
+
+def test_upscale_kernels():
+    o = ops()
+    g = torch.Generator().manual_seed(7)
+    P = 2
+    y1 = torch.randn(P * 4096, 256, generator=g)
+    gam, bet = torch.randn(64, generator=g), torch.randn(64, generator=g)
+    out = o.upscale_shuffle_ln_gelu(y1.to(DEV), P, gam.to(DEV), bet.to(DEV), 1e-6, True).float().cpu()
+    v = y1.view(P, 64, 64, 2, 2, 64)                                         # p,y,x,dy,dx,c
+    ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(v, (64,), gam, bet, 1e-6))
+    ref = ref.permute(0, 1, 3, 2, 4, 5).reshape(P * 16384, 64)
+    assert _rel(out, ref) < 2e-6
+    y2 = torch.randn(P * 16384, 128, generator=g)
+    hyper = torch.randn(P, 4, 32, generator=g)
+    m = o.upscale_hyper_masks(y2.to(DEV), P, hyper.to(DEV)).cpu()
+    u = y2.view(P, 128, 128, 2, 2, 32).permute(0, 1, 3, 2, 4, 5).reshape(P, 256, 256, 32)
+    refm = torch.einsum("plc,pyxc->plyx", hyper.double(), u.double())
+    assert _rel(m, refm) < 1e-5
+
+
+# ------------------------------------------------------------------------------- K-POST / K-NMS
+@pytest.mark.parametrize("tag,inp,orig", [("sq", (1024, 1024), (1024, 1024)), ("ns", (683, 1024), (600, 900)),
+                                           ("id", (768, 1024), (768, 1024))])
+def test_mask_post_vs_oracle_and_golden(tag, inp, orig, golden_dir):
+    o = ops()
+    P = 48
+    low, iou, cls = fixtures.blob_logits(P, seed=0)
+    score, sel, _ = o.select_candidates(iou.to(DEV), cls.to(DEV))
+    counts, boxes = o.mask_post_stats(low.to(DEV), sel, inp, orig, 0.0, 1.0)
+    full = restate.postprocess_masks(low, inp, orig)
+    m = full[torch.arange(P), sel.cpu().long()]
+    # pixels within eps of a threshold may legitimately flip between two fp32 evaluation orders
+    eps = 1e-4
+    for ci, t in enumerate((1.0, -1.0, 0.0)):
+        ref = (m > t).flatten(1).sum(1)
+        slack = ((m - t).abs() < eps).flatten(1).sum(1)
+        assert ((counts[:, ci].cpu().long() - ref).abs() <= slack).all(), (tag, ci)
+    stab_ref = restate.stability_score(m, 0.0, 1.0)
+    stab = counts[:, 0] / counts[:, 1]
+    assert (stab.cpu() - stab_ref).abs().max() < 1e-4
+    box_ref = restate.mask_to_box(m > 0.0)
+    exact = (boxes.cpu().long() == box_ref).all(1)
+    # a box may move only if a near-zero pixel sits on its border
+    lo_b, hi_b = restate.mask_to_box(m > eps), restate.mask_to_box(m > -eps)
+    ok = exact | (((boxes.cpu().long() - lo_b).abs() <= (hi_b - lo_b).abs()).all(1))
+    assert ok.all() and exact.float().mean() > 0.9
+    keep = torch.arange(0, P, 3, dtype=torch.int32, device=DEV)
+    masks, logits = o.mask_post_write(low.to(DEV), sel, keep, inp, orig, 0.0, want_masks=True, want_logits=True)
+    mk = m[keep.cpu().long()]
+    assert (logits.cpu() - mk).abs().max() < 2e-5
+    diff = masks.cpu() != (mk > 0.0)
+    assert (diff & ((mk.abs() >= eps))).sum() == 0
+    if tag in ("sq", "ns"):
+        g = np.load(os.path.join(golden_dir, "stage_post_nms.npz"))
+        np.testing.assert_array_equal(sel.cpu().numpy(), g[f"{tag}_sel"])
+        np.testing.assert_allclose(stab.cpu().numpy(), g[f"{tag}_stability"], atol=1e-4)
+        assert (boxes.cpu().numpy() == g[f"{tag}_boxes"]).all(1).mean() > 0.9
+        np.testing.assert_allclose(score.cpu().numpy(), g[f"{tag}_score"], rtol=1e-5, atol=1e-6)
+        kp = o.box_nms(torch.as_tensor(g[f"{tag}_boxes"]).float().to(DEV), torch.as_tensor(g[f"{tag}_score"]).to(DEV), 0.65)
+        np.testing.assert_array_equal(kp.cpu().numpy(), g[f"{tag}_nms_keep"])
+
+
+@pytest.mark.parametrize("n,seed,binary", [(257, 0, False), (3000, 1, False), (3000, 2, True), (1, 3, False), (64, 5, False),
+                                            (65, 6, True), (5000, 7, False)])
+def test_box_nms_bit_exact(n, seed, binary, golden_dir):
+    o = ops()
+    g = np.load(os.path.join(golden_dir, "stage_post_nms.npz"))
+    b, s = fixtures.random_boxes(n, seed, binary_scores=binary)
+    for thr in (0.65, 0.7):
+        keep = o.box_nms(torch.as_tensor(b).to(DEV), torch.as_tensor(s).to(DEV), thr).cpu().numpy()
+        np.testing.assert_array_equal(keep, restate.nms_reference(b, s, thr))
+        key = f"nms_{n}_{seed}_{thr}"
+        if key in g:
+            np.testing.assert_array_equal(keep, g[key])
+    assert o.box_nms(torch.zeros(0, 4, device=DEV), torch.zeros(0, device=DEV), 0.5).numel() == 0
+
+
+def test_rle_occupancy_overlap(golden_dir):
+    o = ops()
+    low, iou, cls = fixtures.blob_logits(6, seed=3)
+    full = restate.postprocess_masks(low, (1024, 1024), (1024, 1024))[:, 0]
+    masks = full > 0
+    masks[4] = False
+    masks[5] = True
+    rng = np.random.default_rng(0)
+    noise = torch.as_tensor(rng.integers(0, 2, (2, 37, 53)).astype(bool))
+    for mm in (masks, noise):
+        runs = o.rle_encode(mm.to(DEV))
+        for i in range(mm.shape[0]):
+            ref = restate.mask_to_rle(mm[i].numpy())["counts"]
+            assert runs[i].tolist() == ref
+    # occupancy
+    pts = torch.as_tensor(rng.integers(0, 1024, (200, 2)).astype(np.int32))
+    flag = torch.tensor([1, 0, 1, 1, 0, 0], dtype=torch.uint8)
+    occ = o.points_occupied(masks.to(DEV), flag.to(DEV), pts.to(DEV)).cpu().bool()
+    ref = masks[flag.bool()].any(0)[pts[:, 1].long(), pts[:, 0].long()]
+    assert torch.equal(occ, ref)
+    # mask overlap on nearest-resized 150x150 masks (crowdsam/utils.py:431)
+    inter, area = o.mask_overlap(masks.to(DEV))
+    small = torch.nn.functional.interpolate(masks.float().unsqueeze(0), (150, 150))[0].bool()
+    ref_i = (small[:, None] & small[None]).flatten(2).sum(-1)
+    assert torch.equal(inter.cpu().long(), ref_i) and torch.equal(area.cpu().long(), small.flatten(1).sum(1))

@@ -1,0 +1,165 @@
+"""GPU parity of the full hot path against the CPU oracle (oracle/restate.py, pinned to the reference by
+tests/golden) and against the committed golden vectors of the real reference.
+
+Tolerance (north_star): 1e-3.  Stated here as max|a-b| <= 1e-3 * max|b| per tensor in the default
+'x3' precision mode (fp16 hi/lo split, fp32 accumulate); measured errors are ~1e-5.  Boxes / NMS indices
+are bit-exact; bool masks may differ only on pixels whose logit is within 1e-4 of the threshold.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import restate, weights  # noqa: E402
+
+DEV = "cuda"
+TOL = 1e-3
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+_cache = {}
+
+
+def make_predictor(arch, dino_arch="tiny"):
+    key = (arch, dino_arch, os.environ.get("CSAM_PRECISION", "x3"))
+    if key in _cache:
+        return _cache[key]
+    from crowdsam_b200.build import _build_sam
+    from crowdsam_b200.modules import DinoVisionTransformer
+    from crowdsam_b200.predictor import SamPredictor
+
+    D, depth, heads, glob = weights.SAM_ARCHS[arch]
+    sam_sd, dino_sd = weights.make_sam_state(arch), weights.make_dino_state(dino_arch)
+    sam = _build_sam(D, depth, heads, 1, glob)
+    sam.load_state_dict(sam_sd, strict=True)
+    dD, ddepth, dheads = weights.DINO_ARCHS[dino_arch]
+    dino = DinoVisionTransformer(dD, ddepth, dheads)
+    dino.load_state_dict(dino_sd, strict=True)
+    pred = SamPredictor(sam.to(DEV), dino.to(DEV))
+    _cache[key] = (pred, sam_sd, dino_sd, (depth, heads, glob), (ddepth, dheads))
+    return _cache[key]
+
+
+@pytest.mark.parametrize("arch", ["tiny", "tiny_l"])
+def test_set_image_vs_oracle_and_golden(arch, golden_dir):
+    pred, sam_sd, dino_sd, scfg, dcfg = make_predictor(arch)
+    img = weights.synthetic_image(0)
+    pred.set_image(img)
+    t = torch.as_tensor(img).permute(2, 0, 1)[None]
+    feats, dino = restate.set_image(sam_sd, dino_sd, t, scfg, dcfg)
+    assert pred.features.shape == (1, 256, 64, 64) and pred.dino_feats.shape == (1, 73, 73, 1024)
+    assert _rel(pred.features, feats) < TOL, _rel(pred.features, feats)
+    assert _rel(pred.dino_feats, dino) < TOL, _rel(pred.dino_feats, dino)
+    g = np.load(os.path.join(golden_dir, f"model_{arch}.npz"))
+    assert _rel(pred.features[:, ::8, ::2, ::2], g["features"]) < TOL
+    assert _rel(pred.dino_feats[:, ::6, ::6, ::8], g["dino_feats"]) < TOL
+    assert _rel(pred.predict_fg_map()[:, :, ::4, ::4], g["fg_map"]) < TOL
+    assert _rel(pred.model.prompt_encoder.get_dense_pe()[:, ::4, ::4, ::4], g["dense_pe"]) < 1e-5
+    # decoder on the golden prompts
+    pts = g["points"]
+    coords = torch.as_tensor(pred.transform.apply_coords(pts, pred.original_size))[:, None, :]
+    labels = torch.ones(len(pts), dtype=torch.int)[:, None]
+    masks, iou, cls, low = pred.predict_torch(coords, labels, multimask_output=True, return_logits=True)
+    assert _rel(low[:, :, ::8, ::8], g["low_res"]) < TOL, _rel(low[:, :, ::8, ::8], g["low_res"])
+    assert _rel(iou, g["iou_pred"]) < TOL and _rel(cls, g["cls"]) < TOL
+    assert _rel(masks[:, :, ::32, ::32], g["masks"]) < TOL
+    bm = pred.predict_torch(coords, labels, multimask_output=True, return_logits=False)[0]
+    assert bm.dtype == torch.bool and ((bm != (masks > 0)) & (masks.abs() > 1e-4)).sum() == 0
+    one = pred.predict_torch(coords, labels, multimask_output=False, return_logits=True)
+    assert one[0].shape[1] == 1 and one[1].shape == (len(pts), 1)
+
+
+def test_decoder_teacher_forced():
+    """Decoder alone, fed the ORACLE's embeddings through the assignable predictor state (the path
+    tools/train.py uses), so decoder error is measured without encoder error."""
+    pred, sam_sd, dino_sd, scfg, dcfg = make_predictor("tiny")
+    img = weights.synthetic_image(3)
+    t = torch.as_tensor(img).permute(2, 0, 1)[None]
+    feats, dino = restate.set_image(sam_sd, dino_sd, t, scfg, dcfg)
+    pred.reset_image()
+    pred.features, pred.dino_feats = feats.to(DEV), dino.to(DEV)
+    pred.original_size, pred.input_size, pred.is_image_set = (1024, 1024), (1024, 1024), True
+    pts = np.array([[100, 200], [700, 40], [512, 900], [5, 1000], [1023, 0], [333, 333], [64, 64]])
+    coords = torch.as_tensor(pred.transform.apply_coords(pts, (1024, 1024)))[:, None, :]
+    labels = torch.ones(len(pts), dtype=torch.int)[:, None]
+    low, iou, cls = pred.decode_low_res(coords, labels)
+    sparse = restate.embed_points(sam_sd, coords, labels)
+    rl, ri, rc = restate.mask_decoder(sam_sd, feats, restate.dense_pe(sam_sd), sparse, dino)
+    assert _rel(low, rl) < TOL, _rel(low, rl)
+    assert _rel(iou, ri) < TOL and _rel(cls, rc) < TOL, (_rel(iou, ri), _rel(cls, rc))
+    assert _rel(pred.predict_fg_map(), restate.fg_map(sam_sd, dino)) < TOL
+
+
+def test_non_square_image_vs_golden(golden_dir):
+    pred, *_ = make_predictor("tiny")
+    g = np.load(os.path.join(golden_dir, "model_tiny.npz"))
+    img = weights.synthetic_image(1, 600, 900)
+    pred.set_image(img)
+    assert pred.input_size == (683, 1024) and pred.original_size == (600, 900)
+    assert _rel(pred.features[:, ::8, ::2, ::2], g["ns_features"]) < TOL
+    pts = g["ns_points"]
+    coords = torch.as_tensor(pred.transform.apply_coords(pts, pred.original_size))[:, None, :]
+    labels = torch.ones(len(pts), dtype=torch.int)[:, None]
+    masks, iou, cls, low = pred.predict_torch(coords, labels, multimask_output=True, return_logits=True)
+    assert masks.shape == (3, 4, 600, 900)
+    assert _rel(low[:, :, ::8, ::8], g["ns_low_res"]) < TOL
+    assert _rel(masks[:, :, ::24, ::36], g["ns_masks"]) < TOL
+    assert _rel(iou, g["ns_iou_pred"]) < TOL
+
+
+def _decode_coco(s, size):
+    from tests.test_oracle_golden import _decode_coco as d
+
+    return d(s, size)
+
+
+@pytest.mark.parametrize("name", ["tiny_grid8", "tiny_eps"])
+def test_crowdsam_generate_vs_golden_and_oracle(name, golden_dir):
+    from crowdsam_b200.pipeline import CrowdSAM
+
+    pred, sam_sd, dino_sd, scfg, dcfg = make_predictor("tiny")
+    g = np.load(os.path.join(golden_dir, f"pipeline_{name}.npz"))
+    over = {}
+    for k, v in zip(g["cfg_keys"], g["cfg_vals"]):
+        try:
+            over[str(k)] = int(str(v))
+        except ValueError:
+            over[str(k)] = float(str(v))
+    test_cfg = dict(restate.DEFAULT_TEST_CFG)
+    test_cfg.update(over)
+    test_cfg.update(apply_box_offsets=False, fuse_simmap=False, output_rles=True)
+    cfg = {"environ": {"device": DEV}, "model": {"trainfree": False}, "test": test_cfg}
+    model = CrowdSAM(cfg, None, predictor=pred)
+    hw = tuple(int(x) for x in g["hw"])
+    img = weights.synthetic_image(int(g["image_index"]), *hw)
+    np.random.seed(42)
+    res = model.generate(img)
+    assert set(["points", "categories", "stability_score", "boxes", "scores", "rles", "rles_info", "crop_boxes", "fboxes"]) <= set(dict(res.items()).keys())
+    np.testing.assert_array_equal(res["boxes"], g["boxes"])
+    np.testing.assert_array_equal(res["points"], g["points"])
+    np.testing.assert_array_equal(res["categories"], g["categories"])
+    np.testing.assert_allclose(res["scores"], g["scores"], rtol=TOL, atol=1e-5)
+    np.testing.assert_allclose(res["stability_score"], g["stability_score"], rtol=TOL, atol=1e-5)
+    for r, ref in zip(res["rles"], g["rle_counts"]):
+        a, b = _decode_coco(r["counts"], r["size"]), _decode_coco(str(ref), r["size"])
+        assert (a != b).mean() < 1e-4
+
+
+def test_errors_and_state():
+    pred, *_ = make_predictor("tiny")
+    pred.reset_image()
+    with pytest.raises(RuntimeError):
+        pred.predict_torch(torch.zeros(1, 1, 2), torch.ones(1, 1))
+    with pytest.raises(RuntimeError):
+        pred.get_image_embedding()
+    with pytest.raises(AssertionError):
+        pred.set_image(np.zeros((10, 10, 3), np.uint8), image_format="XYZ")
+    with pytest.raises(AssertionError):
+        pred.set_torch_image(torch.zeros(1, 3, 100, 100, dtype=torch.uint8), (100, 100))
