@@ -129,7 +129,7 @@ class DinoEncoder:
         self.D, self.hd = D, D // heads
         self.patch = _Lin(sd, "patch_embed.proj", dev, split, kpad=592)
         # interpolate_pos_encoding (vision_transformer.py:179-211): per-resolution constant, built once
-        pe = sd["pos_embed"].detach().float()
+        pe = sd["pos_embed"].detach().float().cpu()
         N = pe.shape[1] - 1
         M = int(math.sqrt(N))
         s = float(73 + 0.1) / M
@@ -137,7 +137,7 @@ class DinoEncoder:
                                                    antialias=False, scale_factor=(s, s))
         assert patch_pe.shape[-2:] == (73, 73)
         self.pos_patch = patch_pe.permute(0, 2, 3, 1).reshape(73 * 73, D).contiguous().to(dev)
-        self.cls_row = (sd["cls_token"].detach().float().reshape(1, D) + pe[0, :1]).contiguous().to(dev)
+        self.cls_row = (sd["cls_token"].detach().float().cpu().reshape(1, D) + pe[0, :1]).contiguous().to(dev)
         self.blocks = []
         for i in range(depth):
             b = f"blocks.{i}"
@@ -209,7 +209,7 @@ class MaskDecoderEngine:
         self.no_mask = _f(sd, f"{pe}.no_mask_embed.weight", dev).reshape(1, 256)
         self.tok5 = torch.cat([_f(sd, f"{m}.iou_token.weight", dev), _f(sd, f"{m}.mask_tokens.weight", dev)], 0).contiguous()
         # dense PE (prompt_encoder.py:64-73,198-209) is a constant of the weights: built once at load
-        g = sd[f"{pe}.pe_layer.positional_encoding_gaussian_matrix"].detach().float()
+        g = sd[f"{pe}.pe_layer.positional_encoding_gaussian_matrix"].detach().float().cpu()
         grid = torch.ones((64, 64), dtype=torch.float32)
         yy = (grid.cumsum(dim=0) - 0.5) / 64
         xx = (grid.cumsum(dim=1) - 0.5) / 64

@@ -430,6 +430,27 @@ def coco_encode_rle(rle: Dict) -> Dict:
     return {"size": [h, w], "counts": coco_rle_string(rle["counts"])}
 
 
+def coco_rle_decode(s: str, size) -> np.ndarray:
+    """Inverse of coco_rle_string (COCO API rleFrString) followed by rle_to_mask."""
+    counts: List[int] = []
+    p, m = 0, 0
+    while p < len(s):
+        x, k, more = 0, 0, True
+        while more:
+            c = ord(s[p]) - 48
+            x |= (c & 0x1F) << (5 * k)
+            more = bool(c & 0x20)
+            p += 1
+            k += 1
+            if not more and (c & 0x10):
+                x |= -1 << (5 * k)
+        if m > 2:
+            x += counts[m - 2]
+        counts.append(x)
+        m += 1
+    return rle_to_mask({"size": list(size), "counts": counts})
+
+
 def rle_to_mask(rle: Dict) -> np.ndarray:
     """Inverse of mask_to_rle (amg.py:138-150)."""
     h, w = rle["size"]

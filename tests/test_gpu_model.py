@@ -115,9 +115,7 @@ def test_non_square_image_vs_golden(golden_dir):
 
 
 def _decode_coco(s, size):
-    from tests.test_oracle_golden import _decode_coco as d
-
-    return d(s, size)
+    return restate.coco_rle_decode(s, size)
 
 
 @pytest.mark.parametrize("name", ["tiny_grid8", "tiny_eps"])

@@ -116,23 +116,7 @@ def test_pipeline_generate(name, golden_dir):
 
 
 def _decode_coco(s, size):
-    """Inverse of restate.coco_rle_string (COCO API rleFrString)."""
-    counts, p, m = [], 0, 0
-    while p < len(s):
-        x, k, more = 0, 0, True
-        while more:
-            c = ord(s[p]) - 48
-            x |= (c & 0x1F) << (5 * k)
-            more = bool(c & 0x20)
-            p += 1
-            k += 1
-            if not more and (c & 0x10):
-                x |= -1 << (5 * k)
-        if m > 2:
-            x += counts[m - 2]
-        counts.append(x)
-        m += 1
-    return restate.rle_to_mask({"size": size, "counts": counts})
+    return restate.coco_rle_decode(s, size)
 
 
 def test_stage_post_nms_rle(golden_dir):
