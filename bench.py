@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of the Crowd-SAM hot path on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): SAM ViT-L random-init ("recipe v1" synthetic weights),
+DINOv2 ViT-L/14, one synthetic 1024x1024 image per step, 32x32 point grid = 1024 prompts through the
+batched mask decoder, PWD-Net scoring, stability / IoU filters, K-POST masks, box NMS.
+A step = one image.  Reported on one JSON line:
+  value   device-resident throughput (uint8 image already in HBM, no mask RLE / D2H)
+  e2e     the same metric through the public API `CrowdSAM.generate(np.ndarray)`: pinned-host image ->
+          H2D every step, full result dict (boxes, scores, COCO RLEs) read back to the host
+  roofline      dominant kernel class, CUDA-event timed inside the timed region
+  cpu_baseline  the CPU oracle port (oracle/restate.py) on a bounded sample of the same workload
+`--impl reference` times the reference's CPU path (oracle port) instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec (1024px, 32x32 prompt grid)"
+UNIT = "images/s"
+WORKLOAD = "vit_l_1024px_grid32_pwd_nms"
+GRID = 32
+ARCH = "vit_l"
+DINO = "dinov2_vitl14"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def test_cfg(points_per_batch: int):
+    """Reference config overrides of SURVEY.md §8d: every grid cell becomes a prompt, EPS never prunes,
+    the OpenCV small-region pass (not on the north_star path) is off; filters keep their YAML defaults."""
+    from oracle.restate import DEFAULT_TEST_CFG
+
+    c = dict(DEFAULT_TEST_CFG)
+    c.update(grid_size=GRID, pos_sim_thresh=-1, max_prompts=GRID * GRID, points_per_batch=points_per_batch,
+             filter_thresh=1e9, min_mask_region_area=0, apply_box_offsets=False, fuse_simmap=False, output_rles=True)
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline leg and --impl reference)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_seconds(sam_sd, dino_sd, image_index: int, frac_blocks: int = 4, n_prompts: int = 8):
+    """Bounded sample of the workload on the host cores with the oracle port: 1/frac of the SAM ViT-L blocks
+    (6 of 24, one of them global = the model's 1:5 mix), 1/frac of the DINOv2 blocks, patch embed + neck,
+    `n_prompts` of the 1024 prompts through decoder + post-processing.  Returns (extrapolated seconds per
+    image, description).  Extrapolation: blocks x frac, prompts x 1024/n_prompts, fixed parts x 1."""
+    import torch
+    from oracle import restate, weights
+
+    D, depth, heads, glob = weights.SAM_ARCHS[ARCH]
+    dD, ddepth, dheads = weights.DINO_ARCHS[DINO]
+    img = torch.as_tensor(weights.synthetic_image(image_index)).permute(2, 0, 1)[None]
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        x = restate.preprocess(img)
+        # SAM encoder with the first depth/frac blocks (global block 5 included)
+        sd = sam_sd
+        feats = restate.sam_encoder(sd, x, depth // frac_blocks, heads, glob)
+        t_sam = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        x2 = torch.nn.functional.interpolate(x, (1022, 1022), mode="bilinear")
+        dino = restate.dino_forward(dino_sd, x2, ddepth // frac_blocks, dheads).view(1, 73, 73, -1)
+        t_dino = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        from oracle import fixtures
+
+        pts = fixtures.grid_points(GRID)[:n_prompts]
+        coords = torch.as_tensor(restate.apply_coords(pts, (1024, 1024)))[:, None, :]
+        labels = torch.ones(n_prompts, dtype=torch.int)[:, None]
+        sparse = restate.embed_points(sd, coords, labels)
+        low, iou, cls = restate.mask_decoder(sd, feats, restate.dense_pe(sd), sparse, dino)
+        full = restate.postprocess_masks(low, (1024, 1024), (1024, 1024))
+        score = torch.clamp(iou, 0.0) * cls.squeeze(2).sigmoid()
+        sel = score.max(dim=-1)[1]
+        m = full[torch.arange(n_prompts), sel]
+        restate.stability_score(m, 0.0, 1.0)
+        boxes = restate.mask_to_box(m > 0.0)
+        restate.nms_reference(boxes.float().numpy(), score.max(dim=-1)[0].numpy(), 0.65)
+        t_dec = time.perf_counter() - t0
+    total = t_sam * frac_blocks + t_dino * frac_blocks + t_dec * (GRID * GRID / n_prompts)
+    desc = (f"oracle port, {depth // frac_blocks}/{depth} SAM ViT-L blocks + {ddepth // frac_blocks}/{ddepth} DINOv2 blocks "
+            f"+ {n_prompts}/{GRID * GRID} prompts (decoder+post+NMS), extrapolated linearly; "
+            f"measured {t_sam:.2f}s+{t_dino:.2f}s+{t_dec:.2f}s")
+    return total, desc
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+    from oracle import weights
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    sam_sd, dino_sd = weights.make_sam_state(ARCH), weights.make_dino_state(DINO)
+    for i in range(args.warmup):
+        cpu_sample_seconds(sam_sd, dino_sd, i)
+    secs, desc = [], ""
+    for i in range(args.steps):
+        s, desc = cpu_sample_seconds(sam_sd, dino_sd, args.warmup + i)
+        secs.append(s)
+    per_img = sum(secs) / len(secs)
+    value = 1.0 / per_img
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per_img * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "arch": ARCH, "grid": GRID, "prompts": GRID * GRID, "device": "cpu"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points-per-batch", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--arch", default=ARCH)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+
+    from crowdsam_b200 import lib, ops
+    from crowdsam_b200.build import _build_sam
+    from crowdsam_b200.modules import DinoVisionTransformer
+    from crowdsam_b200.pipeline import CrowdSAM
+    from crowdsam_b200.predictor import SamPredictor
+    from oracle import weights     # synthetic weight recipe + images only (test infrastructure, not timed)
+
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+    arch = args.arch
+    D, depth, heads, glob = weights.SAM_ARCHS[arch]
+    sam_sd, dino_sd = weights.make_sam_state(arch), weights.make_dino_state(DINO)
+    sam = _build_sam(D, depth, heads, 1, glob)
+    sam.load_state_dict(sam_sd, strict=True)
+    dD, ddepth, dheads = weights.DINO_ARCHS[DINO]
+    dino = DinoVisionTransformer(dD, ddepth, dheads)
+    dino.load_state_dict(dino_sd, strict=True)
+    pred = SamPredictor(sam.to(dev), dino.to(dev))
+    cfg = {"environ": {"device": str(dev)}, "model": {"trainfree": False}, "test": test_cfg(args.points_per_batch)}
+    model = CrowdSAM(cfg, None, predictor=pred)
+
+    n_total = args.warmup + args.steps
+    # per-rank images: rank r owns global images r, r+world, ... (independent units)
+    imgs_np = [weights.synthetic_image(rank + world * i) for i in range(n_total)]
+    pinned = [torch.as_tensor(x).pin_memory() for x in imgs_np]
+    resident = [torch.as_tensor(x).permute(2, 0, 1).contiguous().to(dev) for x in imgs_np]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather_dets(dets):
+        """The one exchange step: all-gather of padded [K, Nmax, 6] detections + counts."""
+        if world == 1:
+            return
+        nmax = 64
+        buf = torch.zeros((len(dets), nmax, 6), device=dev)
+        cnt = torch.zeros((len(dets),), dtype=torch.int32, device=dev)
+        for i, d in enumerate(dets):
+            if d is None:
+                continue
+            n = min(len(d["boxes"]), nmax)
+            buf[i, :n, :4] = torch.as_tensor(d["boxes"][:n], device=dev).float()
+            buf[i, :n, 4] = torch.as_tensor(d["scores"][:n], device=dev).float()
+            buf[i, :n, 5] = torch.as_tensor(d["categories"][:n], device=dev).float()
+            cnt[i] = n
+        out = [torch.empty_like(buf) for _ in range(world)]
+        outc = [torch.empty_like(cnt) for _ in range(world)]
+        dist.all_gather(out, buf)
+        dist.all_gather(outc, cnt)
+
+    # ---------------- device-resident leg (value) ----------------
+    for i in range(args.warmup):
+        np.random.seed(42)
+        model.run_resident(resident[i])
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.PROFILER = ops.Profiler()
+    l0 = lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dets, nk = [], (0, 0)
+    ev0.record()
+    for i in range(args.steps):
+        np.random.seed(42)
+        d = model.run_resident(resident[args.warmup + i])
+        nk = model.last_counts
+        dets.append(None if d is None else {"boxes": d["boxes"], "scores": d["scores"], "categories": d["categories"]})
+    gather_dets(dets)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    print(f"[bench rank {rank}] resident leg: {ms_total / args.steps:.1f} ms/step, masks into NMS {nk[0]}, kept {nk[1]}",
+          file=sys.stderr)
+    launches = lib.launch_count() - l0
+    prof = ops.PROFILER.summary()
+    ops.PROFILER = None
+    clocks = sampler.stop()
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * args.steps / (ms_total / 1e3)
+
+    # ---------------- end-to-end leg through the public API ----------------
+    for i in range(min(args.warmup, 3)):
+        np.random.seed(42)
+        model.generate(imgs_np[i])
+    barrier()
+    d2h = 0
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        np.random.seed(42)
+        res = model.generate(pinned[args.warmup + i].numpy())
+        d2h = sum(np.asarray(v).nbytes for k, v in res.items() if isinstance(v, np.ndarray)) + \
+            sum(len(r["counts"]) for r in res["rles"])
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3 * 0.0)
+    t = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / (float(t.item()) / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+
+    def roof(name, bound):
+        r = prof.get(name)
+        if not r or r["total_ms"] <= 0:
+            return None
+        per_launch_ms = r["total_ms"] / r["launches"]
+        if bound == "tensor":
+            ach = r["work"] / (r["total_ms"] * 1e-3) / 1e12
+            peak, unit = peaks["tf_sustained"], "TFLOP/s"
+        else:
+            ach = r["work"] / (r["total_ms"] * 1e-3) / 1e9
+            peak, unit = peaks["hbm_gbs"], "GB/s"
+        return {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                "traffic": None, "launches_per_step": r["launches"] / args.steps, "avg_launch_ms": per_launch_ms,
+                "share_of_step": r["total_ms"] / ms_total, "peak_source": peaks["source"]}
+
+    roofs = [x for x in (roof("gemm", "tensor"), roof("vit_attention", "tensor"), roof("mask_post_write", "hbm"),
+                         roof("mask_post_stats", "hbm")) if x]
+    dominant = max(roofs, key=lambda r: r["share_of_step"]) if roofs else None
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        torch.set_num_threads(os.cpu_count() or 1)
+        secs, desc = cpu_sample_seconds(sam_sd, dino_sd, 0)
+        cpu = {"value": 1.0 / secs, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": desc}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16x3(fp32-accurate hi/lo split), fp32 accumulate" if os.environ.get("CSAM_PRECISION", "x3") != "x1" else "f16, fp32 accumulate",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "arch": arch, "dino": DINO, "grid": GRID, "prompts": GRID * GRID,
+                       "points_per_batch": args.points_per_batch, "masks_into_nms": nk[0], "detections": nk[1],
+                       "l2": "working set (weights 2.5 GB + per-batch activations > 10 GB) far exceeds the 126 MB L2",
+                       "parallelism": f"images sharded one per rank x{world}, all-gather of detections"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(imgs_np[0].nbytes),
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": dominant, "rooflines": roofs,
+            "kernel_ms_per_step": {k: v["total_ms"] / args.steps for k, v in prof.items()},
+            "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -60,7 +60,7 @@ class MaskData:
         for k, v in other.items():
             cur = self._stats.get(k)
             if cur is None:
-                self._stats[k] = deepcopy(v)
+                self._stats[k] = v if isinstance(v, torch.Tensor) else deepcopy(v)
             elif isinstance(v, torch.Tensor):
                 self._stats[k] = torch.cat([cur, v], dim=0)
             elif isinstance(v, np.ndarray):
@@ -69,6 +69,23 @@ class MaskData:
                 self._stats[k] = cur + deepcopy(v)
             else:
                 raise TypeError(f"MaskData key {k} has an unsupported type {type(v)}.")
+
+    @staticmethod
+    def merged(parts: "List[MaskData]") -> "MaskData":
+        """Concatenate many batches with ONE copy per field (cat() in a loop re-copies the growing
+        [N,H,W] mask tensor every batch)."""
+        out = MaskData()
+        if not parts:
+            return out
+        for k in parts[0]._stats:
+            vals = [p._stats[k] for p in parts]
+            if isinstance(vals[0], torch.Tensor):
+                out._stats[k] = vals[0] if len(vals) == 1 else torch.cat(vals, dim=0)
+            elif isinstance(vals[0], np.ndarray):
+                out._stats[k] = np.concatenate(vals, axis=0)
+            else:
+                out._stats[k] = [x for v in vals for x in v]
+        return out
 
     def to_numpy(self) -> None:
         for k, v in self._stats.items():

@@ -290,16 +290,21 @@ __global__ void __launch_bounds__(256) attn_few_queries_kernel(csam_dec_attn_arg
   }
 }
 
+// fills a->scratch with the decomposed rel-pos terms [groups*heads*tokens, 2S] (shared by both attention paths)
+int compute_relpos(const csam_attn_args* a, cudaStream_t st) {
+  CSAM_REQUIRE(a->S * a->S == a->tokens, "csam_vit_attention: rel-pos needs tokens == S*S");
+  const long long need = csam_vit_attention_scratch_bytes(a->groups, a->tokens, a->heads, a->hd, a->S);
+  CSAM_REQUIRE(a->scratch && a->scratch_bytes >= need, "csam_vit_attention: scratch too small");
+  relpos_kernel<<<148 * 8, 256, 0, st>>>(static_cast<const __half*>(a->qkv_hi), static_cast<const __half*>(a->qkv_lo),
+                                         a->ld_qkv, a->groups, a->tokens, a->heads, a->hd, a->rel_h, a->rel_w, a->S,
+                                         a->scratch);
+  return check_launch("relpos_kernel");
+}
+
 int vit_attention_simt(const csam_attn_args* a, cudaStream_t st) {
   const float* rel = nullptr;
   if (a->rel_h) {
-    CSAM_REQUIRE(a->S * a->S == a->tokens, "csam_vit_attention: rel-pos needs tokens == S*S");
-    const long long need = csam_vit_attention_scratch_bytes(a->groups, a->tokens, a->heads, a->hd, a->S);
-    CSAM_REQUIRE(a->scratch && a->scratch_bytes >= need, "csam_vit_attention: scratch too small");
-    relpos_kernel<<<148 * 8, 256, 0, st>>>(static_cast<const __half*>(a->qkv_hi), static_cast<const __half*>(a->qkv_lo),
-                                           a->ld_qkv, a->groups, a->tokens, a->heads, a->hd, a->rel_h, a->rel_w, a->S,
-                                           a->scratch);
-    if (check_launch("relpos_kernel")) return 1;
+    if (compute_relpos(a, st)) return 1;
     rel = a->scratch;
   }
   dim3 grid((a->tokens + 31) / 32, a->heads, a->groups);

@@ -1,10 +1,331 @@
-// attention_tc.cu — tcgen05 ViT attention (K-WATTN / K-GATTN).  Placeholder dispatch until the
-// tensor-core kernel lands: fail loudly rather than silently computing on another path.
+// attention_tc.cu — K-WATTN / K-GATTN: flash attention on tcgen05 tensor cores (head dim 64).
+//
+// One CTA = 128 queries of one (group, head); keys stream through in tiles of 64.
+//   warp 0      TMA producer   Q once, then K/V tiles into a 3-stage ring (128B-swizzled boxes)
+//   warp 1      MMA issuer     S = Q K^T  (M128 N64 K64, both operands K-major)  -> TMEM S[2]
+//                              O_j = P V  (M128 N64 K64, V is the MN-major B operand) -> TMEM O[2]
+//   warp 2      TMEM allocator
+//   warps 4..7  softmax        one thread per query row: tcgen05.ld S, scale + decomposed rel-pos
+//                              bias, online softmax in fp32, P written to shared memory as an fp16
+//                              hi/lo pair in the UMMA K-major swizzled layout, O accumulated in
+//                              registers with the usual rescale.
+// S(j+1) is issued before softmax(j) finishes (two S buffers), so the tensor pipe overlaps the
+// exponentials.  With the hi/lo split every product is 3 MMAs (fp32-level accuracy).
+// Reference: image_encoder.py:224-240,325-361; dinov2/layers/attention.py:56-69.
 #include "common.cuh"
+
 namespace csam {
-int vit_attention_simt(const csam_attn_args* a, cudaStream_t st);
-int vit_attention_tc(const csam_attn_args* a, cudaStream_t st) {
-  (void)a; (void)st;
-  return fail("%s", "csam_vit_attention: tcgen05 implementation not built yet (use impl=1)");
+
+int compute_relpos(const csam_attn_args* a, cudaStream_t st);   // attention_simt.cu
+
+constexpr int AT_BM = 128, AT_BN = 64, AT_HD = 64, AT_STAGES = 3, AT_THREADS = 256;
+constexpr int AT_REL_LD = 29;   // 28 rel-pos values per query (S = 14) padded to an odd stride
+
+template <int SPLIT>
+struct AttnCfg {
+  static constexpr int NOPS = (SPLIT == 3) ? 2 : 1;
+  static constexpr int Q_BYTES = AT_BM * AT_HD * 2;          // 16 KB per operand half
+  static constexpr int KV_TILE = AT_BN * AT_HD * 2;          // 8 KB
+  static constexpr int STAGE_BYTES = NOPS * 2 * KV_TILE;     // K(hi,lo) then V(hi,lo)
+  static constexpr int P_BYTES = AT_BM * AT_BN * 2;          // 16 KB per operand half
+  static constexpr int OFF_KV = NOPS * Q_BYTES;
+  static constexpr int OFF_P = OFF_KV + AT_STAGES * STAGE_BYTES;
+  static constexpr int OFF_REL = OFF_P + 2 * NOPS * P_BYTES;
+  static constexpr int OFF_BAR = OFF_REL + AT_BM * AT_REL_LD * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+};
+
+struct AttnBars {
+  uint64_t q_full;
+  uint64_t kv_full[AT_STAGES], kv_empty[AT_STAGES];
+  uint64_t s_full[2], s_empty[2], p_full[2], o_full[2], o_empty[2];
+  uint32_t tmem_slot;
+};
+
+// BIAS: 0 none, 1 window (S = 14, table in shared memory), 2 global (S = 64 == key tile, registers)
+template <int SPLIT, int BIAS>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_constant__ CUtensorMap t_lo,
+                        csam_attn_args a, const float* __restrict__ rel) {
+  using Cfg = AttnCfg<SPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  AttnBars* bars = reinterpret_cast<AttnBars*>(smem + Cfg::OFF_BAR);
+  float* rel_s = reinterpret_cast<float*>(smem + Cfg::OFF_REL);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AT_BM;
+  const int D = a.heads * AT_HD;
+  const int row_base = g * a.tokens;
+  const int n_tiles = (a.tokens + AT_BN - 1) / AT_BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&t_hi);
+    if (SPLIT == 3) tma_prefetch_desc(&t_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&bars->q_full, 1);
+    for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&bars->kv_full[s], 1); mbar_init(&bars->kv_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->s_full[b], 1); mbar_init(&bars->s_empty[b], 128);
+      mbar_init(&bars->p_full[b], 128);
+      mbar_init(&bars->o_full[b], 1); mbar_init(&bars->o_empty[b], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<256>(&bars->tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_slot;   // columns: S0 [0,64) S1 [64,128) O0 [128,192) O1 [192,256)
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(&bars->q_full, Cfg::NOPS * Cfg::Q_BYTES);
+      for (int half = 0; half < 2; ++half) {
+        tma_load_2d(smem + half * 8192, &t_hi, &bars->q_full, h * AT_HD, row_base + q0 + half * 64);
+        if (SPLIT == 3) tma_load_2d(smem + Cfg::Q_BYTES + half * 8192, &t_lo, &bars->q_full, h * AT_HD, row_base + q0 + half * 64);
+      }
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % AT_STAGES;
+        const uint32_t ph = (j / AT_STAGES) & 1;
+        mbar_wait(&bars->kv_empty[st], ph ^ 1);
+        uint8_t* sk = smem + Cfg::OFF_KV + st * Cfg::STAGE_BYTES;
+        uint8_t* sv = sk + Cfg::NOPS * Cfg::KV_TILE;
+        mbar_expect_tx(&bars->kv_full[st], Cfg::STAGE_BYTES);
+        const int row = row_base + j * AT_BN;
+        tma_load_2d(sk, &t_hi, &bars->kv_full[st], D + h * AT_HD, row);
+        tma_load_2d(sv, &t_hi, &bars->kv_full[st], 2 * D + h * AT_HD, row);
+        if (SPLIT == 3) {
+          tma_load_2d(sk + Cfg::KV_TILE, &t_lo, &bars->kv_full[st], D + h * AT_HD, row);
+          tma_load_2d(sv + Cfg::KV_TILE, &t_lo, &bars->kv_full[st], 2 * D + h * AT_HD, row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(AT_BM, AT_BN, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(AT_BM, AT_HD, 0, 1);
+      const uint32_t sq = smem_u32(smem);
+      auto issue_s = [&](int j) {
+        const int st = j % AT_STAGES;
+        mbar_wait(&bars->kv_full[st], (j / AT_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t sk = smem_u32(smem + Cfg::OFF_KV + st * Cfg::STAGE_BYTES);
+        const uint32_t d = tmem_base + (j & 1) * AT_BN;
+#pragma unroll
+        for (int k = 0; k < AT_HD / 16; ++k) {
+          const uint64_t q_hi = umma_desc_sw128(sq + k * 32, 16, 1024);
+          const uint64_t k_hi = umma_desc_sw128(sk + k * 32, 16, 1024);
+          umma_f16(d, q_hi, k_hi, idesc_s, k ? 1u : 0u);
+          if (SPLIT == 3) {
+            const uint64_t q_lo = umma_desc_sw128(sq + Cfg::Q_BYTES + k * 32, 16, 1024);
+            const uint64_t k_lo = umma_desc_sw128(sk + Cfg::KV_TILE + k * 32, 16, 1024);
+            umma_f16(d, q_lo, k_hi, idesc_s, 1u);
+            umma_f16(d, q_hi, k_lo, idesc_s, 1u);
+          }
+        }
+        umma_commit(&bars->s_full[j & 1]);
+      };
+      mbar_wait(&bars->q_full, 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int b = j & 1;
+        const uint32_t use = (j >> 1) & 1;
+        if (j + 1 < n_tiles) {
+          mbar_wait(&bars->s_empty[(j + 1) & 1], (((j + 1) >> 1) & 1) ^ 1);
+          tc_fence_after();
+          issue_s(j + 1);
+        }
+        mbar_wait(&bars->p_full[b], use);
+        mbar_wait(&bars->o_empty[b], use ^ 1);
+        tc_fence_after();
+        const int st = j % AT_STAGES;
+        const uint32_t sv = smem_u32(smem + Cfg::OFF_KV + st * Cfg::STAGE_BYTES + Cfg::NOPS * Cfg::KV_TILE);
+        const uint32_t sp = smem_u32(smem + Cfg::OFF_P + b * Cfg::NOPS * Cfg::P_BYTES);
+        const uint32_t d = tmem_base + 128 + b * AT_HD;
+#pragma unroll
+        for (int k = 0; k < AT_BN / 16; ++k) {
+          const uint64_t p_hi = umma_desc_sw128(sp + k * 32, 16, 1024);
+          const uint64_t v_hi = umma_desc_sw128(sv + k * 2048, 8192, 1024);
+          umma_f16(d, p_hi, v_hi, idesc_pv, k ? 1u : 0u);
+          if (SPLIT == 3) {
+            const uint64_t p_lo = umma_desc_sw128(sp + Cfg::P_BYTES + k * 32, 16, 1024);
+            const uint64_t v_lo = umma_desc_sw128(sv + Cfg::KV_TILE + k * 2048, 8192, 1024);
+            umma_f16(d, p_lo, v_hi, idesc_pv, 1u);
+            umma_f16(d, p_hi, v_lo, idesc_pv, 1u);
+          }
+        }
+        umma_commit(&bars->o_full[b]);
+        umma_commit(&bars->kv_empty[st]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax / accumulate
+    const int r = (warp - 4) * 32 + lane;          // query row in the tile == TMEM lane
+    const int q = q0 + r;
+    const int qc = min(q, a.tokens - 1);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp - 4) * 32) << 16);
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float scale2 = a.scale * LOG2E;
+    float relw[BIAS == 2 ? 64 : 1];
+    const float* relq = nullptr;
+    if (BIAS != 0) relq = rel + (((size_t)g * a.heads + h) * a.tokens + qc) * 2 * a.S;
+    if (BIAS == 2) {
+#pragma unroll
+      for (int c = 0; c < 64; ++c) relw[c] = relq[64 + c] * LOG2E;
+    }
+    if (BIAS == 1) {
+      for (int i = 0; i < 28; ++i) rel_s[r * AT_REL_LD + i] = relq[i] * LOG2E;
+    }
+    float acc[AT_HD];
+#pragma unroll
+    for (int d = 0; d < AT_HD; ++d) acc[d] = 0.f;
+    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+
+    auto accumulate_o = [&](int j, float alpha) {
+      const int b = j & 1;
+      mbar_wait(&bars->o_full[b], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t o[64];
+      tmem_ld32(lane_addr + 128 + b * AT_HD, o);
+      tmem_ld32(lane_addr + 128 + b * AT_HD + 32, o + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&bars->o_empty[b]);
+#pragma unroll
+      for (int d = 0; d < AT_HD; ++d) acc[d] = fmaf(acc[d], alpha, __uint_as_float(o[d]));
+    };
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int b = j & 1;
+      mbar_wait(&bars->s_full[b], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t raw[64];
+      tmem_ld32(lane_addr + b * AT_BN, raw);
+      tmem_ld32(lane_addr + b * AT_BN + 32, raw + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&bars->s_empty[b]);
+      float s[64];
+      float tmax = -INFINITY;
+      const int key0 = j * AT_BN;
+      if (BIAS == 2) {
+        const float bh = relq[j] * LOG2E;           // key tile j == key row kh = j (S == 64)
+#pragma unroll
+        for (int c = 0; c < 64; ++c) s[c] = fmaf(__uint_as_float(raw[c]), scale2, bh + relw[c]);
+      } else if (BIAS == 1) {
+        int kh = key0 / 14, kw = key0 % 14;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          const int khc = min(kh, 13);
+          s[c] = fmaf(__uint_as_float(raw[c]), scale2, rel_s[r * AT_REL_LD + khc] + rel_s[r * AT_REL_LD + 14 + kw]);
+          if (++kw == 14) { kw = 0; ++kh; }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) s[c] = __uint_as_float(raw[c]) * scale2;
+      }
+      if (key0 + AT_BN > a.tokens) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (key0 + c >= a.tokens) s[c] = -INFINITY;
+      }
+#pragma unroll
+      for (int c = 0; c < 64; ++c) tmax = fmaxf(tmax, s[c]);
+      const float m_new = fmaxf(m, tmax);
+      const float alpha = exp2f(m - m_new);
+      float psum = 0.f;
+      uint8_t* pb = smem + Cfg::OFF_P + b * Cfg::NOPS * Cfg::P_BYTES + r * 128;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        __align__(16) __half hi8[8];
+        __align__(16) __half lo8[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float p = exp2f(s[u * 8 + t] - m_new);
+          psum += p;
+          hi8[t] = __float2half_rn(p);
+          lo8[t] = __float2half_rn(p - __half2float(hi8[t]));
+        }
+        const int off = (u ^ (r & 7)) << 4;
+        *reinterpret_cast<uint4*>(pb + off) = *reinterpret_cast<const uint4*>(hi8);
+        if (SPLIT == 3) *reinterpret_cast<uint4*>(pb + Cfg::P_BYTES + off) = *reinterpret_cast<const uint4*>(lo8);
+      }
+      l = fmaf(l, alpha, psum);
+      m = m_new;
+      fence_proxy_async();                 // generic-proxy writes of P -> visible to the tensor core
+      mbar_arrive(&bars->p_full[b]);
+      if (j > 0) accumulate_o(j - 1, alpha_prev);
+      alpha_prev = alpha;
+    }
+    accumulate_o(n_tiles - 1, alpha_prev);
+    if (q < a.tokens) {
+      const float inv = 1.0f / l;
+      __half* ohi = static_cast<__half*>(a.out_hi);
+      __half* olo = static_cast<__half*>(a.out_lo);
+      const size_t oo = ((size_t)row_base + q) * a.ld_out + (size_t)h * AT_HD;
+#pragma unroll
+      for (int d = 0; d < AT_HD; d += 8) {
+        float v8[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v8[t] = acc[d + t] * inv;
+        store_pair8(ohi, olo, oo + d, v8);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<256>(tmem_base);
 }
+
+template <int SPLIT, int BIAS>
+static int launch_attn_tc(const csam_attn_args* a, const float* rel, cudaStream_t st) {
+  using Cfg = AttnCfg<SPLIT>;
+  CUtensorMap t_hi, t_lo;
+  const uint64_t rows = (uint64_t)a->groups * a->tokens;
+  const uint64_t cols = 3ull * a->heads * a->hd;
+  if (make_tmap_2d_f16(&t_hi, a->qkv_hi, rows, cols, a->ld_qkv, 64, 64)) return 1;
+  t_lo = t_hi;
+  if (SPLIT == 3 && make_tmap_2d_f16(&t_lo, a->qkv_lo, rows, cols, a->ld_qkv, 64, 64)) return 1;
+  auto kern = vit_attention_tc_kernel<SPLIT, BIAS>;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+      return fail("%s", "cudaFuncSetAttribute(smem) failed for vit_attention_tc_kernel");
+    attr = true;
+  }
+  dim3 grid((a->tokens + AT_BM - 1) / AT_BM, a->heads, a->groups);
+  kern<<<grid, AT_THREADS, Cfg::SMEM_BYTES, st>>>(t_hi, t_lo, *a, rel);
+  return check_launch("vit_attention_tc_kernel");
+}
+
+int vit_attention_tc(const csam_attn_args* a, cudaStream_t st) {
+  CSAM_REQUIRE(a->hd == 64, "csam_vit_attention(tcgen05): head dim 64 only (use impl=1 for others)");
+  CSAM_REQUIRE((a->ld_qkv % 8) == 0 && (a->ld_out % 8) == 0, "csam_vit_attention: strides must be multiples of 8");
+  CSAM_REQUIRE((reinterpret_cast<uintptr_t>(a->qkv_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->out_hi) & 15) == 0,
+               "csam_vit_attention: 16-byte alignment");
+  const bool split = a->qkv_lo != nullptr;
+  CSAM_REQUIRE(!split || a->out_lo, "csam_vit_attention: split input needs split output");
+  int bias = 0;
+  const float* rel = nullptr;
+  if (a->rel_h) {
+    CSAM_REQUIRE(a->S == 14 || a->S == 64, "csam_vit_attention(tcgen05): S must be 14 (window) or 64 (global)");
+    if (compute_relpos(a, st)) return 1;
+    rel = a->scratch;
+    bias = a->S == 14 ? 1 : 2;
+  }
+  if (split) {
+    if (bias == 0) return launch_attn_tc<3, 0>(a, rel, st);
+    if (bias == 1) return launch_attn_tc<3, 1>(a, rel, st);
+    return launch_attn_tc<3, 2>(a, rel, st);
+  }
+  if (bias == 0) return launch_attn_tc<1, 0>(a, rel, st);
+  if (bias == 1) return launch_attn_tc<1, 1>(a, rel, st);
+  return launch_attn_tc<1, 2>(a, rel, st);
+}
+
 }  // namespace csam

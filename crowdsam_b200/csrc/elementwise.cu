@@ -8,11 +8,15 @@ __constant__ float c_mean[3] = {123.675f, 116.28f, 103.53f};   // build_sam.py:1
 __constant__ float c_std[3] = {58.395f, 57.12f, 57.375f};      // build_sam.py:149
 
 // normalised + zero-padded 1024x1024 virtual image (sam.py:163-173)
+// HWC: img[(y*w + x)*3 + c] (what cv2 / PIL hand over), else planar CHW
+template <bool HWC>
 __device__ __forceinline__ float norm_px(const uint8_t* img, int h, int w, int c, int y, int x) {
   if (y >= h || x >= w) return 0.f;
-  return ((float)img[((size_t)c * h + y) * w + x] - c_mean[c]) / c_std[c];
+  const uint8_t v = HWC ? img[((size_t)y * w + x) * 3 + c] : img[((size_t)c * h + y) * w + x];
+  return ((float)v - c_mean[c]) / c_std[c];
 }
 
+template <bool HWC>
 __global__ void patchify_kernel(const uint8_t* __restrict__ img, int h, int w, int patch, int n_side, int resize_to,
                                 __half* __restrict__ out_hi, __half* __restrict__ out_lo, int kpad) {
   const int pr = blockIdx.x / n_side, pc = blockIdx.x % n_side;
@@ -25,7 +29,7 @@ __global__ void patchify_kernel(const uint8_t* __restrict__ img, int h, int w, i
       const int py = (k / patch) % patch, px = k % patch;
       const int Y = pr * patch + py, X = pc * patch + px;
       if (!resize_to) {
-        v = norm_px(img, h, w, c, Y, X);
+        v = norm_px<HWC>(img, h, w, c, Y, X);
       } else {   // upsample_bilinear2d, align_corners=False (predictor.py:104)
         float sy = fmaxf(scale * (Y + 0.5f) - 0.5f, 0.f);
         float sx = fmaxf(scale * (X + 0.5f) - 0.5f, 0.f);
@@ -33,8 +37,8 @@ __global__ void patchify_kernel(const uint8_t* __restrict__ img, int h, int w, i
         const int y1 = y0 + (y0 < 1023 ? 1 : 0), x1 = x0 + (x0 < 1023 ? 1 : 0);
         const float ly = sy - y0, lx = sx - x0;
         const float hy = 1.f - ly, hx = 1.f - lx;
-        v = hy * (hx * norm_px(img, h, w, c, y0, x0) + lx * norm_px(img, h, w, c, y0, x1)) +
-            ly * (hx * norm_px(img, h, w, c, y1, x0) + lx * norm_px(img, h, w, c, y1, x1));
+        v = hy * (hx * norm_px<HWC>(img, h, w, c, y0, x0) + lx * norm_px<HWC>(img, h, w, c, y0, x1)) +
+            ly * (hx * norm_px<HWC>(img, h, w, c, y1, x0) + lx * norm_px<HWC>(img, h, w, c, y1, x1));
       }
     }
     store_pair(out_hi, out_lo, (size_t)blockIdx.x * kpad + k, v);
@@ -325,12 +329,16 @@ __global__ void select_kernel(const float* __restrict__ iou, const float* __rest
 
 using namespace csam;
 
-extern "C" int csam_patchify(const uint8_t* img, int h, int w, int patch, int n_side, int resize_to,
+extern "C" int csam_patchify(const uint8_t* img, int h, int w, int hwc, int patch, int n_side, int resize_to,
                              void* out_hi, void* out_lo, int kpad, void* stream) {
   CSAM_REQUIRE(img && out_hi && h > 0 && w > 0 && h <= 1024 && w <= 1024, "csam_patchify: bad image");
   CSAM_REQUIRE(kpad >= 3 * patch * patch, "csam_patchify: kpad too small");
-  patchify_kernel<<<n_side * n_side, 256, 0, (cudaStream_t)stream>>>(img, h, w, patch, n_side, resize_to,
-                                                                      (__half*)out_hi, (__half*)out_lo, kpad);
+  if (hwc)
+    patchify_kernel<true><<<n_side * n_side, 256, 0, (cudaStream_t)stream>>>(img, h, w, patch, n_side, resize_to,
+                                                                            (__half*)out_hi, (__half*)out_lo, kpad);
+  else
+    patchify_kernel<false><<<n_side * n_side, 256, 0, (cudaStream_t)stream>>>(img, h, w, patch, n_side, resize_to,
+                                                                             (__half*)out_hi, (__half*)out_lo, kpad);
   return check_launch("patchify_kernel");
 }
 

@@ -67,7 +67,7 @@ _SIGS = {
     "csam_abi_version": (ci, []),
     "csam_launch_count": (cll, []),
     "csam_gemm": (ci, [C.POINTER(GemmArgs), vp]),
-    "csam_patchify": (ci, [vp, ci, ci, ci, ci, ci, vp, vp, ci, vp]),
+    "csam_patchify": (ci, [vp, ci, ci, ci, ci, ci, ci, vp, vp, ci, vp]),
     "csam_layernorm": (ci, [C.POINTER(LnArgs), vp]),
     "csam_vit_attention_scratch_bytes": (cll, [ci, ci, ci, ci, ci]),
     "csam_vit_attention": (ci, [C.POINTER(AttnArgs), vp]),

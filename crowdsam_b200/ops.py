@@ -17,6 +17,44 @@ GEMM_IMPL = int(os.environ.get("CSAM_GEMM_IMPL", "0"))
 ATTN_IMPL = int(os.environ.get("CSAM_ATTN_IMPL", "1"))   # tcgen05 attention pending
 
 
+class Profiler:
+    """Per-kernel-class CUDA-event timing on the launching stream (bench.py roofline numbers).
+    Each record is (start_event, stop_event, work) with work = algorithmic FLOPs or bytes of that launch."""
+
+    def __init__(self):
+        self.records = {}
+
+    def begin(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def end(self, name: str, start, work: float):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.records.setdefault(name, []).append((start, e, work))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, recs in self.records.items():
+            ms = [a.elapsed_time(b) for a, b, _ in recs]
+            out[name] = {"launches": len(recs), "total_ms": sum(ms), "work": sum(w for _, _, w in recs)}
+        return out
+
+
+PROFILER: Optional[Profiler] = None
+
+
+def _pb():
+    return PROFILER.begin() if PROFILER is not None else None
+
+
+def _pe(name, tok, work):
+    if tok is not None:
+        PROFILER.end(name, tok, work)
+
+
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -91,15 +129,20 @@ def gemm(a: H16, w: H16, *, bias=None, act=ACT_NONE, residual=None, res_mod=0, r
         g.out_hi, g.out_lo, g.ldh = _p(out_h16.hi), _p(out_h16.lo), out_h16.hi.stride(0)
     g.impl = GEMM_IMPL if impl is None else impl
     g.b_mn_major = 1 if b_mn_major else 0
+    tok = _pb()
     L.check(L.load().csam_gemm(C.byref(g), _stream()), "csam_gemm")
+    _pe("gemm", tok, 2.0 * M * N * K)
     return out_f32, out_h16
 
 
-def patchify(img_u8_chw: torch.Tensor, patch: int, n_side: int, resize_to: int, kpad: int, split: bool) -> H16:
-    _, h, w = img_u8_chw.shape
-    out = H16.empty((n_side * n_side, kpad), split, img_u8_chw.device)
-    L.check(L.load().csam_patchify(_p(img_u8_chw), h, w, patch, n_side, resize_to, _p(out.hi), _p(out.lo), kpad,
-                                   _stream()), "csam_patchify")
+def patchify(img_u8: torch.Tensor, patch: int, n_side: int, resize_to: int, kpad: int, split: bool) -> H16:
+    """img_u8: uint8 [3,h,w] (planar) or [h,w,3] (interleaved, as cv2 / PIL deliver it)."""
+    assert img_u8.dtype == torch.uint8 and img_u8.dim() == 3 and img_u8.is_contiguous()
+    hwc = img_u8.shape[2] == 3 and img_u8.shape[0] != 3
+    h, w = (img_u8.shape[0], img_u8.shape[1]) if hwc else (img_u8.shape[1], img_u8.shape[2])
+    out = H16.empty((n_side * n_side, kpad), split, img_u8.device)
+    L.check(L.load().csam_patchify(_p(img_u8), h, w, 1 if hwc else 0, patch, n_side, resize_to, _p(out.hi), _p(out.lo),
+                                   kpad, _stream()), "csam_patchify")
     return out
 
 
@@ -133,7 +176,9 @@ def layernorm(x: torch.Tensor, gamma=None, beta=None, eps=1e-6, *, add=None, add
         a.ldh = out2.hi.stride(0)
     a.pe, a.ldpe, a.pe_mod = _p(pe), (pe.stride(0) if pe is not None else 0), pe_mod
     a.act = act
+    tok = _pb()
     L.check(L.load().csam_layernorm(C.byref(a), _stream()), "csam_layernorm")
+    _pe("layernorm", tok, 4.0 * rows_out * cols)
     return out_f32, out_h16, out2
 
 
@@ -156,7 +201,9 @@ def vit_attention(qkv: H16, groups: int, tokens: int, heads: int, hd: int, scale
             _attn_scratch[key] = torch.empty(need, dtype=torch.uint8, device=dev)
         a.scratch, a.scratch_bytes = _p(_attn_scratch[key]), need
     a.impl = ATTN_IMPL if impl is None else impl
+    tok = _pb()
     L.check(L.load().csam_vit_attention(C.byref(a), _stream()), "csam_vit_attention")
+    _pe("vit_attention", tok, 4.0 * groups * heads * tokens * tokens * hd)
     return out
 
 
@@ -207,7 +254,9 @@ def _dec_attn(fn_name, q, k, v, B, nq, nk, heads, hd, want_f32, want_h16, split)
     a.out_f32 = _p(of)
     if oh is not None:
         a.out_hi, a.out_lo = _p(oh.hi), _p(oh.lo)
+    tok = _pb()
     L.check(getattr(L.load(), fn_name)(C.byref(a), _stream()), fn_name)
+    _pe(fn_name[5:], tok, 4.0 * B * nq * nk * Cc)
     return of, oh
 
 
@@ -270,7 +319,9 @@ def mask_post_stats(low, sel, in_size, out_size, thr=0.0, off=1.0):
     counts = torch.empty((P, 3), dtype=torch.int32, device=low.device)
     boxes = torch.empty((P, 4), dtype=torch.int32, device=low.device)
     a.counts, a.boxes = _p(counts), _p(boxes)
+    tok = _pb()
     L.check(L.load().csam_mask_post_stats(C.byref(a), _stream()), "csam_mask_post_stats")
+    _pe("mask_post_stats", tok, 262144.0 * P + 28.0 * P)      # read the selected 256x256 fp32 plane, write counts+box
     return counts, boxes
 
 
@@ -284,7 +335,11 @@ def mask_post_write(low, sel, keep, in_size, out_size, thr=0.0, want_masks=True,
         return masks, logits
     a.keep, a.n_keep = _p(keep), n
     a.masks, a.logits = _p(masks), _p(logits)
+    tok = _pb()
     L.check(L.load().csam_mask_post_write(C.byref(a), _stream()), "csam_mask_post_write")
+    # algorithmic bytes: read one 256x256 fp32 plane + write one bool mask (+ fp32 logits if requested)
+    _pe("mask_post_write", tok, n * (262144.0 + a.out_h * a.out_w * (1.0 if want_masks else 0.0)
+                                       + a.out_h * a.out_w * (4.0 if want_logits else 0.0)))
     return masks, logits
 
 

@@ -137,9 +137,24 @@ class CrowdSAM:
     def _process_crop(self, image, crop_box) -> Optional[MaskData]:
         self.crop_image(image, crop_box)
         self.predictor.set_image(self.image)
+        return self._run_prompts(crop_box)
+
+    @torch.no_grad()
+    def run_resident(self, img_u8_chw: torch.Tensor, encode_rle: bool = False) -> Optional[MaskData]:
+        """Device-resident variant of generate() for a full-frame crop whose uint8 CHW image already
+        lives in HBM at the model resolution (long side 1024): no host resize, no H2D of pixels and, unless
+        asked, no RLE/D2H of masks.  Used by bench.py for the `value` leg; same kernels as generate()."""
+        h, w = int(img_u8_chw.shape[1]), int(img_u8_chw.shape[2])
+        self.orig_image = np.empty((h, w, 0), dtype=np.uint8)
+        self.image, self.downscale = self.orig_image, 1.0
+        self.predictor.set_torch_image(img_u8_chw[None], (h, w))
+        return self._run_prompts([0, 0, w, h], encode_rle=encode_rle)
+
+    def _run_prompts(self, crop_box, encode_rle: bool = True) -> Optional[MaskData]:
         orig_h, orig_w = self.orig_image.shape[:2]
+        self.last_counts = (0, 0)
         points = self.candidate_points(self.image.shape[:2])
-        data = MaskData()
+        parts = []
         # EPS iterator (model.py:229-248): same RNG consumption, occupancy tested on the device
         points = points.astype("int")
         np.random.shuffle(points)
@@ -153,17 +168,22 @@ class CrowdSAM:
                 pts_d = torch.as_tensor(points, dtype=torch.int32, device=self.device)
                 occ = ops.points_occupied(batch["masks"], flag, pts_d).cpu().numpy().astype(bool)
                 points = points[~occ]
-            data.cat(batch)
+            parts.append(batch)
             count += bs
+        data = MaskData.merged(parts)
         self.predictor.reset_image()
         if len(data.items()) == 0 or len(data["masks"]) == 0:
             return None
+        n_into_nms = len(data["boxes"])
         keep = ops.box_nms(data["boxes"].float(), data["iou_preds"], self.box_nms_thresh)       # model.py:257-263
         data.filter(keep)
         if self.min_mask_region_area > 0:
             data = self.postprocess_small_regions(data, self.min_mask_region_area,
                                                   max(self.box_nms_thresh, self.crop_nms_thresh))
         data["scores"] = data["iou_preds"]
+        self.last_counts = (n_into_nms, len(data["boxes"]))          # N masks into NMS, K detections kept
+        if not encode_rle:
+            return data
         data["rles"] = amg.mask_to_rle_pytorch(data["masks"])
         data["rles_info"] = [crop_box, [orig_h, orig_w]]
         del data["masks"]

@@ -31,12 +31,29 @@ class SamPredictor:
         if image_format != self.model.image_format:
             image = image[..., ::-1]
         resized = self.transform.apply_image(np.ascontiguousarray(image))
-        t = torch.as_tensor(resized).permute(2, 0, 1).contiguous()[None]      # pageable -> pinned -> device
-        t = t.to(self.device, non_blocking=False)
+        # interleaved HWC bytes go to the device as they are (one H2D copy); the patch-gather kernel reads HWC
+        hwc = torch.as_tensor(resized).to(self.device, non_blocking=True)
         mask_t = None
         if mask is not None:
             mask_t = torch.as_tensor(self.transform.apply_image(mask), device=self.device).permute(2, 0, 1).contiguous()[None]
-        return self.set_torch_image(t, image.shape[:2], transformed_mask=mask_t, cal_image=cal_image)
+        if cal_image:
+            self._set_u8(hwc, tuple(image.shape[:2]), tuple(resized.shape[:2]))
+        if mask_t is not None:
+            size = self.model.image_encoder.img_size
+            h, w = mask_t.shape[-2:]
+            return torch.nn.functional.pad(mask_t, (0, size - w, 0, size - h))
+
+    @torch.no_grad()
+    def _set_u8(self, img_u8: torch.Tensor, original_size, input_size):
+        """img_u8: uint8 [h,w,3] or [3,h,w] on the device at the model resolution."""
+        self.reset_image()
+        self.original_size, self.input_size = tuple(original_size), tuple(input_size)
+        feats, feat_tok = self.model.image_encoder.forward_u8(img_u8)
+        dino_f32, dino_h = self.dino_model.forward_features_u8(img_u8)
+        self.features = feats
+        self.dino_feats = dino_f32.view(1, 73, 73, -1)
+        self._bind(feats, self.dino_feats, feat_tok, dino_h)
+        self.is_image_set = True
 
     @torch.no_grad()
     def set_torch_image(self, transformed_image: torch.Tensor, original_image_size: Tuple[int, ...],
@@ -46,22 +63,13 @@ class SamPredictor:
                 and max(*transformed_image.shape[2:]) == size), \
             f"set_torch_image input must be BCHW with long side {size}."
         if cal_image:
-            self.reset_image()
-            self.original_size = tuple(original_image_size)
-            self.input_size = tuple(transformed_image.shape[-2:])
             img = transformed_image[0]
             if img.dtype != torch.uint8:
                 r = img.round()
                 if not torch.equal(r, img) or r.min() < 0 or r.max() > 255:
                     raise NotImplementedError("the B200 path takes 8-bit images (as SamPredictor.set_image produces)")
                 img = r.to(torch.uint8)
-            img = img.to(self.device).contiguous()
-            feats, feat_tok = self.model.image_encoder.forward_u8(img)
-            dino_f32, dino_h = self.dino_model.forward_features_u8(img)
-            self.features = feats
-            self.dino_feats = dino_f32.view(1, 73, 73, -1)
-            self._bind(feats, self.dino_feats, feat_tok, dino_h)
-            self.is_image_set = True
+            self._set_u8(img.to(self.device).contiguous(), original_image_size, transformed_image.shape[-2:])
         if transformed_mask is not None:
             h, w = transformed_mask.shape[-2:]
             return torch.nn.functional.pad(transformed_mask, (0, size - w, 0, size - h))

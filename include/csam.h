@@ -74,10 +74,11 @@ CSAM_API int csam_gemm(const csam_gemm_args* a, void* stream);
  * Image -> patch matrix.  sam.py:163-173 (normalise + zero pad) fused with the im2col of the
  * 16x16/s16 patch-embed conv (image_encoder.py:391-395), and, for DINOv2, with the bilinear
  * 1024->1022 resize (predictor.py:104) and the 14x14/s14 im2col (dinov2 layers/patch_embed.py).
- * img: uint8 [3,h,w] planar (after ResizeLongestSide); out: h16 pair [n_side*n_side, kpad],
+ * img: uint8 [3,h,w] planar, or [h,w,3] interleaved when hwc != 0 (after ResizeLongestSide);
+ * out: h16 pair [n_side*n_side, kpad],
  * column = c*patch*patch + py*patch + px (conv weight order), zero beyond 3*patch*patch.
  * ------------------------------------------------------------------------------------------ */
-CSAM_API int csam_patchify(const uint8_t* img, int h, int w, int patch, int n_side, int resize_to,
+CSAM_API int csam_patchify(const uint8_t* img, int h, int w, int hwc, int patch, int n_side, int resize_to,
                   void* out_hi, void* out_lo, int kpad, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -225,29 +225,34 @@ def _attn_ref(qkv, groups, tokens, heads, hd, rel_h=None, rel_w=None, S=0):
 
 
 @pytest.mark.parametrize("impl", ATTN_IMPLS)
-@pytest.mark.parametrize("groups,S,heads,hd", [(3, 14, 2, 64), (1, 32, 2, 64), (2, 14, 2, 80)])
-def test_vit_attention_relpos(groups, S, heads, hd, impl):
+@pytest.mark.parametrize("split", [True, False])
+@pytest.mark.parametrize("groups,S,heads,hd", [(3, 14, 2, 64), (1, 32, 2, 64), (2, 14, 2, 80), (1, 64, 2, 64), (25, 14, 1, 64)])
+def test_vit_attention_relpos(groups, S, heads, hd, split, impl):
     o = ops()
+    if impl == 0 and (hd != 64 or S not in (14, 64)):
+        pytest.skip("tcgen05 attention: head dim 64, S in {14, 64}")
     g = torch.Generator().manual_seed(S)
     tokens = S * S
     qkv = torch.randn(groups * tokens, 3 * heads * hd, generator=g)
     rel_h, rel_w = torch.randn(2 * S - 1, hd, generator=g) * 0.3, torch.randn(2 * S - 1, hd, generator=g) * 0.3
-    qh = _h16(qkv, True)
+    qh = _h16(qkv, split)
     ref = _attn_ref(qh.float().cpu(), groups, tokens, heads, hd, rel_h, rel_w, S)
     out = o.vit_attention(qh, groups, tokens, heads, hd, hd ** -0.5, rel_h.to(DEV), rel_w.to(DEV), S, impl=impl)
-    assert _rel(out.float(), ref) < 1e-5
+    # x1 on the tensor cores rounds P to fp16 (2^-11); SIMT keeps fp32 P
+    assert _rel(out.float(), ref) < (1e-5 if split else 2e-3), _rel(out.float(), ref)
 
 
 @pytest.mark.parametrize("impl", ATTN_IMPLS)
-def test_vit_attention_plain_ragged(impl):
+@pytest.mark.parametrize("tokens", [333, 64, 1, 1301])
+def test_vit_attention_plain_ragged(tokens, impl):
     o = ops()
     g = torch.Generator().manual_seed(9)
-    tokens, heads, hd = 333, 3, 64
-    qkv = torch.randn(tokens, 3 * heads * hd, generator=g)
+    heads, hd = 3, 64
+    qkv = torch.randn(tokens, 3 * heads * hd, generator=g) * 2
     qh = _h16(qkv, True)
     ref = _attn_ref(qh.float().cpu(), 1, tokens, heads, hd)
     out = o.vit_attention(qh, 1, tokens, heads, hd, hd ** -0.5, impl=impl)
-    assert _rel(out.float(), ref) < 1e-5
+    assert _rel(out.float(), ref) < 1e-5, _rel(out.float(), ref)
 
 
 def test_decoder_attentions():
