@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--points-per-batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--arch", default=ARCH)
+    ap.add_argument("--gemm-shapes", action="store_true", help="stderr: per-shape GEMM time table")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -258,7 +259,7 @@ def main():
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    ops.PROFILER = ops.Profiler()
+    ops.PROFILER = ops.Profiler(detail=args.gemm_shapes)
     l0 = lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dets, nk = [], (0, 0)
@@ -277,6 +278,13 @@ def main():
     launches = lib.launch_count() - l0
     prof = ops.PROFILER.summary()
     ops.PROFILER = None
+    if args.gemm_shapes and rank == 0:
+        rows = sorted(((k, v) for k, v in prof.items() if k.startswith("gemm ")), key=lambda kv: -kv[1]["total_ms"])
+        for k, v in rows:
+            tf = v["work"] / (v["total_ms"] * 1e-3) / 1e12
+            print(f"[gemm] {k:28s} n/step={v['launches'] / args.steps:6.1f} ms/step={v['total_ms'] / args.steps:8.3f} "
+                  f"avg_us={1e3 * v['total_ms'] / v['launches']:8.1f} TFLOP/s={tf:7.1f}", file=sys.stderr)
+        prof = {k: v for k, v in prof.items() if not k.startswith("gemm ")}
     clocks = sampler.stop()
     t = torch.tensor([ms_total], device=dev)
     if world > 1:

@@ -290,15 +290,52 @@ __global__ void __launch_bounds__(256) attn_few_queries_kernel(csam_dec_attn_arg
   }
 }
 
+// Block = one query row qh of one (group, head): the S queries of that row share the S rel_h table rows
+// Rh[qh - kh + S-1]; rel_w rows are indexed by qw - kw.  Everything is staged in shared memory once.
+__global__ void __launch_bounds__(256) relpos_rows_kernel(const __half* __restrict__ qhi, const __half* __restrict__ qlo,
+                                                          int ld, int tokens, int heads, int hd,
+                                                          const float* __restrict__ rel_h, const float* __restrict__ rel_w,
+                                                          int S, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int ldh = hd + 1;
+  float* qs = sm;                       // [S][hd+1]
+  float* th = qs + S * ldh;             // [S][hd+1]      rows qh - kh + S-1, kh = 0..S-1
+  float* tw = th + S * ldh;             // [2S-1][hd+1]
+  const int qh = blockIdx.x, h = blockIdx.y, g = blockIdx.z;
+  for (int i = threadIdx.x; i < S * hd; i += 256) {
+    const int r = i / hd, d = i % hd;
+    qs[r * ldh + d] = load_pair(qhi, qlo, ((size_t)g * tokens + qh * S + r) * ld + (size_t)h * hd + d);
+    th[r * ldh + d] = rel_h[(size_t)(qh - r + S - 1) * hd + d];
+  }
+  for (int i = threadIdx.x; i < (2 * S - 1) * hd; i += 256) tw[(i / hd) * ldh + i % hd] = rel_w[i];
+  __syncthreads();
+  float* o = out + (((size_t)g * heads + h) * tokens + (size_t)qh * S) * 2 * S;
+  for (int i = threadIdx.x; i < S * 2 * S; i += 256) {
+    const int qw = i % S, j = i / S;          // lanes vary qw: distinct smem rows, conflict-free (odd stride)
+    const float* q = qs + qw * ldh;
+    const float* t = (j < S) ? th + j * ldh : tw + (qw - (j - S) + S - 1) * ldh;
+    float acc = 0.f;
+    for (int d = 0; d < hd; ++d) acc = fmaf(q[d], t[d], acc);
+    o[(size_t)qw * 2 * S + j] = acc;
+  }
+}
+
 // fills a->scratch with the decomposed rel-pos terms [groups*heads*tokens, 2S] (shared by both attention paths)
 int compute_relpos(const csam_attn_args* a, cudaStream_t st) {
   CSAM_REQUIRE(a->S * a->S == a->tokens, "csam_vit_attention: rel-pos needs tokens == S*S");
   const long long need = csam_vit_attention_scratch_bytes(a->groups, a->tokens, a->heads, a->hd, a->S);
   CSAM_REQUIRE(a->scratch && a->scratch_bytes >= need, "csam_vit_attention: scratch too small");
-  relpos_kernel<<<148 * 8, 256, 0, st>>>(static_cast<const __half*>(a->qkv_hi), static_cast<const __half*>(a->qkv_lo),
-                                         a->ld_qkv, a->groups, a->tokens, a->heads, a->hd, a->rel_h, a->rel_w, a->S,
-                                         a->scratch);
-  return check_launch("relpos_kernel");
+  const size_t smem = (size_t)(4 * a->S - 1) * (a->hd + 1) * sizeof(float);
+  CSAM_REQUIRE(smem <= 100 * 1024 && a->groups <= 65535, "csam_vit_attention: rel-pos table too large");
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(relpos_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr = true;
+  }
+  relpos_rows_kernel<<<dim3(a->S, a->heads, a->groups), 256, smem, st>>>(
+      static_cast<const __half*>(a->qkv_hi), static_cast<const __half*>(a->qkv_lo), a->ld_qkv, a->tokens, a->heads,
+      a->hd, a->rel_h, a->rel_w, a->S, a->scratch);
+  return check_launch("relpos_rows_kernel");
 }
 
 int vit_attention_simt(const csam_attn_args* a, cudaStream_t st) {
@@ -315,6 +352,139 @@ int vit_attention_simt(const csam_attn_args* a, cudaStream_t st) {
   return check_launch("vit_attention_simt_kernel");
 }
 
+// ---- decoder cross attentions, C = 128 = 8 heads x 16: coalesced warp-cooperative fast paths ------
+// A warp reads one 512-byte row with one float4 per lane; lane l owns dims [4l,4l+4) of head l/4, so a
+// head's dot product is a 4-lane butterfly.
+
+// image -> token: every image token (row) attends to NK <= 8 tokens of its prompt.
+template <int NK>
+__global__ void __launch_bounds__(256) attn_i2t_kernel(csam_dec_attn_args a, int rows_per_block) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* kb = a.k + (size_t)(a.Bk == 1 ? 0 : b) * NK * 128 + lane * 4;
+  const float* vb = a.v + (size_t)(a.Bk == 1 ? 0 : b) * NK * 128 + lane * 4;
+  float4 kr[NK], vr[NK];
+#pragma unroll
+  for (int j = 0; j < NK; ++j) {
+    kr[j] = *reinterpret_cast<const float4*>(kb + j * 128);
+    vr[j] = *reinterpret_cast<const float4*>(vb + j * 128);
+  }
+  const float* qb = a.q + (size_t)(a.Bq == 1 ? 0 : b) * a.nq * 128;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, a.nq);
+  __half* ohi = static_cast<__half*>(a.out_hi);
+  __half* olo = static_cast<__half*>(a.out_lo);
+  for (int r = r0 + warp; r < r1; r += 8) {
+    const float4 q = *reinterpret_cast<const float4*>(qb + (size_t)r * 128 + lane * 4);
+    float s[NK];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NK; ++j) {
+      float d = q.x * kr[j].x + q.y * kr[j].y + q.z * kr[j].z + q.w * kr[j].w;
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      s[j] = d * 0.25f;                       // 1/sqrt(16)
+      m = fmaxf(m, s[j]);
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < NK; ++j) { s[j] = expf(s[j] - m); l += s[j]; }
+    const float inv = 1.0f / l;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < NK; ++j) {
+      const float p = s[j] * inv;
+      o[0] = fmaf(p, vr[j].x, o[0]); o[1] = fmaf(p, vr[j].y, o[1]);
+      o[2] = fmaf(p, vr[j].z, o[2]); o[3] = fmaf(p, vr[j].w, o[3]);
+    }
+    const size_t oo = ((size_t)b * a.nq + r) * 128 + lane * 4;
+    if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + oo) = make_float4(o[0], o[1], o[2], o[3]);
+    if (ohi) store_pair4(ohi, olo, oo, o);
+  }
+}
+
+// token -> image: NQ <= 8 tokens attend to all nk image tokens of their prompt; one block per prompt,
+// each warp streams a strided set of 4-key tiles with an online softmax, partials merged in smem.
+template <int NQ>
+__global__ void __launch_bounds__(512) attn_t2i_kernel(csam_dec_attn_args a) {
+  extern __shared__ float sm[];
+  constexpr int NW = 16;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* qb = a.q + (size_t)(a.Bq == 1 ? 0 : b) * NQ * 128 + lane * 4;
+  const float* kb = a.k + (size_t)(a.Bk == 1 ? 0 : b) * a.nk * 128 + lane * 4;
+  const float* vb = a.v + (size_t)(a.Bk == 1 ? 0 : b) * a.nk * 128 + lane * 4;
+  float4 qr[NQ];
+  float m[NQ], l[NQ];
+  float4 acc[NQ];
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    qr[i] = *reinterpret_cast<const float4*>(qb + i * 128);
+    qr[i].x *= 0.25f; qr[i].y *= 0.25f; qr[i].z *= 0.25f; qr[i].w *= 0.25f;
+    m[i] = -INFINITY; l[i] = 0.f; acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int k0 = warp * 4; k0 < a.nk; k0 += NW * 4) {
+    float4 kk[4], vv[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int key = min(k0 + t, a.nk - 1);
+      kk[t] = *reinterpret_cast<const float4*>(kb + (size_t)key * 128);
+      vv[t] = *reinterpret_cast<const float4*>(vb + (size_t)key * 128);
+    }
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      float s[4];
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float d = qr[i].x * kk[t].x + qr[i].y * kk[t].y + qr[i].z * kk[t].z + qr[i].w * kk[t].w;
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        s[t] = (k0 + t < a.nk) ? d : -INFINITY;
+        tmax = fmaxf(tmax, s[t]);
+      }
+      const float mn = fmaxf(m[i], tmax);
+      const float al = expf(m[i] - mn);
+      float4 ac = acc[i];
+      ac.x *= al; ac.y *= al; ac.z *= al; ac.w *= al;
+      float li = l[i] * al;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float p = expf(s[t] - mn);
+        li += p;
+        ac.x = fmaf(p, vv[t].x, ac.x); ac.y = fmaf(p, vv[t].y, ac.y);
+        ac.z = fmaf(p, vv[t].z, ac.z); ac.w = fmaf(p, vv[t].w, ac.w);
+      }
+      acc[i] = ac; l[i] = li; m[i] = mn;
+    }
+  }
+  // merge the NW partial states: sm_m/sm_l [NW][NQ][8 heads], sm_acc [NW][NQ][128]
+  float* sm_m = sm;
+  float* sm_l = sm_m + NW * NQ * 8;
+  float* sm_acc = sm_l + NW * NQ * 8;
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    if ((lane & 3) == 0) { sm_m[(warp * NQ + i) * 8 + (lane >> 2)] = m[i]; sm_l[(warp * NQ + i) * 8 + (lane >> 2)] = l[i]; }
+    *reinterpret_cast<float4*>(sm_acc + (size_t)(warp * NQ + i) * 128 + lane * 4) = acc[i];
+  }
+  __syncthreads();
+  __half* ohi = static_cast<__half*>(a.out_hi);
+  __half* olo = static_cast<__half*>(a.out_lo);
+  for (int t = threadIdx.x; t < NQ * 128; t += 512) {
+    const int i = t >> 7, d = t & 127, hgrp = d >> 4;
+    float M = -INFINITY;
+    for (int w = 0; w < NW; ++w) M = fmaxf(M, sm_m[(w * NQ + i) * 8 + hgrp]);
+    float num = 0.f, den = 0.f;
+    for (int w = 0; w < NW; ++w) {
+      const float e = expf(sm_m[(w * NQ + i) * 8 + hgrp] - M);   // warps that saw no key: exp(-inf) = 0
+      num = fmaf(sm_acc[(size_t)(w * NQ + i) * 128 + d], e, num);
+      den = fmaf(sm_l[(w * NQ + i) * 8 + hgrp], e, den);
+    }
+    const float o = num / den;
+    const size_t oo = ((size_t)b * NQ + i) * 128 + d;
+    if (a.out_f32) a.out_f32[oo] = o;
+    if (ohi) store_pair(ohi, olo, oo, o);
+  }
+}
+
 }  // namespace csam
 
 using namespace csam;
@@ -328,6 +498,12 @@ extern "C" int csam_attn_few_keys(const csam_dec_attn_args* a, void* stream) {
   CSAM_REQUIRE(a && a->q && a->k && a->v && (a->out_f32 || a->out_hi), "csam_attn_few_keys: bad args");
   CSAM_REQUIRE(a->nk >= 1 && a->nk <= 8 && a->hd <= 32 && a->B <= 65535, "csam_attn_few_keys: nk <= 8, hd <= 32");
   const int C = a->heads * a->hd;
+  if (a->heads == 8 && a->hd == 16 && a->nk == 7) {   // image -> token cross attention
+    const int rows_per_block = 256;
+    dim3 g((a->nq + rows_per_block - 1) / rows_per_block, a->B);
+    attn_i2t_kernel<7><<<g, 256, 0, (cudaStream_t)stream>>>(*a, rows_per_block);
+    return check_launch("attn_i2t_kernel");
+  }
   dim3 grid((a->nq + 127) / 128, a->B);
   attn_few_keys_kernel<<<grid, 128, 2 * a->nk * C * sizeof(float), (cudaStream_t)stream>>>(*a);
   return check_launch("attn_few_keys_kernel");
@@ -337,6 +513,16 @@ extern "C" int csam_attn_few_queries(const csam_dec_attn_args* a, void* stream) 
   CSAM_REQUIRE(a && a->q && a->k && a->v && (a->out_f32 || a->out_hi), "csam_attn_few_queries: bad args");
   CSAM_REQUIRE(a->nq >= 1 && a->nq <= 8 && a->hd <= 32 && (a->hd % 4) == 0 && a->B <= 65535,
                "csam_attn_few_queries: nq <= 8, hd <= 32");
+  if (a->heads == 8 && a->hd == 16 && a->nq == 7) {   // token -> image cross attention
+    const size_t sm = (size_t)16 * 7 * (8 + 8 + 128) * sizeof(float);
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaFuncSetAttribute(attn_t2i_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      attr2 = true;
+    }
+    attn_t2i_kernel<7><<<a->B, 512, sm, (cudaStream_t)stream>>>(*a);
+    return check_launch("attn_t2i_kernel");
+  }
   const size_t smem = ((size_t)a->nq * a->nk + a->nq * a->hd + 16 * 8 * 16) * sizeof(float);
   CSAM_REQUIRE(smem <= 200 * 1024, "csam_attn_few_queries: nk too large for shared memory");
   static bool attr = false;

@@ -52,6 +52,15 @@ __device__ __forceinline__ float load_pair(const __half* hi, const __half* lo, s
   if (lo) v += __half2float(lo[i]);
   return v;
 }
+// 4 consecutive values -> two 8-byte stores
+__device__ __forceinline__ void store_pair4(__half* hi, __half* lo, size_t i, const float* v) {
+  __align__(8) __half h[4];
+  __align__(8) __half l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_h(v[j], h[j], l[j]);
+  *reinterpret_cast<uint2*>(hi + i) = *reinterpret_cast<const uint2*>(h);
+  if (lo) *reinterpret_cast<uint2*>(lo + i) = *reinterpret_cast<const uint2*>(l);
+}
 // 8 consecutive values -> two 16-byte stores
 __device__ __forceinline__ void store_pair8(__half* hi, __half* lo, size_t i, const float* v) {
   __align__(16) __half h[8];

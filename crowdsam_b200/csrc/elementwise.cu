@@ -48,6 +48,8 @@ __global__ void patchify_kernel(const uint8_t* __restrict__ img, int h, int w, i
 // ---- LayerNorm: one warp per output row, row cached in registers ----------------------
 constexpr int LN_MAX_V4 = 16;   // cols <= 32*4*16 = 2048
 
+// NV4 = float4 slots per lane (cols <= 128*NV4): small rows keep few registers -> high occupancy
+template <int NV4>
 __global__ void __launch_bounds__(256) layernorm_kernel(csam_ln_args a) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(csam_ln_args a) {
   __half* olo = static_cast<__half*>(a.out_lo);
   __half* o2hi = static_cast<__half*>(a.out2_hi);
   __half* o2lo = static_cast<__half*>(a.out2_lo);
-  float4 v[LN_MAX_V4];
+  float4 v[NV4];
   if (src < 0) {   // zero row (window padding happens after the norm)
     for (int i = lane; i < nv; i += 32) {
       const int c = i * 4;
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(csam_ln_args a) {
   const float* ad = a.add ? a.add + (size_t)(a.add_mod > 0 ? src % a.add_mod : src) * a.ldadd : nullptr;
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < LN_MAX_V4; ++j) {
+  for (int j = 0; j < NV4; ++j) {
     const int i = lane + j * 32;
     if (i < nv) {
       float4 t = *reinterpret_cast<const float4*>(x + i * 4);
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(csam_ln_args a) {
     mean = warp_sum(s) / a.cols;
     float q = 0.f;
 #pragma unroll
-    for (int j = 0; j < LN_MAX_V4; ++j) {
+    for (int j = 0; j < NV4; ++j) {
       const int i = lane + j * 32;
       if (i < nv) {
         const float dx = v[j].x - mean, dy = v[j].y - mean, dz = v[j].z - mean, dw = v[j].w - mean;
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(csam_ln_args a) {
   }
   const float* pe = a.pe ? a.pe + (size_t)(a.pe_mod > 0 ? row % a.pe_mod : row) * a.ldpe : nullptr;
 #pragma unroll
-  for (int j = 0; j < LN_MAX_V4; ++j) {
+  for (int j = 0; j < NV4; ++j) {
     const int i = lane + j * 32;
     if (i < nv) {
       const int c = i * 4;
@@ -115,15 +117,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(csam_ln_args a) {
         for (int t = 0; t < 4; ++t) y[t] = apply_act(y[t], a.act);
       }
       if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + (size_t)row * a.ldo + c) = make_float4(y[0], y[1], y[2], y[3]);
-      if (ohi) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) store_pair(ohi, olo, (size_t)row * a.ldh + c + t, y[t]);
-      }
+      if (ohi) store_pair4(ohi, olo, (size_t)row * a.ldh + c, y);
       if (o2hi) {
         const float4 p = *reinterpret_cast<const float4*>(pe + c);
         const float z[4] = {y[0] + p.x, y[1] + p.y, y[2] + p.z, y[3] + p.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) store_pair(o2hi, o2lo, (size_t)row * a.ldh + c + t, z[t]);
+        store_pair4(o2hi, o2lo, (size_t)row * a.ldh + c, z);
       }
     }
   }
@@ -349,7 +347,10 @@ extern "C" int csam_layernorm(const csam_ln_args* a, void* stream) {
                    (!a->add || (a->ldadd % 4) == 0) && (!a->pe || (a->ldpe % 4) == 0),
                "csam_layernorm: strides must be multiples of 4");
   CSAM_REQUIRE(!a->out2_hi || a->pe, "csam_layernorm: out2 needs pe");
-  layernorm_kernel<<<(a->rows_out + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*a);
+  const dim3 grid((a->rows_out + 7) / 8);
+  if (a->cols <= 256) layernorm_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
+  else if (a->cols <= 1024) layernorm_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
+  else layernorm_kernel<LN_MAX_V4><<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
   return check_launch("layernorm_kernel");
 }
 

@@ -45,6 +45,38 @@ __device__ __forceinline__ const float* plane_of(const csam_post_args& a, int p)
 
 constexpr int POST_ROWS = 8;   // output rows per block
 
+// 16 consecutive output pixels (Y, X0..X0+15), X0 a multiple of 16.
+// Identity stage 2 (the CrowdSAM path): the x4 bilinear has only 4 horizontal phases, so the 16 pixels
+// need 6 low-res columns of 2 rows: 12 loads instead of 64, and the weights are compile-time constants
+// (.625 .875 .125 .375 -- exactly what ATen's formula yields in fp32).  Same operation order as the
+// reference: hy*(hx*v00 + lx*v01) + ly*(hx*v10 + lx*v11).
+__device__ __forceinline__ void eval16(const float* __restrict__ L, const PostGeom& g, int Y, int X0, float* v) {
+  if (g.identity) {
+    int y0, y1; float ly;
+    coord256(Y, y0, y1, ly);
+    const float hy = 1.f - ly;
+    const int k0 = X0 >> 2;
+    float r0[6], r1[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const int cc = min(max(k0 - 1 + c, 0), 255);
+      r0[c] = L[y0 * 256 + cc];
+      r1[c] = L[y1 * 256 + cc];
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int i0 = (j + 2) >> 2;                                 // relative low-res column of the left tap
+      float lx = ((j & 3) == 0) ? 0.625f : ((j & 3) == 1) ? 0.875f : ((j & 3) == 2) ? 0.125f : 0.375f;
+      if (X0 == 0 && j < 2) lx = 0.f;                              // source index clamped to 0 at the left border
+      const float hx = 1.f - lx;
+      v[j] = hy * (hx * r0[i0] + lx * r0[i0 + 1]) + ly * (hx * r1[i0] + lx * r1[i0 + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = (X0 + j < g.out_w) ? eval_logit(L, g, Y, X0 + j) : 0.f;
+  }
+}
+
 __global__ void post_init_kernel(int* counts, int* boxes, int P) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
@@ -60,7 +92,7 @@ __global__ void post_finalize_kernel(int* boxes, int P) {
   }
 }
 
-__global__ void __launch_bounds__(256) post_stats_kernel(csam_post_args a, PostGeom g) {
+__global__ void __launch_bounds__(256) post_stats_kernel(csam_post_args a, PostGeom g, int segs_per_row) {
   const int p = blockIdx.y;
   const float* L = plane_of(a, p);
   const int y_begin = blockIdx.x * POST_ROWS;
@@ -68,15 +100,26 @@ __global__ void __launch_bounds__(256) post_stats_kernel(csam_post_args a, PostG
   const float t_hi = a.thr + a.off, t_lo = a.thr - a.off;
   int c_hi = 0, c_lo = 0, c_mid = 0;
   int xmin = INT_MAX, xmax = -1, ymin = INT_MAX, ymax = -1;
-  const int n = (y_end - y_begin) * g.out_w;
+  const int n = (y_end - y_begin) * segs_per_row;
   for (int i = threadIdx.x; i < n; i += 256) {
-    const int Y = y_begin + i / g.out_w, X = i % g.out_w;
-    const float v = eval_logit(L, g, Y, X);
-    c_hi += v > t_hi;
-    c_lo += v > t_lo;
-    if (v > a.thr) {
-      ++c_mid;
-      xmin = min(xmin, X); xmax = max(xmax, X); ymin = min(ymin, Y); ymax = max(ymax, Y);
+    const int Y = y_begin + i / segs_per_row, X0 = (i % segs_per_row) * 16;
+    const int nx = min(16, g.out_w - X0);
+    float v[16];
+    eval16(L, g, Y, X0, v);
+    unsigned bits = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < nx) {
+        c_hi += v[j] > t_hi;
+        c_lo += v[j] > t_lo;
+        bits |= (v[j] > a.thr ? 1u : 0u) << j;
+      }
+    }
+    if (bits) {
+      c_mid += __popc(bits);
+      xmin = min(xmin, X0 + __ffs(bits) - 1);
+      xmax = max(xmax, X0 + 31 - __clz(bits));
+      ymin = min(ymin, Y); ymax = max(ymax, Y);
     }
   }
 #pragma unroll
@@ -112,19 +155,30 @@ __global__ void __launch_bounds__(256) post_write_kernel(csam_post_args a, PostG
   for (int s = blockIdx.x * 256 + threadIdx.x; s < total; s += gridDim.x * 256) {
     const int Y = s / segs_per_row, X0 = (s % segs_per_row) * 16;
     const int nx = min(16, g.out_w - X0);
-    __align__(16) uint8_t b[16];
     float v[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      v[j] = (j < nx) ? eval_logit(L, g, Y, X0 + j) : 0.f;
-      b[j] = v[j] > a.thr ? 1 : 0;
-    }
+    eval16(L, g, Y, X0, v);
     const size_t o = (size_t)Y * g.out_w + X0;
     if (mo) {
-      if (vec) *reinterpret_cast<uint4*>(mo + o) = *reinterpret_cast<const uint4*>(b);
-      else for (int j = 0; j < nx; ++j) mo[o + j] = b[j];
+      uint32_t w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        w[q] = (v[q * 4] > a.thr ? 1u : 0u) | (v[q * 4 + 1] > a.thr ? 0x100u : 0u) |
+               (v[q * 4 + 2] > a.thr ? 0x10000u : 0u) | (v[q * 4 + 3] > a.thr ? 0x1000000u : 0u);
+      if (vec) {
+        *reinterpret_cast<uint4*>(mo + o) = make_uint4(w[0], w[1], w[2], w[3]);
+      } else {
+        for (int j = 0; j < nx; ++j) mo[o + j] = (uint8_t)((w[j >> 2] >> ((j & 3) * 8)) & 1u);
+      }
     }
-    if (lo) for (int j = 0; j < nx; ++j) lo[o + j] = v[j];
+    if (lo) {
+      if (vec) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(lo + o + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+      } else {
+        for (int j = 0; j < nx; ++j) lo[o + j] = v[j];
+      }
+    }
   }
 }
 
@@ -152,7 +206,7 @@ extern "C" int csam_mask_post_stats(const csam_post_args* a, void* stream) {
   post_init_kernel<<<(a->P + 255) / 256, 256, 0, st>>>(a->counts, a->boxes, a->P);
   if (check_launch("post_init_kernel")) return 1;
   dim3 grid((g.out_h + POST_ROWS - 1) / POST_ROWS, a->P);
-  post_stats_kernel<<<grid, 256, 0, st>>>(*a, g);
+  post_stats_kernel<<<grid, 256, 0, st>>>(*a, g, (g.out_w + 15) / 16);
   if (check_launch("post_stats_kernel")) return 1;
   post_finalize_kernel<<<(a->P + 255) / 256, 256, 0, st>>>(a->boxes, a->P);
   return check_launch("post_finalize_kernel");
@@ -166,7 +220,7 @@ extern "C" int csam_mask_post_write(const csam_post_args* a, void* stream) {
   CSAM_REQUIRE((a->masks || a->logits) && n > 0 && n <= 65535, "csam_mask_post_write: need an output, n <= 65535");
   const int segs = (g.out_w + 15) / 16;
   const int total = g.out_h * segs;
-  dim3 grid(min((total + 255) / 256, 64), n);
+  dim3 grid(min((total + 255) / 256, 256), n);
   post_write_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a, g, segs);
   return check_launch("post_write_kernel");
 }

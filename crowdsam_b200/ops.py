@@ -21,8 +21,9 @@ class Profiler:
     """Per-kernel-class CUDA-event timing on the launching stream (bench.py roofline numbers).
     Each record is (start_event, stop_event, work) with work = algorithmic FLOPs or bytes of that launch."""
 
-    def __init__(self):
+    def __init__(self, detail: bool = False):
         self.records = {}
+        self.detail = detail      # also key GEMM records by shape
 
     def begin(self):
         e = torch.cuda.Event(enable_timing=True)
@@ -132,6 +133,8 @@ def gemm(a: H16, w: H16, *, bias=None, act=ACT_NONE, residual=None, res_mod=0, r
     tok = _pb()
     L.check(L.load().csam_gemm(C.byref(g), _stream()), "csam_gemm")
     _pe("gemm", tok, 2.0 * M * N * K)
+    if tok is not None and PROFILER.detail:
+        PROFILER.end(f"gemm {M}x{N}x{K}", tok, 2.0 * M * N * K)
     return out_f32, out_h16
 
 

@@ -64,8 +64,14 @@ def _put_mlp(sd, g, name, dims: Sequence[int]):
 
 
 def make_sam_state(arch: str = "vit_l", n_class: int = 1, seed: int = 0,
-                   recipe_v1: bool = True) -> Dict[str, torch.Tensor]:
-    """State dict for `Sam` (segment_anything_cs/modeling/sam.py:16-47)."""
+                   recipe_v1: bool = True, recipe: str = "") -> Dict[str, torch.Tensor]:
+    """State dict for `Sam` (segment_anything_cs/modeling/sam.py:16-47).
+    recipe "v1" = SURVEY.md §8d (used for the reduced-depth golden archs); "v2" (default for the full-depth
+    archs) additionally zeroes the last hypernetwork bias and centres the classifier logit, because with
+    24-layer encoders v1 gives masks with a large negative mean (stability 0.60, 3% pass) and classifier
+    logits around -6 (scores < 0.1), i.e. nothing reaches NMS [measured with the oracle on ViT-L]."""
+    if not recipe:
+        recipe = "v1" if arch.startswith("tiny") else "v2"
     D, depth, heads, glob = SAM_ARCHS[arch]
     hd = D // heads
     g = torch.Generator().manual_seed(seed)
@@ -145,6 +151,10 @@ def make_sam_state(arch: str = "vit_l", n_class: int = 1, seed: int = 0,
         sd[f"{m}.iou_prediction_head.layers.2.weight"] *= 10.0
         sd[f"{m}.iou_prediction_head.layers.2.bias"] = torch.full((4,), 0.5)
         sd[f"{m}.point_classifier.layers.1.weight"] *= 50.0
+        if recipe == "v2":
+            for i in range(4):
+                sd[f"{m}.output_hypernetworks_mlps.{i}.layers.2.bias"].zero_()
+            sd[f"{m}.point_classifier.layers.1.bias"] = torch.full((n_class,), 6.0)
     return sd
 
 

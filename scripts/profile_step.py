@@ -40,6 +40,10 @@ if "--stats" in sys.argv:
 for i in range(n_steps):
     np.random.seed(42)
     l0 = lib.launch_count()
+    if i == n_steps - 1:
+        torch.cuda.nvtx.range_push("step")
     model.run_resident(imgs[i])
     torch.cuda.synchronize()
+    if i == n_steps - 1:
+        torch.cuda.nvtx.range_pop()
     print("step", i, "launches", lib.launch_count() - l0, "counts", model.last_counts)
