@@ -4,7 +4,17 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor 2D, 128B swizzle, mbarrier complete_tx)
 //   warp 1      MMA issuer     (one lane issues tcgen05.mma kind::f16, accumulators in TMEM)
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue       (tcgen05.ld 32x32b -> bias/act/LayerScale/residual -> global)
+//   warps 4..11 epilogue       (tcgen05.ld 32x32b -> fused epilogue -> global); two warps per TMEM lane
+//                              quadrant, each owning half of the tile's columns
+// Epilogue variants (template EPI):
+//   EPI_STD  bias / GELU / ReLU / LayerScale / row scale / residual / row scatter, fp32 + h16-pair outputs
+//   EPI_LN   N == 256: residual add + LayerNorm over the full row + (y, y+pe) h16 pairs + fp32 y
+//            (decoder image->token out_proj fused with norm4, transformer.py:184-190)
+//   EPI_UP1  N == 256 = 4 positions x 64 ch of ConvTranspose2d#1: bias + LayerNorm2d(64) + GELU, stored
+//            pixel-shuffled as the h16-pair operand of ConvTranspose2d#2 (mask_decoder.py:56-60)
+//   EPI_UP2  N == 128 = 4 positions x 32 ch of ConvTranspose2d#2: bias + GELU + dot with the 4 hypernetwork
+//            vectors of the prompt -> low-res mask logits (mask_decoder.py:61-62,175-181); the upscaled
+//            embedding [P,32,256,256] (8.4 MB / prompt) never reaches HBM
 // Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
 // "h16 pair" operands (hi + lo) turn every k-step into 3 MMAs (hi*hi + lo*hi + hi*lo) for
 // fp32-level accuracy; with lo == NULL it is a plain single-pass fp16 GEMM.
@@ -22,7 +32,13 @@ struct GemmEpi {
   float* out_f32; int ldo;
   __half* out_hi; __half* out_lo; int ldh;
   int vec_ok;   // all strides / bases allow 16-byte vector access
+  // fused epilogues
+  const float* gamma; const float* beta; float eps;
+  const float* pe; int ldpe; int pe_mod; __half* out2_hi; __half* out2_lo;
+  const float* hyper; float* masks;
 };
+
+enum { EPI_STD = 0, EPI_LN = 1, EPI_UP1 = 2, EPI_UP2 = 3 };
 
 // v[0..NV) are the raw accumulators of row r, columns [c0, c0+NV)
 template <int NV>
@@ -82,7 +98,7 @@ __device__ __forceinline__ void epi_store(const GemmEpi& e, int r, int c0, float
 constexpr int BM = 128;
 constexpr int BK = 64;           // 64 fp16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;   // 4 control warps + 8 epilogue warps
 
 template <int BN, int SPLIT>
 struct GemmCfg {
@@ -92,10 +108,10 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = NOPS * (A_BYTES + W_BYTES);
   static constexpr int STAGES = (SPLIT == 3) ? (BN >= 256 ? 2 : 3) : (BN >= 256 ? 4 : 6);
   static constexpr int TMEM_COLS = 2 * BN;                    // two accumulator buffers
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*epilogue scratch*/;
 };
 
-template <int BN, int SPLIT, bool B_MN>
+template <int BN, int SPLIT, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant__ CUtensorMap ta_lo,
                const __grid_constant__ CUtensorMap tw_hi, const __grid_constant__ CUtensorMap tw_lo,
@@ -109,6 +125,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);   // 4 KB epilogue scratch
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -122,7 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 128); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 256); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -200,25 +217,169 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const int q = warp - 4;                      // TMEM lane quadrant == warp % 4
+    const int ew = warp - 4;
+    const int q = ew & 3;                        // TMEM lane quadrant == warp % 4
+    const int ch = ew >> 2;                      // which half of the tile's columns this warp owns
+    constexpr int HALF = BN / 2;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     int local = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
       const int buf = local & 1;
       const uint32_t bphase = (local >> 1) & 1;
       const int m0 = (t % tiles_m) * BM;
       const int n0 = (t / tiles_m) * BN;
+      if constexpr (EPI == EPI_UP2) {
+        // stage the 4 x 32 hypernetwork vectors of this tile's prompt (all 128 rows share it)
+        const int et = threadIdx.x - 128;
+        if (et < 128) epi_smem[buf * 128 + et] = e.hyper[(size_t)(m0 >> 14) * 128 + et];
+        asm volatile("bar.sync 5, 256;" ::: "memory");
+      }
       mbar_wait(&tfull_bar[buf], bphase);
       tc_fence_after();
       const int r = m0 + q * 32 + lane;
+      const uint32_t col_addr = lane_addr + buf * BN + ch * HALF;
+      if constexpr (EPI == EPI_STD) {
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c, raw);
-        tmem_ld_wait();
-        float v[32];
+        for (int c = 0; c < HALF; c += 32) {
+          uint32_t raw[32];
+          tmem_ld32(col_addr + c, raw);
+          tmem_ld_wait();
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        epi_store<32>(e, r, n0 + c, v);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          epi_store<32>(e, r, n0 + ch * HALF + c, v);
+        }
+      } else if constexpr (EPI == EPI_LN) {
+        // full-row LayerNorm: this thread owns columns [ch*128, ch*128+128) of row r
+        static_assert(EPI != EPI_LN || BN == 256, "EPI_LN needs the whole 256-wide row in one tile");
+        const bool valid = r < e.M;
+        const int rr = e.res_mod > 0 ? (r % e.res_mod) : r;
+        const float* res = (e.residual && valid) ? e.residual + (size_t)rr * e.ldr + ch * 128 : nullptr;
+        float x[128];
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 128; c += 32) {
+          uint32_t raw[32];
+          tmem_ld32(col_addr + c, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = e.bias ? *reinterpret_cast<const float4*>(e.bias + ch * 128 + c + j) : make_float4(0, 0, 0, 0);
+            const float4 rv = res ? *reinterpret_cast<const float4*>(res + c + j) : make_float4(0, 0, 0, 0);
+            x[c + j + 0] = __uint_as_float(raw[j + 0]) + b.x + rv.x;
+            x[c + j + 1] = __uint_as_float(raw[j + 1]) + b.y + rv.y;
+            x[c + j + 2] = __uint_as_float(raw[j + 2]) + b.z + rv.z;
+            x[c + j + 3] = __uint_as_float(raw[j + 3]) + b.w + rv.w;
+            sum += (x[c + j] + x[c + j + 1]) + (x[c + j + 2] + x[c + j + 3]);
+          }
+        }
+        // accumulator drained: release the TMEM buffer before the (long) normalise + store phase
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[buf]);
+        float* ex_sum = epi_smem;            // [2][128]
+        float* ex_sq = epi_smem + 256;       // [2][128]
+        const int row_in_tile = q * 32 + lane;
+        ex_sum[ch * 128 + row_in_tile] = sum;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        const float mean = (ex_sum[row_in_tile] + ex_sum[128 + row_in_tile]) * (1.0f / 256.0f);
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 128; ++j) { const float d = x[j] - mean; sq = fmaf(d, d, sq); }
+        ex_sq[ch * 128 + row_in_tile] = sq;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        const float rstd = 1.0f / sqrtf((ex_sq[row_in_tile] + ex_sq[128 + row_in_tile]) * (1.0f / 256.0f) + e.eps);
+        if (valid) {
+          const float* pe = e.pe ? e.pe + (size_t)(e.pe_mod > 0 ? r % e.pe_mod : r) * e.ldpe + ch * 128 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 128; j += 8) {
+            float y[8], z[8];
+#pragma unroll
+            for (int u = 0; u < 8; u += 4) {
+              const float4 g = *reinterpret_cast<const float4*>(e.gamma + ch * 128 + j + u);
+              const float4 b = *reinterpret_cast<const float4*>(e.beta + ch * 128 + j + u);
+              y[u + 0] = (x[j + u + 0] - mean) * rstd * g.x + b.x;
+              y[u + 1] = (x[j + u + 1] - mean) * rstd * g.y + b.y;
+              y[u + 2] = (x[j + u + 2] - mean) * rstd * g.z + b.z;
+              y[u + 3] = (x[j + u + 3] - mean) * rstd * g.w + b.w;
+            }
+            const size_t col = (size_t)ch * 128 + j;
+            if (e.out_f32) {
+              *reinterpret_cast<float4*>(e.out_f32 + (size_t)r * e.ldo + col) = make_float4(y[0], y[1], y[2], y[3]);
+              *reinterpret_cast<float4*>(e.out_f32 + (size_t)r * e.ldo + col + 4) = make_float4(y[4], y[5], y[6], y[7]);
+            }
+            if (e.out_hi) store_pair8(e.out_hi, e.out_lo, (size_t)r * e.ldh + col, y);
+            if (e.out2_hi) {
+              const float4 p0 = *reinterpret_cast<const float4*>(pe + j);
+              const float4 p1 = *reinterpret_cast<const float4*>(pe + j + 4);
+              z[0] = y[0] + p0.x; z[1] = y[1] + p0.y; z[2] = y[2] + p0.z; z[3] = y[3] + p0.w;
+              z[4] = y[4] + p1.x; z[5] = y[5] + p1.y; z[6] = y[6] + p1.z; z[7] = y[7] + p1.w;
+              store_pair8(e.out2_hi, e.out2_lo, (size_t)r * e.ldh + col, z);
+            }
+          }
+        }
+        continue;   // tempty already signalled
+      } else if constexpr (EPI == EPI_UP1) {
+        // two of the four (dy,dx) positions per warp half: pos = ch*2 + g
+        const bool valid = r < e.M;
+        const int p = r >> 12, pix = r & 4095, yy = pix >> 6, xx = pix & 63;
+#pragma unroll 1
+        for (int gI = 0; gI < 2; ++gI) {
+          const int pos = ch * 2 + gI;
+          float x[64];
+          float sum = 0.f;
+#pragma unroll
+          for (int c = 0; c < 64; c += 32) {
+            uint32_t raw[32];
+            tmem_ld32(col_addr + gI * 64 + c, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              x[c + j] = __uint_as_float(raw[j]) + e.bias[pos * 64 + c + j];
+              sum += x[c + j];
+            }
+          }
+          const float mean = sum * (1.0f / 64.0f);
+          float sq = 0.f;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) { const float d = x[j] - mean; sq = fmaf(d, d, sq); }
+          const float rstd = 1.0f / sqrtf(sq * (1.0f / 64.0f) + e.eps);
+          if (valid) {
+            const size_t orow = (size_t)p * 16384 + (size_t)(2 * yy + (pos >> 1)) * 128 + (2 * xx + (pos & 1));
+#pragma unroll
+            for (int j = 0; j < 64; j += 8) {
+              float y[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) y[u] = gelu_erf((x[j + u] - mean) * rstd * e.gamma[j + u] + e.beta[j + u]);
+              store_pair8(e.out_hi, e.out_lo, orow * 64 + j, y);
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_UP2) {
+        // row r = p*16384 + Y1*128 + X1 ; this warp half handles dy = ch, dx = 0,1 (32 channels each)
+        const bool valid = r < e.M;
+        const int p = r >> 14, pix = r & 16383, Y1 = pix >> 7, X1 = pix & 127;
+        const float* hy = epi_smem + buf * 128;
+        float mk[4][2];
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          uint32_t raw[32];
+          tmem_ld32(col_addr + dx * 32, raw);
+          tmem_ld_wait();
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float u = gelu_erf(__uint_as_float(raw[j]) + e.bias[(ch * 2 + dx) * 32 + j]);
+            a0 = fmaf(u, hy[j], a0); a1 = fmaf(u, hy[32 + j], a1);
+            a2 = fmaf(u, hy[64 + j], a2); a3 = fmaf(u, hy[96 + j], a3);
+          }
+          mk[0][dx] = a0; mk[1][dx] = a1; mk[2][dx] = a2; mk[3][dx] = a3;
+        }
+        if (valid) {
+          const int Y = 2 * Y1 + ch, X0 = 2 * X1;
+#pragma unroll
+          for (int l = 0; l < 4; ++l)
+            *reinterpret_cast<float2*>(e.masks + (((size_t)p * 4 + l) * 256 + Y) * 256 + X0) = make_float2(mk[l][0], mk[l][1]);
+        }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[buf]);
@@ -312,7 +473,7 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int SPLIT, bool B_MN>
+template <int BN, int SPLIT, bool B_MN, int EPI = EPI_STD>
 static int launch_tc(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st) {
   using Cfg = GemmCfg<BN, SPLIT>;
   CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
@@ -328,7 +489,7 @@ static int launch_tc(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st)
     tw_lo = tw_hi;
     if (SPLIT == 3 && make_tmap_2d_f16(&tw_lo, a->w_lo, a->K, a->N, a->ldw, BK, 64)) return 1;
   }
-  auto kern = gemm_tc_kernel<BN, SPLIT, B_MN>;
+  auto kern = gemm_tc_kernel<BN, SPLIT, B_MN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
@@ -351,8 +512,12 @@ extern "C" int csam_gemm(const csam_gemm_args* a, void* stream) {
   CSAM_REQUIRE(a && a->a_hi && a->w_hi, "csam_gemm: null operand");
   CSAM_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "csam_gemm: empty problem");
   CSAM_REQUIRE((a->a_lo == nullptr) == (a->w_lo == nullptr), "csam_gemm: both operands must be split or neither");
-  CSAM_REQUIRE(a->out_f32 || a->out_hi, "csam_gemm: no output");
+  CSAM_REQUIRE(a->out_f32 || a->out_hi || a->masks, "csam_gemm: no output");
   GemmEpi e;
+  e.gamma = a->gamma; e.beta = a->beta; e.eps = a->eps;
+  e.pe = a->pe; e.ldpe = a->ldpe; e.pe_mod = a->pe_mod;
+  e.out2_hi = static_cast<__half*>(a->out2_hi); e.out2_lo = static_cast<__half*>(a->out2_lo);
+  e.hyper = a->hyper; e.masks = a->masks;
   e.M = a->M; e.N = a->N;
   e.bias = a->bias; e.row_scale = a->row_scale; e.col_scale = a->col_scale; e.act = a->act;
   e.residual = a->residual; e.ldr = a->ldr; e.res_mod = a->res_mod; e.row_map = a->row_map;
@@ -379,6 +544,24 @@ extern "C" int csam_gemm(const csam_gemm_args* a, void* stream) {
   CSAM_REQUIRE((a->lda % 8) == 0 && (a->ldw % 8) == 0, "csam_gemm: lda/ldw must be multiples of 8");
   const bool split = a->a_lo != nullptr;
   const bool small_n = a->N <= 64;
+  if (a->epi == CSAM_EPI_LN) {
+    CSAM_REQUIRE(a->N == 256 && a->gamma && a->beta && !a->row_map && !a->row_scale && !a->col_scale && a->act == 0,
+                 "csam_gemm(EPI_LN): N must be 256 with gamma/beta and no other epilogue options");
+    CSAM_REQUIRE(e.vec_ok && (!a->pe || ((a->ldpe & 3) == 0 && al16(a->pe))) && (!a->out2_hi || a->pe) &&
+                     al16(a->gamma) && al16(a->beta), "csam_gemm(EPI_LN): alignment");
+    return split ? launch_tc<256, 3, false, EPI_LN>(a, e, st) : launch_tc<256, 1, false, EPI_LN>(a, e, st);
+  }
+  if (a->epi == CSAM_EPI_UP1) {
+    CSAM_REQUIRE(a->N == 256 && (a->M % 4096) == 0 && a->bias && a->gamma && a->beta && a->out_hi,
+                 "csam_gemm(EPI_UP1): N = 4x64, M = P*4096, bias/gamma/beta and an h16 output are required");
+    return split ? launch_tc<256, 3, false, EPI_UP1>(a, e, st) : launch_tc<256, 1, false, EPI_UP1>(a, e, st);
+  }
+  if (a->epi == CSAM_EPI_UP2) {
+    CSAM_REQUIRE(a->N == 128 && (a->M % 16384) == 0 && a->bias && a->hyper && a->masks,
+                 "csam_gemm(EPI_UP2): N = 4x32, M = P*16384, bias, hyper and masks are required");
+    return split ? launch_tc<128, 3, false, EPI_UP2>(a, e, st) : launch_tc<128, 1, false, EPI_UP2>(a, e, st);
+  }
+  CSAM_REQUIRE(a->epi == CSAM_EPI_STD, "csam_gemm: unknown epilogue");
   if (a->b_mn_major) {
     CSAM_REQUIRE(!small_n, "csam_gemm: b_mn_major needs N > 64");
     return split ? launch_tc<128, 3, true>(a, e, st) : launch_tc<128, 1, true>(a, e, st);

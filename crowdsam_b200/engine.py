@@ -335,12 +335,15 @@ class MaskDecoderEngine:
                 qi = qi.view(P, 4096, 128)
             _, a = ops.attn_few_keys(qi, kt.view(P, 7, 128), vt.view(P, 7, 128), P, 4096, 7, 8, 16,
                                      want_h16=True, split=split)
-            if li == 0:
-                pre, _ = ia.o(a.view(P * 4096, 128), residual=I["keys0"], res_mod=4096, want_f32=True)
-            else:
-                pre, _ = ia.o(a.view(P * 4096, 128), residual=keys_f32, out_f32=keys_f32)
-            keys_f32, keys_h, keys_pe_h = ln(pre, Lr["n4"][0], Lr["n4"][1], 1e-5, out_f32=pre, want_h16=True,
-                                             split=split, pe=self.pe_tok, pe_mod=4096, want_out2=True)
+            # out_proj + residual + norm4 in one GEMM epilogue; emits keys (fp32, only needed as the next
+            # layer's residual), keys as h16 pair (v_proj / upscaling operand) and keys+pe (k/q_proj operand)
+            keys_h = H16.empty((P * 4096, 256), split, self.dev)
+            keys_pe_h = H16.empty((P * 4096, 256), split, self.dev)
+            nxt = torch.empty((P * 4096, 256), dtype=torch.float32, device=self.dev) if li == 0 else None
+            ia.o(a.view(P * 4096, 128), residual=(I["keys0"] if li == 0 else keys_f32), res_mod=(4096 if li == 0 else 0),
+                 epi=1, gamma=Lr["n4"][0], beta=Lr["n4"][1], eps=1e-5, out_f32=nxt, out_h16=keys_h, out2=keys_pe_h,
+                 pe=self.pe_tok, pe_mod=4096)
+            keys_f32 = nxt
         # final token -> image attention (transformer.py:104-112)
         fa = self.final
         qc, _ = fa.q(q_pe_h, want_f32=True)
@@ -351,22 +354,23 @@ class MaskDecoderEngine:
         pre, _ = fa.o(a.view(T, 128), residual=queries, want_f32=True)
         hs, hs_h, _ = ln(pre, self.nf[0], self.nf[1], 1e-5, want_f32=True, want_h16=True, split=split)
         del kc, vc, keys_pe_h, keys_f32, pre
-        # upscaling + hypernetwork masks (mask_decoder.py:172-181)
-        y1, _ = self.ct1(keys_h, want_f32=True)                                       # [P*4096, 4*64]
-        up1 = ops.upscale_shuffle_ln_gelu(y1, P, self.up_ln[0], self.up_ln[1], 1e-6, split)
-        del y1
-        y2, _ = self.ct2(up1, act=ACT_GELU, want_f32=True)                            # [P*16384, 4*32]
-        del up1
         hs2 = hs_h.view(P, 7 * 256)
 
         def cols(h: H16, c0: int, c1: int) -> H16:
             return H16(h.hi[:, c0:c1], None if h.lo is None else h.lo[:, c0:c1])
 
+        # hypernetwork MLPs first: their output is consumed by the fused upscaling epilogue
         hyper = torch.empty((P, 4, 32), dtype=torch.float32, device=self.dev)
         for l in range(4):
             self.hyper[l](cols(hs2, (1 + l) * 256, (2 + l) * 256), out_f32=hyper[:, l, :])
-        masks = ops.upscale_hyper_masks(y2, P, hyper)
-        del y2
+        # upscaling (mask_decoder.py:172-181): ConvT1 (+LN2d+GELU, pixel shuffle) and ConvT2 (+GELU + hypernet
+        # dot) are GEMMs with fused epilogues; the [P,32,256,256] upscaled embedding never exists in HBM
+        up1 = H16.empty((P * 16384, 64), split, self.dev)
+        ops.gemm(keys_h, self.ct1.w, bias=self.ct1.b, epi=2, gamma=self.up_ln[0], beta=self.up_ln[1], eps=1e-6,
+                 out_h16=up1)
+        masks = torch.empty((P, 4, 256, 256), dtype=torch.float32, device=self.dev)
+        ops.gemm(up1, self.ct2.w, bias=self.ct2.b, epi=3, hyper=hyper, masks=masks)
+        del up1
         # IoU head (mask_decoder.py:184)
         iou = self.iou_head(cols(hs2, 0, 256))                                         # [P,4]
         # PWD-Net (mask_decoder.py:187-198): softmax-weighted pooling of the DINO map as one GEMM

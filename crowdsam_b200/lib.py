@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libcsam_sm100.so")
+LIB_PATH = os.environ.get("CSAM_LIB_PATH", os.path.join(_HERE, "_C", "libcsam_sm100.so"))
 _lib = None
 
 vp, ci, cf, cll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
@@ -24,7 +24,10 @@ class GemmArgs(C.Structure):
                 ("row_map", vp),
                 ("out_f32", vp), ("ldo", ci),
                 ("out_hi", vp), ("out_lo", vp), ("ldh", ci),
-                ("impl", ci), ("b_mn_major", ci)]
+                ("impl", ci), ("b_mn_major", ci),
+                ("epi", ci), ("gamma", vp), ("beta", vp), ("eps", cf),
+                ("pe", vp), ("ldpe", ci), ("pe_mod", ci), ("out2_hi", vp), ("out2_lo", vp),
+                ("hyper", vp), ("masks", vp)]
 
 
 class LnArgs(C.Structure):
@@ -120,7 +123,7 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.csam_abi_version() != 1:
+    if lib.csam_abi_version() != 2:
         raise RuntimeError("libcsam_sm100.so ABI version mismatch")
     _lib = lib
     return lib

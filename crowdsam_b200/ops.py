@@ -14,7 +14,7 @@ ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 
 # GEMM / attention implementation switches (validation only): 0 = tcgen05, 1 = SIMT
 GEMM_IMPL = int(os.environ.get("CSAM_GEMM_IMPL", "0"))
-ATTN_IMPL = int(os.environ.get("CSAM_ATTN_IMPL", "1"))   # tcgen05 attention pending
+ATTN_IMPL = int(os.environ.get("CSAM_ATTN_IMPL", "0"))
 
 
 class Profiler:
@@ -102,8 +102,10 @@ class H16:
 
 def gemm(a: H16, w: H16, *, bias=None, act=ACT_NONE, residual=None, res_mod=0, row_map=None,
          row_scale=None, col_scale=None, out_f32=None, out_h16: Optional[H16] = None,
-         want_f32=False, want_h16=False, impl=None, b_mn_major=False, M=None):
-    """out = epilogue(a[M,K] @ w[N,K]^T); returns (fp32 or None, H16 or None)."""
+         want_f32=False, want_h16=False, impl=None, b_mn_major=False, M=None,
+         epi=0, gamma=None, beta=None, eps=0.0, pe=None, pe_mod=0, out2: Optional[H16] = None, hyper=None, masks=None):
+    """out = epilogue(a[M,K] @ w[N,K]^T); returns (fp32 or None, H16 or None).
+    epi: 0 standard, 1 full-row LayerNorm (N == 256), 2 ConvT1+LN2d+GELU shuffle, 3 ConvT2+GELU+hypernet dot."""
     assert a.hi.dim() == 2 and w.hi.dim() == 2
     M = a.hi.shape[0] if M is None else M
     K = a.hi.shape[1]
@@ -130,6 +132,16 @@ def gemm(a: H16, w: H16, *, bias=None, act=ACT_NONE, residual=None, res_mod=0, r
         g.out_hi, g.out_lo, g.ldh = _p(out_h16.hi), _p(out_h16.lo), out_h16.hi.stride(0)
     g.impl = GEMM_IMPL if impl is None else impl
     g.b_mn_major = 1 if b_mn_major else 0
+    g.epi, g.gamma, g.beta, g.eps = epi, _p(gamma), _p(beta), eps
+    g.pe, g.ldpe, g.pe_mod = _p(pe), (pe.stride(0) if pe is not None else 0), pe_mod
+    if out2 is not None:
+        g.out2_hi, g.out2_lo = _p(out2.hi), _p(out2.lo)
+        if out_h16 is not None:
+            assert out2.hi.stride(0) == out_h16.hi.stride(0)
+        g.ldh = out2.hi.stride(0)
+    g.hyper, g.masks = _p(hyper), _p(masks)
+    if epi != 0:
+        assert g.impl == 0, "fused epilogues exist on the tcgen05 path only"
     tok = _pb()
     L.check(L.load().csam_gemm(C.byref(g), _stream()), "csam_gemm")
     _pe("gemm", tok, 2.0 * M * N * K)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSAM_ABI_VERSION 1
+#define CSAM_ABI_VERSION 2
 #if defined(__GNUC__)
 #define CSAM_API __attribute__((visibility("default")))
 #else
@@ -52,6 +52,15 @@ CSAM_API long long csam_launch_count(void);
  * ------------------------------------------------------------------------------------------ */
 enum { CSAM_ACT_NONE = 0, CSAM_ACT_GELU = 1, CSAM_ACT_RELU = 2 };
 enum { CSAM_GEMM_TCGEN05 = 0, CSAM_GEMM_SIMT = 1 };   /* SIMT = slow validation kernel */
+/* fused epilogues of the mask decoder (tcgen05 only):
+ *  CSAM_EPI_LN   N == 256: y = LayerNorm(acc + bias + residual) * gamma + beta over the whole row;
+ *                outputs (each optional): out_f32 = y, h16 pair (out_hi/lo) = y, h16 pair (out2_hi/lo) =
+ *                y + pe[row % pe_mod].  transformer.py:184-190 (image->token out_proj + norm4).
+ *  CSAM_EPI_UP1  N == 256 (col = (dy*2+dx)*64 + c), M = P*4096: ConvTranspose2d#1 + LayerNorm2d(64) + GELU,
+ *                written pixel-shuffled as h16 pair [P*16384, 64].  mask_decoder.py:56-60.
+ *  CSAM_EPI_UP2  N == 128 (col = (dy*2+dx)*32 + c), M = P*16384: ConvTranspose2d#2 + GELU + dot with
+ *                hyper[P,4,32] -> masks fp32 [P,4,256,256].  mask_decoder.py:61-62,175-181. */
+enum { CSAM_EPI_STD = 0, CSAM_EPI_LN = 1, CSAM_EPI_UP1 = 2, CSAM_EPI_UP2 = 3 };
 
 typedef struct {
   const void* a_hi; const void* a_lo;     /* [M,K] fp16, row stride lda (elements, multiple of 8) */
@@ -67,6 +76,10 @@ typedef struct {
   void* out_hi; void* out_lo; int ldh;    /* optional h16-pair output */
   int impl;                               /* CSAM_GEMM_TCGEN05 / CSAM_GEMM_SIMT */
   int b_mn_major;                         /* 1: W given as [K,N] row-major (ldw = N stride) */
+  int epi;                                /* CSAM_EPI_* */
+  const float* gamma; const float* beta; float eps;          /* EPI_LN / EPI_UP1 */
+  const float* pe; int ldpe; int pe_mod; void* out2_hi; void* out2_lo;   /* EPI_LN second output */
+  const float* hyper; float* masks;                          /* EPI_UP2 */
 } csam_gemm_args;
 CSAM_API int csam_gemm(const csam_gemm_args* a, void* stream);
 

@@ -419,3 +419,67 @@ def test_rle_occupancy_overlap(golden_dir):
     small = torch.nn.functional.interpolate(masks.float().unsqueeze(0), (150, 150))[0].bool()
     ref_i = (small[:, None] & small[None]).flatten(2).sum(-1)
     assert torch.equal(inter.cpu().long(), ref_i) and torch.equal(area.cpu().long(), small.flatten(1).sum(1))
+
+
+# ----------------------------------------------------------------- fused decoder GEMM epilogues
+@pytest.mark.skipif(0 not in IMPLS, reason="tcgen05 only")
+@pytest.mark.parametrize("split", [True, False])
+def test_gemm_epilogue_layernorm256(split):
+    """out_proj + residual (broadcast over prompts) + LayerNorm + (y, y+pe) outputs in one kernel."""
+    o = ops()
+    g = torch.Generator().manual_seed(21)
+    M, K = 3 * 200 + 37, 128
+    a, w = torch.randn(M, K, generator=g), torch.randn(256, K, generator=g) * 0.2
+    bias, gam, bet = torch.randn(256, generator=g), torch.randn(256, generator=g), torch.randn(256, generator=g)
+    res, pe = torch.randn(200, 256, generator=g), torch.randn(200, 256, generator=g)
+    ah, wh = _h16(a, split), _h16(w, split)
+    x = ah.float().cpu().double() @ wh.float().cpu().double().T + bias.double() + res.double()[torch.arange(M) % 200]
+    ref = torch.nn.functional.layer_norm(x, (256,), gam.double(), bet.double(), 1e-5)
+    out = torch.empty(M, 256, device=DEV)
+    oh, o2 = o.H16.empty((M, 256), split, DEV), o.H16.empty((M, 256), split, DEV)
+    o.gemm(ah, wh, bias=bias.to(DEV), residual=res.to(DEV), res_mod=200, epi=1, gamma=gam.to(DEV), beta=bet.to(DEV),
+           eps=1e-5, out_f32=out, out_h16=oh, out2=o2, pe=pe.to(DEV), pe_mod=200)
+    assert _rel(out, ref) < 1e-5
+    tol = 1e-5 if split else 1e-3
+    assert _rel(oh.float(), ref) < tol
+    assert _rel(o2.float(), ref + pe.double()[torch.arange(M) % 200]) < tol
+    # no-residual / no-pe / fp32-only variant
+    out2 = torch.empty(M, 256, device=DEV)
+    o.gemm(ah, wh, bias=bias.to(DEV), epi=1, gamma=gam.to(DEV), beta=bet.to(DEV), eps=1e-5, out_f32=out2)
+    x2 = ah.float().cpu().double() @ wh.float().cpu().double().T + bias.double()
+    assert _rel(out2, torch.nn.functional.layer_norm(x2, (256,), gam.double(), bet.double(), 1e-5)) < 1e-5
+
+
+@pytest.mark.skipif(0 not in IMPLS, reason="tcgen05 only")
+def test_gemm_epilogue_upscaling():
+    """ConvT1 + LN2d + GELU (pixel shuffle) and ConvT2 + GELU + hypernetwork dot against F.conv_transpose2d."""
+    o = ops()
+    g = torch.Generator().manual_seed(22)
+    P = 2
+    src = torch.randn(P, 256, 64, 64, generator=g)
+    w1, b1 = torch.randn(256, 64, 2, 2, generator=g) * 0.06, torch.randn(64, generator=g) * 0.1
+    gam, bet = torch.randn(64, generator=g), torch.randn(64, generator=g)
+    w2, b2 = torch.randn(64, 32, 2, 2, generator=g) * 0.1, torch.randn(32, generator=g) * 0.1
+    hyper = torch.randn(P, 4, 32, generator=g)
+    keys = _h16(src.flatten(2).permute(0, 2, 1).reshape(P * 4096, 256).contiguous(), True)
+    w1g = _h16(w1.permute(2, 3, 1, 0).reshape(256, 256).contiguous(), True)
+    w2g = _h16(w2.permute(2, 3, 1, 0).reshape(128, 64).contiguous(), True)
+    up1 = o.H16.empty((P * 16384, 64), True, DEV)
+    o.gemm(keys, w1g, bias=b1.repeat(4).to(DEV), epi=2, gamma=gam.to(DEV), beta=bet.to(DEV), eps=1e-6, out_h16=up1)
+    # reference with the operands as the kernel sees them
+    srcq = keys.float().cpu().view(P, 4096, 256).permute(0, 2, 1).reshape(P, 256, 64, 64).double()
+    w1q = w1g.float().cpu().view(2, 2, 64, 256).permute(3, 2, 0, 1).double()
+    y = torch.nn.functional.conv_transpose2d(srcq, w1q, b1.double(), stride=2)            # [P,64,128,128]
+    u = y.mean(1, keepdim=True)
+    s2 = (y - u).pow(2).mean(1, keepdim=True)
+    y = (y - u) / torch.sqrt(s2 + 1e-6) * gam.double()[:, None, None] + bet.double()[:, None, None]
+    y = torch.nn.functional.gelu(y)
+    ref1 = y.permute(0, 2, 3, 1).reshape(P * 16384, 64)
+    assert _rel(up1.float(), ref1) < 1e-5
+    masks = torch.empty(P, 4, 256, 256, device=DEV)
+    o.gemm(up1, w2g, bias=b2.repeat(4).to(DEV), epi=3, hyper=hyper.to(DEV), masks=masks)
+    up1q = up1.float().cpu().view(P, 128, 128, 64).permute(0, 3, 1, 2).double()
+    w2q = w2g.float().cpu().view(2, 2, 32, 64).permute(3, 2, 0, 1).double()
+    z = torch.nn.functional.gelu(torch.nn.functional.conv_transpose2d(up1q, w2q, b2.double(), stride=2))   # [P,32,256,256]
+    refm = torch.einsum("plc,pchw->plhw", hyper.double(), z)
+    assert _rel(masks, refm) < 1e-5
