@@ -195,7 +195,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from crowdsam_b200 import lib, ops
+    from crowdsam_b200 import lib, ops, parallel
     from crowdsam_b200.build import _build_sam
     from crowdsam_b200.modules import DinoVisionTransformer
     from crowdsam_b200.pipeline import CrowdSAM
@@ -234,23 +234,8 @@ def main():
 
     def gather_dets(dets):
         """The one exchange step: all-gather of padded [K, Nmax, 6] detections + counts."""
-        if world == 1:
-            return
-        nmax = 64
-        buf = torch.zeros((len(dets), nmax, 6), device=dev)
-        cnt = torch.zeros((len(dets),), dtype=torch.int32, device=dev)
-        for i, d in enumerate(dets):
-            if d is None:
-                continue
-            n = min(len(d["boxes"]), nmax)
-            buf[i, :n, :4] = torch.as_tensor(d["boxes"][:n], device=dev).float()
-            buf[i, :n, 4] = torch.as_tensor(d["scores"][:n], device=dev).float()
-            buf[i, :n, 5] = torch.as_tensor(d["categories"][:n], device=dev).float()
-            cnt[i] = n
-        out = [torch.empty_like(buf) for _ in range(world)]
-        outc = [torch.empty_like(cnt) for _ in range(world)]
-        dist.all_gather(out, buf)
-        dist.all_gather(outc, cnt)
+        if world > 1:
+            parallel.gather_detections(dets, nmax=64, device=dev)
 
     # ---------------- device-resident leg (value) ----------------
     for i in range(args.warmup):

@@ -36,6 +36,7 @@ struct GemmEpi {
   const float* gamma; const float* beta; float eps;
   const float* pe; int ldpe; int pe_mod; __half* out2_hi; __half* out2_lo;
   const float* hyper; float* masks;
+  const __half* res_hi; const __half* res_lo; int ldrh;   // EPI_LN: residual given as an h16 pair
 };
 
 enum { EPI_STD = 0, EPI_LN = 1, EPI_UP1 = 2, EPI_UP2 = 3 };
@@ -92,6 +93,24 @@ __device__ __forceinline__ void epi_store(const GemmEpi& e, int r, int c0, float
   }
 }
 
+// ---- warp-private staging tile: 32 rows x 16 fp32 columns, float4 slots XOR-swizzled ---------------
+// tcgen05.ld hands every lane one ROW; global memory wants lanes along COLUMNS.  Each epilogue warp
+// transposes 16 columns at a time through 2 KB of shared memory so that bias / residual / pe reads and all
+// stores are coalesced 64-byte row segments (8 rows x 4 float4 per warp instruction).
+__device__ __forceinline__ int wb_off(int row, int slot) { return row * 16 + ((slot ^ ((row >> 1) & 3)) << 2); }
+__device__ __forceinline__ void stage_put(float* wb, int lane, const float* v) {
+#pragma unroll
+  for (int s = 0; s < 4; ++s)
+    *reinterpret_cast<float4*>(wb + wb_off(lane, s)) = make_float4(v[4 * s], v[4 * s + 1], v[4 * s + 2], v[4 * s + 3]);
+}
+__device__ __forceinline__ void stage_get(const float* wb, int lane, float* v) {
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const float4 t = *reinterpret_cast<const float4*>(wb + wb_off(lane, s));
+    v[4 * s] = t.x; v[4 * s + 1] = t.y; v[4 * s + 2] = t.z; v[4 * s + 3] = t.w;
+  }
+}
+
 // =========================================================================================
 // tcgen05 kernel
 // =========================================================================================
@@ -108,7 +127,8 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = NOPS * (A_BYTES + W_BYTES);
   static constexpr int STAGES = (SPLIT == 3) ? (BN >= 256 ? 2 : 3) : (BN >= 256 ? 4 : 6);
   static constexpr int TMEM_COLS = 2 * BN;                    // two accumulator buffers
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*epilogue scratch*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*epilogue scratch*/ +
+                                    8 * 2048 /*per-warp staging tiles*/;
 };
 
 template <int BN, int SPLIT, bool B_MN, int EPI>
@@ -238,38 +258,118 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
       tc_fence_after();
       const int r = m0 + q * 32 + lane;
       const uint32_t col_addr = lane_addr + buf * BN + ch * HALF;
+      float* wb = epi_smem + 1024 + ew * 512;          // this warp's 32x16 staging tile
+      const int row_base = m0 + q * 32;                // tile rows of this warp: row_base + 0..31
       if constexpr (EPI == EPI_STD) {
+        const bool staged = e.vec_ok && (e.N & 3) == 0;
+        const float rs = (e.row_scale && r < e.M) ? e.row_scale[r] : 1.f;
 #pragma unroll 1
-        for (int c = 0; c < HALF; c += 32) {
-          uint32_t raw[32];
-          tmem_ld32(col_addr + c, raw);
+        for (int c = 0; c < HALF; c += 16) {
+          const int col0 = n0 + ch * HALF + c;
+          if (col0 >= e.N) break;                      // warp-uniform
+          uint32_t raw[16];
+          tmem_ld16(col_addr + c, raw);
           tmem_ld_wait();
-          float v[32];
+          float v[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          epi_store<32>(e, r, n0 + ch * HALF + c, v);
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+          if (!staged) {                               // odd shapes (N = 1, 30, ...): per-lane scalar path
+            epi_store<16>(e, r, col0, v);
+            continue;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= rs;
+          stage_put(wb, lane, v);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + (lane >> 2), sl = lane & 3;
+            const int row = row_base + rr, col = col0 + sl * 4;
+            int orow = -1;
+            if (row < e.M) orow = e.row_map ? e.row_map[row] : row;
+            if (orow >= 0 && col < e.N) {
+              float4 x = *reinterpret_cast<const float4*>(wb + wb_off(rr, sl));
+              if (e.bias) { const float4 b = *reinterpret_cast<const float4*>(e.bias + col); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
+              x.x = apply_act(x.x, e.act); x.y = apply_act(x.y, e.act); x.z = apply_act(x.z, e.act); x.w = apply_act(x.w, e.act);
+              if (e.col_scale) { const float4 cs = *reinterpret_cast<const float4*>(e.col_scale + col); x.x *= cs.x; x.y *= cs.y; x.z *= cs.z; x.w *= cs.w; }
+              if (e.residual) {
+                const int rrow = e.res_mod > 0 ? (orow % e.res_mod) : orow;
+                const float4 rv = *reinterpret_cast<const float4*>(e.residual + (size_t)rrow * e.ldr + col);
+                x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
+              }
+              if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + (size_t)orow * e.ldo + col) = x;
+              if (e.out_hi) { const float y4[4] = {x.x, x.y, x.z, x.w}; store_pair4(e.out_hi, e.out_lo, (size_t)orow * e.ldh + col, y4); }
+            }
+          }
+          __syncwarp();
         }
       } else if constexpr (EPI == EPI_LN) {
-        // full-row LayerNorm: this thread owns columns [ch*128, ch*128+128) of row r
+        // full-row LayerNorm: this lane owns columns [ch*128, ch*128+128) of row r
         static_assert(EPI != EPI_LN || BN == 256, "EPI_LN needs the whole 256-wide row in one tile");
-        const bool valid = r < e.M;
-        const int rr = e.res_mod > 0 ? (r % e.res_mod) : r;
-        const float* res = (e.residual && valid) ? e.residual + (size_t)rr * e.ldr + ch * 128 : nullptr;
         float x[128];
         float sum = 0.f;
+        {
+          // pull the NEXT tile's residual rows towards L2 while this tile is normalised: the epilogue warps
+          // alone cannot keep enough loads in flight to hide HBM latency
+          const int tn = t + gridDim.x;
+          if (tn < num_tiles && e.res_mod == 0) {
+            const int prow = (tn % tiles_m) * BM + (threadIdx.x - 128) / 2;      // 256 threads -> 128 rows x 2 halves
+            const int phalf = (threadIdx.x - 128) & 1;
+            if (prow < e.M) {
+              if (e.residual) {
+                const char* pa = reinterpret_cast<const char*>(e.residual + (size_t)prow * e.ldr) + phalf * 512;
 #pragma unroll
-        for (int c = 0; c < 128; c += 32) {
-          uint32_t raw[32];
-          tmem_ld32(col_addr + c, raw);
+                for (int i = 0; i < 4; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + i * 128));
+              } else if (e.res_hi) {
+                const char* ph = reinterpret_cast<const char*>(e.res_hi + (size_t)prow * e.ldrh) + phalf * 256;
+                const char* pl = reinterpret_cast<const char*>(e.res_lo + (size_t)prow * e.ldrh) + phalf * 256;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(ph + i * 128));
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(pl + i * 128));
+                }
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 128; c += 16) {
+          const int colb = ch * 128 + c;
+          // residual tile, read coalesced, transposed to the row-per-lane layout
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + (lane >> 2), sl = lane & 3;
+            const int row = row_base + rr;
+            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < e.M) {
+              const int rrow = e.res_mod > 0 ? (row % e.res_mod) : row;
+              if (e.residual) {
+                rv = *reinterpret_cast<const float4*>(e.residual + (size_t)rrow * e.ldr + colb + sl * 4);
+              } else if (e.res_hi) {
+                const uint2 uh = *reinterpret_cast<const uint2*>(e.res_hi + (size_t)rrow * e.ldrh + colb + sl * 4);
+                const uint2 ul = *reinterpret_cast<const uint2*>(e.res_lo + (size_t)rrow * e.ldrh + colb + sl * 4);
+                const __half2 h0 = *reinterpret_cast<const __half2*>(&uh.x), h1 = *reinterpret_cast<const __half2*>(&uh.y);
+                const __half2 l0 = *reinterpret_cast<const __half2*>(&ul.x), l1 = *reinterpret_cast<const __half2*>(&ul.y);
+                rv.x = __low2float(h0) + __low2float(l0); rv.y = __high2float(h0) + __high2float(l0);
+                rv.z = __low2float(h1) + __low2float(l1); rv.w = __high2float(h1) + __high2float(l1);
+              }
+            }
+            *reinterpret_cast<float4*>(wb + wb_off(rr, sl)) = rv;
+          }
+          __syncwarp();
+          float rv16[16];
+          stage_get(wb, lane, rv16);
+          __syncwarp();
+          uint32_t raw[16];
+          tmem_ld16(col_addr + c, raw);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = e.bias ? *reinterpret_cast<const float4*>(e.bias + ch * 128 + c + j) : make_float4(0, 0, 0, 0);
-            const float4 rv = res ? *reinterpret_cast<const float4*>(res + c + j) : make_float4(0, 0, 0, 0);
-            x[c + j + 0] = __uint_as_float(raw[j + 0]) + b.x + rv.x;
-            x[c + j + 1] = __uint_as_float(raw[j + 1]) + b.y + rv.y;
-            x[c + j + 2] = __uint_as_float(raw[j + 2]) + b.z + rv.z;
-            x[c + j + 3] = __uint_as_float(raw[j + 3]) + b.w + rv.w;
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b = e.bias ? *reinterpret_cast<const float4*>(e.bias + colb + j) : make_float4(0, 0, 0, 0);
+            x[c + j + 0] = __uint_as_float(raw[j + 0]) + b.x + rv16[j + 0];
+            x[c + j + 1] = __uint_as_float(raw[j + 1]) + b.y + rv16[j + 1];
+            x[c + j + 2] = __uint_as_float(raw[j + 2]) + b.z + rv16[j + 2];
+            x[c + j + 3] = __uint_as_float(raw[j + 3]) + b.w + rv16[j + 3];
             sum += (x[c + j] + x[c + j + 1]) + (x[c + j + 2] + x[c + j + 3]);
           }
         }
@@ -288,54 +388,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
         ex_sq[ch * 128 + row_in_tile] = sq;
         asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
         const float rstd = 1.0f / sqrtf((ex_sq[row_in_tile] + ex_sq[128 + row_in_tile]) * (1.0f / 256.0f) + e.eps);
-        if (valid) {
-          const float* pe = e.pe ? e.pe + (size_t)(e.pe_mod > 0 ? r % e.pe_mod : r) * e.ldpe + ch * 128 : nullptr;
 #pragma unroll
-          for (int j = 0; j < 128; j += 8) {
-            float y[8], z[8];
+        for (int c = 0; c < 128; c += 16) {
+          const int colb = ch * 128 + c;
+          float nv[16];
 #pragma unroll
-            for (int u = 0; u < 8; u += 4) {
-              const float4 g = *reinterpret_cast<const float4*>(e.gamma + ch * 128 + j + u);
-              const float4 b = *reinterpret_cast<const float4*>(e.beta + ch * 128 + j + u);
-              y[u + 0] = (x[j + u + 0] - mean) * rstd * g.x + b.x;
-              y[u + 1] = (x[j + u + 1] - mean) * rstd * g.y + b.y;
-              y[u + 2] = (x[j + u + 2] - mean) * rstd * g.z + b.z;
-              y[u + 3] = (x[j + u + 3] - mean) * rstd * g.w + b.w;
-            }
-            const size_t col = (size_t)ch * 128 + j;
-            if (e.out_f32) {
-              *reinterpret_cast<float4*>(e.out_f32 + (size_t)r * e.ldo + col) = make_float4(y[0], y[1], y[2], y[3]);
-              *reinterpret_cast<float4*>(e.out_f32 + (size_t)r * e.ldo + col + 4) = make_float4(y[4], y[5], y[6], y[7]);
-            }
-            if (e.out_hi) store_pair8(e.out_hi, e.out_lo, (size_t)r * e.ldh + col, y);
-            if (e.out2_hi) {
-              const float4 p0 = *reinterpret_cast<const float4*>(pe + j);
-              const float4 p1 = *reinterpret_cast<const float4*>(pe + j + 4);
-              z[0] = y[0] + p0.x; z[1] = y[1] + p0.y; z[2] = y[2] + p0.z; z[3] = y[3] + p0.w;
-              z[4] = y[4] + p1.x; z[5] = y[5] + p1.y; z[6] = y[6] + p1.z; z[7] = y[7] + p1.w;
-              store_pair8(e.out2_hi, e.out2_lo, (size_t)r * e.ldh + col, z);
+          for (int j = 0; j < 16; ++j) nv[j] = (x[c + j] - mean) * rstd;
+          stage_put(wb, lane, nv);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + (lane >> 2), sl = lane & 3;
+            const int row = row_base + rr, col = colb + sl * 4;
+            if (row < e.M) {
+              const float4 n4 = *reinterpret_cast<const float4*>(wb + wb_off(rr, sl));
+              const float4 g4 = *reinterpret_cast<const float4*>(e.gamma + col);
+              const float4 b4 = *reinterpret_cast<const float4*>(e.beta + col);
+              const float y[4] = {n4.x * g4.x + b4.x, n4.y * g4.y + b4.y, n4.z * g4.z + b4.z, n4.w * g4.w + b4.w};
+              if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ldo + col) = make_float4(y[0], y[1], y[2], y[3]);
+              if (e.out_hi) store_pair4(e.out_hi, e.out_lo, (size_t)row * e.ldh + col, y);
+              if (e.out2_hi) {
+                const float4 p4 = *reinterpret_cast<const float4*>(e.pe + (size_t)(e.pe_mod > 0 ? row % e.pe_mod : row) * e.ldpe + col);
+                const float z[4] = {y[0] + p4.x, y[1] + p4.y, y[2] + p4.z, y[3] + p4.w};
+                store_pair4(e.out2_hi, e.out2_lo, (size_t)row * e.ldh + col, z);
+              }
             }
           }
+          __syncwarp();
         }
         continue;   // tempty already signalled
       } else if constexpr (EPI == EPI_UP1) {
         // two of the four (dy,dx) positions per warp half: pos = ch*2 + g
-        const bool valid = r < e.M;
-        const int p = r >> 12, pix = r & 4095, yy = pix >> 6, xx = pix & 63;
 #pragma unroll 1
         for (int gI = 0; gI < 2; ++gI) {
           const int pos = ch * 2 + gI;
           float x[64];
           float sum = 0.f;
 #pragma unroll
-          for (int c = 0; c < 64; c += 32) {
-            uint32_t raw[32];
-            tmem_ld32(col_addr + gI * 64 + c, raw);
+          for (int c = 0; c < 64; c += 16) {
+            uint32_t raw[16];
+            tmem_ld16(col_addr + gI * 64 + c, raw);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              x[c + j] = __uint_as_float(raw[j]) + e.bias[pos * 64 + c + j];
-              sum += x[c + j];
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b = *reinterpret_cast<const float4*>(e.bias + pos * 64 + c + j);
+              x[c + j + 0] = __uint_as_float(raw[j + 0]) + b.x;
+              x[c + j + 1] = __uint_as_float(raw[j + 1]) + b.y;
+              x[c + j + 2] = __uint_as_float(raw[j + 2]) + b.z;
+              x[c + j + 3] = __uint_as_float(raw[j + 3]) + b.w;
+              sum += (x[c + j] + x[c + j + 1]) + (x[c + j + 2] + x[c + j + 3]);
             }
           }
           const float mean = sum * (1.0f / 64.0f);
@@ -343,15 +444,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 64; ++j) { const float d = x[j] - mean; sq = fmaf(d, d, sq); }
           const float rstd = 1.0f / sqrtf(sq * (1.0f / 64.0f) + e.eps);
-          if (valid) {
-            const size_t orow = (size_t)p * 16384 + (size_t)(2 * yy + (pos >> 1)) * 128 + (2 * xx + (pos & 1));
 #pragma unroll
-            for (int j = 0; j < 64; j += 8) {
-              float y[8];
+          for (int c = 0; c < 64; c += 16) {
+            float nv[16];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) y[u] = gelu_erf((x[j + u] - mean) * rstd * e.gamma[j + u] + e.beta[j + u]);
-              store_pair8(e.out_hi, e.out_lo, orow * 64 + j, y);
+            for (int j = 0; j < 16; ++j) nv[j] = (x[c + j] - mean) * rstd;
+            stage_put(wb, lane, nv);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int rr = it * 8 + (lane >> 2), sl = lane & 3;
+              const int row = row_base + rr, col = c + sl * 4;
+              if (row < e.M) {
+                const int p = row >> 12, pix = row & 4095, yy = pix >> 6, xx = pix & 63;
+                const size_t orow = (size_t)p * 16384 + (size_t)(2 * yy + (pos >> 1)) * 128 + (2 * xx + (pos & 1));
+                const float4 n4 = *reinterpret_cast<const float4*>(wb + wb_off(rr, sl));
+                const float4 g4 = *reinterpret_cast<const float4*>(e.gamma + col);
+                const float4 b4 = *reinterpret_cast<const float4*>(e.beta + col);
+                const float y[4] = {gelu_erf(n4.x * g4.x + b4.x), gelu_erf(n4.y * g4.y + b4.y),
+                                    gelu_erf(n4.z * g4.z + b4.z), gelu_erf(n4.w * g4.w + b4.w)};
+                store_pair4(e.out_hi, e.out_lo, orow * 64 + col, y);
+              }
             }
+            __syncwarp();
           }
         }
       } else if constexpr (EPI == EPI_UP2) {
@@ -518,6 +633,9 @@ extern "C" int csam_gemm(const csam_gemm_args* a, void* stream) {
   e.pe = a->pe; e.ldpe = a->ldpe; e.pe_mod = a->pe_mod;
   e.out2_hi = static_cast<__half*>(a->out2_hi); e.out2_lo = static_cast<__half*>(a->out2_lo);
   e.hyper = a->hyper; e.masks = a->masks;
+  e.res_hi = static_cast<const __half*>(a->res_hi); e.res_lo = static_cast<const __half*>(a->res_lo); e.ldrh = a->ldrh;
+  CSAM_REQUIRE(!a->res_hi || (a->epi == CSAM_EPI_LN && a->res_lo && !a->residual && (a->ldrh & 3) == 0),
+               "csam_gemm: an h16-pair residual is supported by EPI_LN only (both halves, no fp32 residual)");
   e.M = a->M; e.N = a->N;
   e.bias = a->bias; e.row_scale = a->row_scale; e.col_scale = a->col_scale; e.act = a->act;
   e.residual = a->residual; e.ldr = a->ldr; e.res_mod = a->res_mod; e.row_map = a->row_map;

@@ -92,6 +92,148 @@ __global__ void post_finalize_kernel(int* boxes, int P) {
   }
 }
 
+// ---- identity fast path: one thread = 4 output rows x 16 pixels -------------------------------------
+// Output rows 4g-2 .. 4g+1 all interpolate between low-res rows g-1 and g, so the horizontal pass
+// (hx*v0 + lx*v1 for both rows) is done once for 64 pixels: 12 loads, ~5 flops / pixel, and the operation
+// order is exactly the reference's hy*(hx*v00 + lx*v01) + ly*(hx*v10 + lx*v11).
+struct Quad {
+  float ha[16], hb[16];   // horizontal interpolation of low-res rows g-1 (clamped) and g (clamped)
+};
+__device__ __forceinline__ void quad_rows(const float* __restrict__ L, int gI, int X0, Quad& q) {
+  const int ya = max(gI - 1, 0), yb = min(gI, 255);
+  const int k0 = X0 >> 2;
+  float ra[6], rb[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    const int cc = min(max(k0 - 1 + c, 0), 255);
+    ra[c] = L[ya * 256 + cc];
+    rb[c] = L[yb * 256 + cc];
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int i0 = (j + 2) >> 2;
+    float lx = ((j & 3) == 0) ? 0.625f : ((j & 3) == 1) ? 0.875f : ((j & 3) == 2) ? 0.125f : 0.375f;
+    if (X0 == 0 && j < 2) lx = 0.f;
+    const float hx = 1.f - lx;
+    q.ha[j] = hx * ra[i0] + lx * ra[i0 + 1];
+    q.hb[j] = hx * rb[i0] + lx * rb[i0 + 1];
+  }
+}
+// vertical weight of output row Y = 4g - 2 + jr
+__device__ __forceinline__ float quad_ly(int Y, int jr) {
+  if (Y < 2) return 0.f;                                  // source index clamped to 0 at the top border
+  return jr == 0 ? 0.125f : jr == 1 ? 0.375f : jr == 2 ? 0.625f : 0.875f;
+}
+
+
+
+__global__ void __launch_bounds__(256) post_stats_quad_kernel(csam_post_args a, PostGeom g, int segs_per_row) {
+  const int p = blockIdx.y;
+  const float* L = plane_of(a, p);
+  const int groups = (g.out_h + 2 + 3) / 4;
+  const int total = groups * segs_per_row;
+  const float t_hi = a.thr + a.off, t_lo = a.thr - a.off;
+  int c_hi = 0, c_lo = 0, c_mid = 0;
+  int xmin = INT_MAX, xmax = -1, ymin = INT_MAX, ymax = -1;
+  for (int s = blockIdx.x * 256 + threadIdx.x; s < total; s += gridDim.x * 256) {
+    const int gI = s / segs_per_row, X0 = (s % segs_per_row) * 16;
+    const int nx = min(16, g.out_w - X0);
+    Quad q;
+    quad_rows(L, gI, X0, q);
+#pragma unroll
+    for (int jr = 0; jr < 4; ++jr) {
+      const int Y = 4 * gI - 2 + jr;
+      if (Y < 0 || Y >= g.out_h) continue;
+      const float ly = quad_ly(Y, jr), hy = 1.f - ly;
+      unsigned bits = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float v = hy * q.ha[j] + ly * q.hb[j];
+        if (j < nx) {
+          c_hi += v > t_hi;
+          c_lo += v > t_lo;
+          bits |= (v > a.thr ? 1u : 0u) << j;
+        }
+      }
+      if (bits) {
+        c_mid += __popc(bits);
+        xmin = min(xmin, X0 + __ffs(bits) - 1);
+        xmax = max(xmax, X0 + 31 - __clz(bits));
+        ymin = min(ymin, Y); ymax = max(ymax, Y);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    c_hi += __shfl_xor_sync(0xffffffffu, c_hi, o);
+    c_lo += __shfl_xor_sync(0xffffffffu, c_lo, o);
+    c_mid += __shfl_xor_sync(0xffffffffu, c_mid, o);
+    xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+    ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+    xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+    ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+  }
+  __shared__ int sred[8][7];
+  const int wid = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    sred[wid][0] = c_hi; sred[wid][1] = c_lo; sred[wid][2] = c_mid;
+    sred[wid][3] = xmin; sred[wid][4] = ymin; sred[wid][5] = xmax; sred[wid][6] = ymax;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      c_hi += sred[w][0]; c_lo += sred[w][1]; c_mid += sred[w][2];
+      xmin = min(xmin, sred[w][3]); ymin = min(ymin, sred[w][4]);
+      xmax = max(xmax, sred[w][5]); ymax = max(ymax, sred[w][6]);
+    }
+    if (c_hi) atomicAdd(&a.counts[p * 3 + 0], c_hi);
+    if (c_lo) atomicAdd(&a.counts[p * 3 + 1], c_lo);
+    if (c_mid) {
+      atomicAdd(&a.counts[p * 3 + 2], c_mid);
+      atomicMin(&a.boxes[p * 4 + 0], xmin); atomicMin(&a.boxes[p * 4 + 1], ymin);
+      atomicMax(&a.boxes[p * 4 + 2], xmax); atomicMax(&a.boxes[p * 4 + 3], ymax);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) post_write_quad_kernel(csam_post_args a, PostGeom g, int segs_per_row) {
+  const int i = blockIdx.y;
+  const int p = a.keep ? a.keep[i] : i;
+  const float* L = plane_of(a, p);
+  const int groups = (g.out_h + 2 + 3) / 4;
+  const int total = groups * segs_per_row;
+  uint8_t* mo = a.masks ? a.masks + (size_t)i * g.out_h * g.out_w : nullptr;
+  float* lo = a.logits ? a.logits + (size_t)i * g.out_h * g.out_w : nullptr;
+  for (int s = blockIdx.x * 256 + threadIdx.x; s < total; s += gridDim.x * 256) {
+    const int gI = s / segs_per_row, X0 = (s % segs_per_row) * 16;
+    Quad q;
+    quad_rows(L, gI, X0, q);
+#pragma unroll
+    for (int jr = 0; jr < 4; ++jr) {
+      const int Y = 4 * gI - 2 + jr;
+      if (Y < 0 || Y >= g.out_h) continue;
+      const float ly = quad_ly(Y, jr), hy = 1.f - ly;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = hy * q.ha[j] + ly * q.hb[j];
+      const size_t o = (size_t)Y * g.out_w + X0;
+      if (mo) {
+        uint32_t w[4];
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq)
+          w[qq] = (v[qq * 4] > a.thr ? 1u : 0u) | (v[qq * 4 + 1] > a.thr ? 0x100u : 0u) |
+                  (v[qq * 4 + 2] > a.thr ? 0x10000u : 0u) | (v[qq * 4 + 3] > a.thr ? 0x1000000u : 0u);
+        *reinterpret_cast<uint4*>(mo + o) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      if (lo) {
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq)
+          *reinterpret_cast<float4*>(lo + o + qq * 4) = make_float4(v[qq * 4], v[qq * 4 + 1], v[qq * 4 + 2], v[qq * 4 + 3]);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) post_stats_kernel(csam_post_args a, PostGeom g, int segs_per_row) {
   const int p = blockIdx.y;
   const float* L = plane_of(a, p);
@@ -205,9 +347,16 @@ extern "C" int csam_mask_post_stats(const csam_post_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   post_init_kernel<<<(a->P + 255) / 256, 256, 0, st>>>(a->counts, a->boxes, a->P);
   if (check_launch("post_init_kernel")) return 1;
-  dim3 grid((g.out_h + POST_ROWS - 1) / POST_ROWS, a->P);
-  post_stats_kernel<<<grid, 256, 0, st>>>(*a, g, (g.out_w + 15) / 16);
-  if (check_launch("post_stats_kernel")) return 1;
+  const int segs = (g.out_w + 15) / 16;
+  if (g.identity) {
+    const int total = ((g.out_h + 5) / 4) * segs;
+    post_stats_quad_kernel<<<dim3(min((total + 255) / 256, 65), a->P), 256, 0, st>>>(*a, g, segs);
+    if (check_launch("post_stats_quad_kernel")) return 1;
+  } else {
+    dim3 grid((g.out_h + POST_ROWS - 1) / POST_ROWS, a->P);
+    post_stats_kernel<<<grid, 256, 0, st>>>(*a, g, segs);
+    if (check_launch("post_stats_kernel")) return 1;
+  }
   post_finalize_kernel<<<(a->P + 255) / 256, 256, 0, st>>>(a->boxes, a->P);
   return check_launch("post_finalize_kernel");
 }
@@ -221,6 +370,11 @@ extern "C" int csam_mask_post_write(const csam_post_args* a, void* stream) {
   const int segs = (g.out_w + 15) / 16;
   const int total = g.out_h * segs;
   dim3 grid(min((total + 255) / 256, 256), n);
+  if (g.identity && (g.out_w & 15) == 0) {
+    const int tq = ((g.out_h + 5) / 4) * segs;
+    post_write_quad_kernel<<<dim3(min((tq + 255) / 256, 65), n), 256, 0, (cudaStream_t)stream>>>(*a, g, segs);
+    return check_launch("post_write_quad_kernel");
+  }
   post_write_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a, g, segs);
   return check_launch("post_write_kernel");
 }

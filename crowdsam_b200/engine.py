@@ -232,6 +232,17 @@ class MaskDecoderEngine:
                 i2t=_Attn(sd, Lp + ".cross_attn_image_to_token", dev, split)))
         self.final = _Attn(sd, f"{t}.final_attn_token_to_image", dev, split)
         self.nf = (_f(sd, f"{t}.norm_final_attn.weight", dev), _f(sd, f"{t}.norm_final_attn.bias", dev))
+        # (keys + pe) only ever feeds linear projections, and pe is a constant of the weights, so
+        # proj(keys + pe) = keys W^T + (pe W^T + b): the second term is precomputed here once and enters the
+        # projection GEMM as a row-periodic residual.  The [P,4096,256] "keys + pe" operand never exists.
+        def pe_proj(name):
+            w = sd[name + ".weight"].detach().double().cpu()
+            b = sd[name + ".bias"].detach().double().cpu()
+            return (self.pe_tok.double().cpu() @ w.T + b).float().contiguous().to(dev)
+
+        self.pe_k = [pe_proj(f"{t}.layers.{i}.cross_attn_token_to_image.k_proj") for i in range(2)]
+        self.pe_qi = [pe_proj(f"{t}.layers.{i}.cross_attn_image_to_token.q_proj") for i in range(2)]
+        self.pe_kf = pe_proj(f"{t}.final_attn_token_to_image.k_proj")
         # ConvTranspose2d(k2,s2) as GEMM: N index = (dy*2+dx)*C_out + o   (mask_decoder.py:56-62)
         w1 = sd[f"{m}.output_upscaling.0.weight"].detach().float().permute(2, 3, 1, 0).reshape(256, 256)
         b1 = sd[f"{m}.output_upscaling.0.bias"].detach().float().repeat(4)
@@ -256,12 +267,11 @@ class MaskDecoderEngine:
         (mask_decoder.py:187-188)."""
         split = self.split
         L0 = self.layers[0]
-        keys0, keys0_h, keys0_pe_h = ops.layernorm(feat_tok, normalize=False, add=self.no_mask, add_mod=1,
-                                                   want_f32=True, want_h16=True, split=split,
-                                                   pe=self.pe_tok, want_out2=True)
-        k0, _ = L0["t2i"].k(keys0_pe_h, want_f32=True)
+        keys0, keys0_h, _ = ops.layernorm(feat_tok, normalize=False, add=self.no_mask, add_mod=1,
+                                          want_f32=True, want_h16=True, split=split)
+        k0, _ = ops.gemm(keys0_h, L0["t2i"].k.w, residual=self.pe_k[0], want_f32=True)
         v0, _ = L0["t2i"].v(keys0_h, want_f32=True)
-        q0, _ = L0["i2t"].q(keys0_pe_h, want_f32=True)
+        q0, _ = ops.gemm(keys0_h, L0["i2t"].q.w, residual=self.pe_qi[0], want_f32=True)
         dproj, dproj_h = self.dino_proj(dino_tok_h, want_f32=True, want_h16=True)      # [5329,256]
         planes = ops.transpose_f32(dproj).view(256, 73, 73)
         dmap = ops.bilinear(planes, 256, 256, chlast=False)                            # [256,256,256]
@@ -295,7 +305,7 @@ class MaskDecoderEngine:
         tokens = ops.prompt_tokens(coords01, labels, self.gauss, self.tok5, self.point_emb, self.nap).view(T, 256)
         _, tok_h, _ = ln(tokens, normalize=False, want_h16=True, split=split)
         queries, q_h, q_pe_h = tokens, tok_h, tok_h
-        keys_f32, keys_h, keys_pe_h = None, None, None
+        keys_f32, keys_h = None, None
         for li, Lr in enumerate(self.layers):
             # (1) token self-attention (transformer.py:163-169)
             sa = Lr["sa"]
@@ -313,7 +323,7 @@ class MaskDecoderEngine:
             if li == 0:
                 kc, vc = I["k0"], I["v0"]
             else:
-                kc, _ = ta.k(keys_pe_h, want_f32=True)
+                kc, _ = ops.gemm(keys_h, ta.k.w, residual=self.pe_k[li], res_mod=4096, want_f32=True)
                 vc, _ = ta.v(keys_h, want_f32=True)
                 kc, vc = kc.view(P, 4096, 128), vc.view(P, 4096, 128)
             _, a = ops.attn_few_queries(qc.view(P, 7, 128), kc, vc, P, 7, 4096, 8, 16, want_h16=True, split=split)
@@ -331,29 +341,36 @@ class MaskDecoderEngine:
             if li == 0:
                 qi = I["q0"]
             else:
-                qi, _ = ia.q(keys_pe_h, want_f32=True)
+                qi, _ = ops.gemm(keys_h, ia.q.w, residual=self.pe_qi[li], res_mod=4096, want_f32=True)
                 qi = qi.view(P, 4096, 128)
             _, a = ops.attn_few_keys(qi, kt.view(P, 7, 128), vt.view(P, 7, 128), P, 4096, 7, 8, 16,
                                      want_h16=True, split=split)
-            # out_proj + residual + norm4 in one GEMM epilogue; emits keys (fp32, only needed as the next
-            # layer's residual), keys as h16 pair (v_proj / upscaling operand) and keys+pe (k/q_proj operand)
-            keys_h = H16.empty((P * 4096, 256), split, self.dev)
-            keys_pe_h = H16.empty((P * 4096, 256), split, self.dev)
-            nxt = torch.empty((P * 4096, 256), dtype=torch.float32, device=self.dev) if li == 0 else None
-            ia.o(a.view(P * 4096, 128), residual=(I["keys0"] if li == 0 else keys_f32), res_mod=(4096 if li == 0 else 0),
-                 epi=1, gamma=Lr["n4"][0], beta=Lr["n4"][1], eps=1e-5, out_f32=nxt, out_h16=keys_h, out2=keys_pe_h,
-                 pe=self.pe_tok, pe_mod=4096)
-            keys_f32 = nxt
+            # out_proj + residual + norm4 in one GEMM epilogue.  The new keys are stored once, as an h16 pair:
+            # it is the operand of the next projections / upscaling AND (hi + lo = fp32-accurate) the next
+            # layer's residual, so no fp32 copy of the [P,4096,256] stream is written in split mode.
+            new_h = H16.empty((P * 4096, 256), split, self.dev)
+            nxt = None
+            if li == 0 and not split:
+                nxt = torch.empty((P * 4096, 256), dtype=torch.float32, device=self.dev)
+            if li == 0:
+                res_kw = dict(residual=I["keys0"], res_mod=4096)
+            elif split:
+                res_kw = dict(residual_h16=keys_h)
+            else:
+                res_kw = dict(residual=keys_f32)
+            ops.gemm(a.view(P * 4096, 128), ia.o.w, bias=ia.o.b, epi=1, gamma=Lr["n4"][0], beta=Lr["n4"][1], eps=1e-5,
+                     out_f32=nxt, out_h16=new_h, **res_kw)
+            keys_h, keys_f32 = new_h, nxt
         # final token -> image attention (transformer.py:104-112)
         fa = self.final
         qc, _ = fa.q(q_pe_h, want_f32=True)
-        kc, _ = fa.k(keys_pe_h, want_f32=True)
+        kc, _ = ops.gemm(keys_h, fa.k.w, residual=self.pe_kf, res_mod=4096, want_f32=True)
         vc, _ = fa.v(keys_h, want_f32=True)
         _, a = ops.attn_few_queries(qc.view(P, 7, 128), kc.view(P, 4096, 128), vc.view(P, 4096, 128), P, 7, 4096, 8, 16,
                                     want_h16=True, split=split)
         pre, _ = fa.o(a.view(T, 128), residual=queries, want_f32=True)
         hs, hs_h, _ = ln(pre, self.nf[0], self.nf[1], 1e-5, want_f32=True, want_h16=True, split=split)
-        del kc, vc, keys_pe_h, keys_f32, pre
+        del kc, vc, keys_f32, pre
         hs2 = hs_h.view(P, 7 * 256)
 
         def cols(h: H16, c0: int, c1: int) -> H16:

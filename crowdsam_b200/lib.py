@@ -27,7 +27,8 @@ class GemmArgs(C.Structure):
                 ("impl", ci), ("b_mn_major", ci),
                 ("epi", ci), ("gamma", vp), ("beta", vp), ("eps", cf),
                 ("pe", vp), ("ldpe", ci), ("pe_mod", ci), ("out2_hi", vp), ("out2_lo", vp),
-                ("hyper", vp), ("masks", vp)]
+                ("hyper", vp), ("masks", vp),
+                ("res_hi", vp), ("res_lo", vp), ("ldrh", ci)]
 
 
 class LnArgs(C.Structure):
@@ -123,7 +124,7 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.csam_abi_version() != 2:
+    if lib.csam_abi_version() != 3:
         raise RuntimeError("libcsam_sm100.so ABI version mismatch")
     _lib = lib
     return lib

@@ -103,7 +103,8 @@ class H16:
 def gemm(a: H16, w: H16, *, bias=None, act=ACT_NONE, residual=None, res_mod=0, row_map=None,
          row_scale=None, col_scale=None, out_f32=None, out_h16: Optional[H16] = None,
          want_f32=False, want_h16=False, impl=None, b_mn_major=False, M=None,
-         epi=0, gamma=None, beta=None, eps=0.0, pe=None, pe_mod=0, out2: Optional[H16] = None, hyper=None, masks=None):
+         epi=0, gamma=None, beta=None, eps=0.0, pe=None, pe_mod=0, out2: Optional[H16] = None, hyper=None, masks=None,
+         residual_h16: Optional[H16] = None):
     """out = epilogue(a[M,K] @ w[N,K]^T); returns (fp32 or None, H16 or None).
     epi: 0 standard, 1 full-row LayerNorm (N == 256), 2 ConvT1+LN2d+GELU shuffle, 3 ConvT2+GELU+hypernet dot."""
     assert a.hi.dim() == 2 and w.hi.dim() == 2
@@ -140,6 +141,8 @@ def gemm(a: H16, w: H16, *, bias=None, act=ACT_NONE, residual=None, res_mod=0, r
             assert out2.hi.stride(0) == out_h16.hi.stride(0)
         g.ldh = out2.hi.stride(0)
     g.hyper, g.masks = _p(hyper), _p(masks)
+    if residual_h16 is not None:
+        g.res_hi, g.res_lo, g.ldrh = _p(residual_h16.hi), _p(residual_h16.lo), residual_h16.hi.stride(0)
     if epi != 0:
         assert g.impl == 0, "fused epilogues exist on the tcgen05 path only"
     tok = _pb()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSAM_ABI_VERSION 2
+#define CSAM_ABI_VERSION 3
 #if defined(__GNUC__)
 #define CSAM_API __attribute__((visibility("default")))
 #else
@@ -80,6 +80,7 @@ typedef struct {
   const float* gamma; const float* beta; float eps;          /* EPI_LN / EPI_UP1 */
   const float* pe; int ldpe; int pe_mod; void* out2_hi; void* out2_lo;   /* EPI_LN second output */
   const float* hyper; float* masks;                          /* EPI_UP2 */
+  const void* res_hi; const void* res_lo; int ldrh;          /* EPI_LN: residual as an h16 pair (instead of fp32) */
 } csam_gemm_args;
 CSAM_API int csam_gemm(const csam_gemm_args* a, void* stream);
 

@@ -443,6 +443,13 @@ def test_gemm_epilogue_layernorm256(split):
     tol = 1e-5 if split else 1e-3
     assert _rel(oh.float(), ref) < tol
     assert _rel(o2.float(), ref + pe.double()[torch.arange(M) % 200]) < tol
+    if split:   # residual supplied as an h16 pair (hi + lo), full length
+        resf = torch.randn(M, 256, generator=g)
+        rh = _h16(resf, True)
+        x3 = ah.float().cpu().double() @ wh.float().cpu().double().T + bias.double() + rh.float().cpu().double()
+        o3 = o.H16.empty((M, 256), True, DEV)
+        o.gemm(ah, wh, bias=bias.to(DEV), residual_h16=rh, epi=1, gamma=gam.to(DEV), beta=bet.to(DEV), eps=1e-5, out_h16=o3)
+        assert _rel(o3.float(), torch.nn.functional.layer_norm(x3, (256,), gam.double(), bet.double(), 1e-5)) < 1e-5
     # no-residual / no-pe / fp32-only variant
     out2 = torch.empty(M, 256, device=DEV)
     o.gemm(ah, wh, bias=bias.to(DEV), epi=1, gamma=gam.to(DEV), beta=bet.to(DEV), eps=1e-5, out_f32=out2)
