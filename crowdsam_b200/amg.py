@@ -159,6 +159,15 @@ def mask_to_rle_pytorch(tensor: torch.Tensor) -> List[Dict[str, Any]]:
     return [{"size": [h, w], "counts": r.tolist()} for r in runs]
 
 
+def mask_to_rle_arrays(tensor: torch.Tensor) -> List[Dict[str, Any]]:
+    """Same as mask_to_rle_pytorch but keeps the run lengths as numpy arrays (no per-element Python objects);
+    used inside the pipeline where the counts go straight into the COCO string encoder."""
+    n, h, w = tensor.shape
+    if n == 0:
+        return []
+    return [{"size": [h, w], "counts": r} for r in ops.rle_encode(tensor.to(torch.bool))]
+
+
 def rle_to_mask(rle: Dict[str, Any]) -> np.ndarray:
     h, w = rle["size"]
     vals = np.zeros(len(rle["counts"]), dtype=bool)
@@ -172,18 +181,32 @@ def area_from_rle(rle: Dict[str, Any]) -> int:
 
 def _coco_string(counts: Sequence[int]) -> str:
     """COCO API run-length string (maskApi.c rleToString): counts beyond the second are delta coded
-    against counts[i-2]; each value is emitted as 5-bit groups, bit 5 = continuation, + 48."""
-    chars = []
-    for i, c in enumerate(counts):
-        x = int(c) - (int(counts[i - 2]) if i > 2 else 0)
-        while True:
-            low = x & 0x1F
-            x >>= 5
-            done = (x == -1) if (low & 0x10) else (x == 0)
-            chars.append(chr((low if done else low | 0x20) + 48))
-            if done:
-                break
-    return "".join(chars)
+    against counts[i-2]; each value is emitted as 5-bit groups (little endian), bit 5 = continuation, + 48.
+    Vectorised over all counts: one numpy pass per 5-bit group (at most 7 for int32 values)."""
+    c = np.asarray(counts, dtype=np.int64)
+    n = c.shape[0]
+    if n == 0:
+        return ""
+    x = c.copy()
+    if n > 3:
+        x[3:] -= c[1:-2]
+    groups = []          # per pass: (emitted char codes, active mask)
+    active = np.ones(n, dtype=bool)
+    while active.any():
+        low = x & 0x1F
+        x = x >> 5       # arithmetic shift, like the C code on a signed long
+        done = np.where((low & 0x10) != 0, x == -1, x == 0)
+        ch = np.where(done, low, low | 0x20) + 48
+        groups.append((ch, active.copy()))
+        active &= ~done
+    n_chars = np.zeros(n, dtype=np.int64)
+    for _, a in groups:
+        n_chars += a
+    starts = np.concatenate([[0], np.cumsum(n_chars)[:-1]])
+    out = np.empty(int(n_chars.sum()), dtype=np.uint8)
+    for k, (ch, a) in enumerate(groups):
+        out[starts[a] + k] = ch[a]
+    return out.tobytes().decode("ascii")
 
 
 def coco_encode_rle(uncompressed_rle: Dict[str, Any]) -> Dict[str, Any]:
@@ -192,7 +215,7 @@ def coco_encode_rle(uncompressed_rle: Dict[str, Any]) -> Dict[str, Any]:
     try:
         from pycocotools import mask as mask_utils  # type: ignore
 
-        rle = mask_utils.frPyObjects(uncompressed_rle, h, w)
+        rle = mask_utils.frPyObjects({"size": [h, w], "counts": [int(c) for c in uncompressed_rle["counts"]]}, h, w)
         rle["counts"] = rle["counts"].decode("utf-8")
         return rle
     except ImportError:

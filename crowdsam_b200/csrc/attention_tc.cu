@@ -21,16 +21,19 @@ int compute_relpos(const csam_attn_args* a, cudaStream_t st);   // attention_sim
 constexpr int AT_BM = 128, AT_BN = 64, AT_HD = 64, AT_STAGES = 3, AT_THREADS = 256;
 constexpr int AT_REL_LD = 29;   // 28 rel-pos values per query (S = 14) padded to an odd stride
 
-template <int SPLIT>
+// PLO: also split the probabilities P into hi + lo (3 MMAs for P V); without it P is a single fp16
+// (relative error 2^-12 per probability, measured 2e-5 at the encoder output) and P V needs 2 MMAs
+template <int SPLIT, bool PLO>
 struct AttnCfg {
   static constexpr int NOPS = (SPLIT == 3) ? 2 : 1;
+  static constexpr int PNOPS = (SPLIT == 3 && PLO) ? 2 : 1;
   static constexpr int Q_BYTES = AT_BM * AT_HD * 2;          // 16 KB per operand half
   static constexpr int KV_TILE = AT_BN * AT_HD * 2;          // 8 KB
   static constexpr int STAGE_BYTES = NOPS * 2 * KV_TILE;     // K(hi,lo) then V(hi,lo)
   static constexpr int P_BYTES = AT_BM * AT_BN * 2;          // 16 KB per operand half
   static constexpr int OFF_KV = NOPS * Q_BYTES;
   static constexpr int OFF_P = OFF_KV + AT_STAGES * STAGE_BYTES;
-  static constexpr int OFF_REL = OFF_P + 2 * NOPS * P_BYTES;
+  static constexpr int OFF_REL = OFF_P + 2 * PNOPS * P_BYTES;
   static constexpr int OFF_BAR = OFF_REL + AT_BM * AT_REL_LD * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 };
@@ -43,13 +46,16 @@ struct AttnBars {
 };
 
 // BIAS: 0 none, 1 window (S = 14, table in shared memory), 2 global (S = 64 == key tile, registers)
-template <int SPLIT, int BIAS>
+template <int SPLIT, int BIAS, bool PLO>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_constant__ CUtensorMap t_lo,
                         csam_attn_args a, const float* __restrict__ rel) {
-  using Cfg = AttnCfg<SPLIT>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using Cfg = AttnCfg<SPLIT, PLO>;
+  // Dynamic shared memory is the only shared allocation of this kernel, so it starts at the (1024-byte
+  // aligned) base of the CTA's window; keeping `smem` a plain __shared__ array (no integer round-trip) lets
+  // the compiler emit LDS/STS instead of generic LD/ST for every staging access.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   AttnBars* bars = reinterpret_cast<AttnBars*>(smem + Cfg::OFF_BAR);
   float* rel_s = reinterpret_cast<float*>(smem + Cfg::OFF_REL);
 
@@ -145,7 +151,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
         tc_fence_after();
         const int st = j % AT_STAGES;
         const uint32_t sv = smem_u32(smem + Cfg::OFF_KV + st * Cfg::STAGE_BYTES + Cfg::NOPS * Cfg::KV_TILE);
-        const uint32_t sp = smem_u32(smem + Cfg::OFF_P + b * Cfg::NOPS * Cfg::P_BYTES);
+        const uint32_t sp = smem_u32(smem + Cfg::OFF_P + b * Cfg::PNOPS * Cfg::P_BYTES);
         const uint32_t d = tmem_base + 128 + b * AT_HD;
 #pragma unroll
         for (int k = 0; k < AT_BN / 16; ++k) {
@@ -153,10 +159,12 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
           const uint64_t v_hi = umma_desc_sw128(sv + k * 2048, 8192, 1024);
           umma_f16(d, p_hi, v_hi, idesc_pv, k ? 1u : 0u);
           if (SPLIT == 3) {
-            const uint64_t p_lo = umma_desc_sw128(sp + Cfg::P_BYTES + k * 32, 16, 1024);
             const uint64_t v_lo = umma_desc_sw128(sv + Cfg::KV_TILE + k * 2048, 8192, 1024);
-            umma_f16(d, p_lo, v_hi, idesc_pv, 1u);
             umma_f16(d, p_hi, v_lo, idesc_pv, 1u);
+            if (PLO) {
+              const uint64_t p_lo = umma_desc_sw128(sp + Cfg::P_BYTES + k * 32, 16, 1024);
+              umma_f16(d, p_lo, v_hi, idesc_pv, 1u);
+            }
           }
         }
         umma_commit(&bars->o_full[b]);
@@ -239,21 +247,29 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
       const float m_new = fmaxf(m, tmax);
       const float alpha = exp2f(m - m_new);
       float psum = 0.f;
-      uint8_t* pb = smem + Cfg::OFF_P + b * Cfg::NOPS * Cfg::P_BYTES + r * 128;
+      uint8_t* pb = smem + Cfg::OFF_P + b * Cfg::PNOPS * Cfg::P_BYTES + r * 128;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        __align__(16) __half hi8[8];
-        __align__(16) __half lo8[8];
+        float pv[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          const float p = exp2f(s[u * 8 + t] - m_new);
-          psum += p;
-          hi8[t] = __float2half_rn(p);
-          lo8[t] = __float2half_rn(p - __half2float(hi8[t]));
+          pv[t] = exp2f(s[u * 8 + t] - m_new);
+          psum += pv[t];
         }
+        __align__(16) __half2 hi2[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) hi2[t] = __floats2half2_rn(pv[2 * t], pv[2 * t + 1]);   // one packed cvt per pair
         const int off = (u ^ (r & 7)) << 4;
-        *reinterpret_cast<uint4*>(pb + off) = *reinterpret_cast<const uint4*>(hi8);
-        if (SPLIT == 3) *reinterpret_cast<uint4*>(pb + Cfg::P_BYTES + off) = *reinterpret_cast<const uint4*>(lo8);
+        *reinterpret_cast<uint4*>(pb + off) = *reinterpret_cast<const uint4*>(hi2);
+        if (SPLIT == 3 && PLO) {
+          __align__(16) __half2 lo2[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 hf = __half22float2(hi2[t]);
+            lo2[t] = __floats2half2_rn(pv[2 * t] - hf.x, pv[2 * t + 1] - hf.y);
+          }
+          *reinterpret_cast<uint4*>(pb + Cfg::P_BYTES + off) = *reinterpret_cast<const uint4*>(lo2);
+        }
       }
       l = fmaf(l, alpha, psum);
       m = m_new;
@@ -282,16 +298,16 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
   if (warp == 2) tmem_dealloc<256>(tmem_base);
 }
 
-template <int SPLIT, int BIAS>
+template <int SPLIT, int BIAS, bool PLO>
 static int launch_attn_tc(const csam_attn_args* a, const float* rel, cudaStream_t st) {
-  using Cfg = AttnCfg<SPLIT>;
+  using Cfg = AttnCfg<SPLIT, PLO>;
   CUtensorMap t_hi, t_lo;
   const uint64_t rows = (uint64_t)a->groups * a->tokens;
   const uint64_t cols = 3ull * a->heads * a->hd;
   if (make_tmap_2d_f16(&t_hi, a->qkv_hi, rows, cols, a->ld_qkv, 64, 64)) return 1;
   t_lo = t_hi;
   if (SPLIT == 3 && make_tmap_2d_f16(&t_lo, a->qkv_lo, rows, cols, a->ld_qkv, 64, 64)) return 1;
-  auto kern = vit_attention_tc_kernel<SPLIT, BIAS>;
+  auto kern = vit_attention_tc_kernel<SPLIT, BIAS, PLO>;
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
@@ -318,14 +334,19 @@ int vit_attention_tc(const csam_attn_args* a, cudaStream_t st) {
     rel = a->scratch;
     bias = a->S == 14 ? 1 : 2;
   }
-  if (split) {
-    if (bias == 0) return launch_attn_tc<3, 0>(a, rel, st);
-    if (bias == 1) return launch_attn_tc<3, 1>(a, rel, st);
-    return launch_attn_tc<3, 2>(a, rel, st);
+  if (split && a->p_split) {
+    if (bias == 0) return launch_attn_tc<3, 0, true>(a, rel, st);
+    if (bias == 1) return launch_attn_tc<3, 1, true>(a, rel, st);
+    return launch_attn_tc<3, 2, true>(a, rel, st);
   }
-  if (bias == 0) return launch_attn_tc<1, 0>(a, rel, st);
-  if (bias == 1) return launch_attn_tc<1, 1>(a, rel, st);
-  return launch_attn_tc<1, 2>(a, rel, st);
+  if (split) {
+    if (bias == 0) return launch_attn_tc<3, 0, false>(a, rel, st);
+    if (bias == 1) return launch_attn_tc<3, 1, false>(a, rel, st);
+    return launch_attn_tc<3, 2, false>(a, rel, st);
+  }
+  if (bias == 0) return launch_attn_tc<1, 0, false>(a, rel, st);
+  if (bias == 1) return launch_attn_tc<1, 1, false>(a, rel, st);
+  return launch_attn_tc<1, 2, false>(a, rel, st);
 }
 
 }  // namespace csam

@@ -52,21 +52,30 @@ __device__ __forceinline__ float load_pair(const __half* hi, const __half* lo, s
   if (lo) v += __half2float(lo[i]);
   return v;
 }
+// Packed split of two values: hi = fp16x2(a,b), lo = fp16x2(a - hi.x, b - hi.y).  One F2FP per pair instead of
+// one conversion per element; the subtraction is exact in fp32.  Inputs are clamped to the fp16 range.
+__device__ __forceinline__ void split_h2(float a, float b, __half2& hi, __half2& lo) {
+  a = clamp_h(a);
+  b = clamp_h(b);
+  hi = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(hi);
+  lo = __floats2half2_rn(a - hf.x, b - hf.y);
+}
 // 4 consecutive values -> two 8-byte stores
 __device__ __forceinline__ void store_pair4(__half* hi, __half* lo, size_t i, const float* v) {
-  __align__(8) __half h[4];
-  __align__(8) __half l[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) split_h(v[j], h[j], l[j]);
+  __align__(8) __half2 h[2];
+  __align__(8) __half2 l[2];
+  split_h2(v[0], v[1], h[0], l[0]);
+  split_h2(v[2], v[3], h[1], l[1]);
   *reinterpret_cast<uint2*>(hi + i) = *reinterpret_cast<const uint2*>(h);
   if (lo) *reinterpret_cast<uint2*>(lo + i) = *reinterpret_cast<const uint2*>(l);
 }
 // 8 consecutive values -> two 16-byte stores
 __device__ __forceinline__ void store_pair8(__half* hi, __half* lo, size_t i, const float* v) {
-  __align__(16) __half h[8];
-  __align__(16) __half l[8];
+  __align__(16) __half2 h[4];
+  __align__(16) __half2 l[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) split_h(v[j], h[j], l[j]);
+  for (int j = 0; j < 4; ++j) split_h2(v[2 * j], v[2 * j + 1], h[j], l[j]);
   *reinterpret_cast<uint4*>(hi + i) = *reinterpret_cast<const uint4*>(h);
   if (lo) *reinterpret_cast<uint4*>(lo + i) = *reinterpret_cast<const uint4*>(l);
 }

@@ -119,33 +119,45 @@ constexpr int BK = 64;           // 64 fp16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 384;   // 4 control warps + 8 epilogue warps
 
-template <int BN, int SPLIT>
+// WRES ("weights resident"): the skinny decoder GEMMs (millions of rows, N <= BN, K <= 256) have a weight matrix
+// of at most 128 KB.  Streaming it with every tile would spend 1/2 .. 2/3 of the L2->SM fill bandwidth on
+// re-reading the same bytes, so a persistent CTA loads W once and the ring carries only the A operand.
+constexpr int WRES_MAX_BYTES = 128 * 1024;
+template <int BN, int SPLIT, bool WRES = false>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
   static constexpr int W_BYTES = BN * BK * 2;
   static constexpr int NOPS = (SPLIT == 3) ? 2 : 1;           // hi (+ lo) per operand
-  static constexpr int STAGE_BYTES = NOPS * (A_BYTES + W_BYTES);
-  static constexpr int STAGES = (SPLIT == 3) ? (BN >= 256 ? 2 : 3) : (BN >= 256 ? 4 : 6);
+  static constexpr int STAGE_BYTES = WRES ? NOPS * A_BYTES : NOPS * (A_BYTES + W_BYTES);
+  static constexpr int STAGES = WRES ? ((SPLIT == 3) ? 2 : 4)
+                                     : ((SPLIT == 3) ? (BN >= 256 ? 2 : 3) : (BN >= 256 ? 4 : 6));
+  static constexpr int OFF_RING = WRES ? WRES_MAX_BYTES : 0;  // resident W first, then the ring
   static constexpr int TMEM_COLS = 2 * BN;                    // two accumulator buffers
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*epilogue scratch*/ +
+  static constexpr int SMEM_BYTES = OFF_RING + STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*epilogue scratch*/ +
                                     8 * 2048 /*per-warp staging tiles*/;
 };
 
-template <int BN, int SPLIT, bool B_MN, int EPI>
+template <int BN, int SPLIT, bool B_MN, int EPI, bool WRES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant__ CUtensorMap ta_lo,
                const __grid_constant__ CUtensorMap tw_hi, const __grid_constant__ CUtensorMap tw_lo,
                GemmEpi e, int K, int tiles_m, int tiles_n) {
-  using Cfg = GemmCfg<BN, SPLIT>;
+  using Cfg = GemmCfg<BN, SPLIT, WRES>;
   constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  static_assert(!(WRES && B_MN), "resident weights are K-major only");
+  // Dynamic shared memory is the only shared allocation of this kernel, so it starts at the (1024-byte
+  // aligned) base of the CTA's window; keeping `smem` a plain __shared__ array (no integer round-trip) lets
+  // the compiler emit LDS/STS instead of generic LD/ST for every staging access.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  uint8_t* ring = smem + Cfg::OFF_RING;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);   // 4 KB epilogue scratch
+  uint64_t* w_bar = tempty_bar + 2;             // resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  float* epi_smem = reinterpret_cast<float*>(ring + STAGES * Cfg::STAGE_BYTES + 256);   // 4 KB epilogue scratch
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -160,6 +172,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 256); }
+    mbar_init(w_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -172,18 +185,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      if (WRES) {   // the whole weight matrix (tiles_n == 1), once
+        mbar_expect_tx(w_bar, num_kb * Cfg::NOPS * Cfg::W_BYTES);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          uint8_t* swr = smem + kb * Cfg::NOPS * Cfg::W_BYTES;
+          tma_load_2d(swr, &tw_hi, w_bar, kb * BK, 0);
+          if (SPLIT == 3) tma_load_2d(swr + Cfg::W_BYTES, &tw_lo, w_bar, kb * BK, 0);
+        }
+      }
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t % tiles_m) * BM;
-        const int n0 = (t / tiles_m) * BN;
+        const int m0 = (t / tiles_n) * BM;     // n-fastest: the CTAs sharing an A tile run back to back (L2)
+        const int n0 = (t % tiles_n) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
           uint8_t* sw = sa + Cfg::NOPS * Cfg::A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const int k0 = kb * BK;
           tma_load_2d(sa, &ta_hi, &full_bar[stage], k0, m0);
           if (SPLIT == 3) tma_load_2d(sa + Cfg::A_BYTES, &ta_lo, &full_bar[stage], k0, m0);
-          if (!B_MN) {
+          if (WRES) {
+            // weights already resident
+          } else if (!B_MN) {
             tma_load_2d(sw, &tw_hi, &full_bar[stage], k0, n0);
             if (SPLIT == 3) tma_load_2d(sw + Cfg::W_BYTES, &tw_lo, &full_bar[stage], k0, n0);
           } else {
@@ -204,6 +227,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, B_MN ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int local = 0;
+      if (WRES) { mbar_wait(w_bar, 0); tc_fence_after(); }
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
         const int buf = local & 1;
         const uint32_t bphase = (local >> 1) & 1;
@@ -213,8 +237,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sw = sa + Cfg::NOPS * Cfg::A_BYTES;
+          const uint32_t sa = smem_u32(ring + stage * Cfg::STAGE_BYTES);
+          const uint32_t sw = WRES ? smem_u32(smem + kb * Cfg::NOPS * Cfg::W_BYTES) : sa + Cfg::NOPS * Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t a_hi = umma_desc_sw128(sa + k * 32, 16, 1024);
@@ -246,8 +270,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
       const int buf = local & 1;
       const uint32_t bphase = (local >> 1) & 1;
-      const int m0 = (t % tiles_m) * BM;
-      const int n0 = (t / tiles_m) * BN;
+      const int m0 = (t / tiles_n) * BM;     // n-fastest: the CTAs sharing an A tile run back to back (L2)
+      const int n0 = (t % tiles_n) * BN;
       if constexpr (EPI == EPI_UP2) {
         // stage the 4 x 32 hypernetwork vectors of this tile's prompt (all 128 rows share it)
         const int et = threadIdx.x - 128;
@@ -281,22 +305,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
           for (int j = 0; j < 16; ++j) v[j] *= rs;
           stage_put(wb, lane, v);
           __syncwarp();
+          // all residual loads of the 4 row groups are issued before the first store: the output may alias the
+          // residual (in-place), so the compiler cannot hoist them itself and each load would otherwise expose
+          // a full L2 / HBM round trip
+          int orow4[4];
+          float4 res4[4];
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int rr = it * 8 + (lane >> 2), sl = lane & 3;
             const int row = row_base + rr, col = col0 + sl * 4;
             int orow = -1;
-            if (row < e.M) orow = e.row_map ? e.row_map[row] : row;
-            if (orow >= 0 && col < e.N) {
+            if (row < e.M && col < e.N) orow = e.row_map ? e.row_map[row] : row;
+            orow4[it] = orow;
+            res4[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (orow >= 0 && e.residual) {
+              const int rrow = e.res_mod > 0 ? (orow % e.res_mod) : orow;
+              res4[it] = *reinterpret_cast<const float4*>(e.residual + (size_t)rrow * e.ldr + col);
+            }
+          }
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + (lane >> 2), sl = lane & 3;
+            const int col = col0 + sl * 4;
+            const int orow = orow4[it];
+            if (orow >= 0) {
               float4 x = *reinterpret_cast<const float4*>(wb + wb_off(rr, sl));
               if (e.bias) { const float4 b = *reinterpret_cast<const float4*>(e.bias + col); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
               x.x = apply_act(x.x, e.act); x.y = apply_act(x.y, e.act); x.z = apply_act(x.z, e.act); x.w = apply_act(x.w, e.act);
               if (e.col_scale) { const float4 cs = *reinterpret_cast<const float4*>(e.col_scale + col); x.x *= cs.x; x.y *= cs.y; x.z *= cs.z; x.w *= cs.w; }
-              if (e.residual) {
-                const int rrow = e.res_mod > 0 ? (orow % e.res_mod) : orow;
-                const float4 rv = *reinterpret_cast<const float4*>(e.residual + (size_t)rrow * e.ldr + col);
-                x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
-              }
+              x.x += res4[it].x; x.y += res4[it].y; x.z += res4[it].z; x.w += res4[it].w;
               if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + (size_t)orow * e.ldo + col) = x;
               if (e.out_hi) { const float y4[4] = {x.x, x.y, x.z, x.w}; store_pair4(e.out_hi, e.out_lo, (size_t)orow * e.ldh + col, y4); }
             }
@@ -313,7 +350,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
           // alone cannot keep enough loads in flight to hide HBM latency
           const int tn = t + gridDim.x;
           if (tn < num_tiles && e.res_mod == 0) {
-            const int prow = (tn % tiles_m) * BM + (threadIdx.x - 128) / 2;      // 256 threads -> 128 rows x 2 halves
+            const int prow = (tn / tiles_n) * BM + (threadIdx.x - 128) / 2;      // 256 threads -> 128 rows x 2 halves
             const int phalf = (threadIdx.x - 128) & 1;
             if (prow < e.M) {
               if (e.residual) {
@@ -588,9 +625,9 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int SPLIT, bool B_MN, int EPI = EPI_STD>
+template <int BN, int SPLIT, bool B_MN, int EPI = EPI_STD, bool WRES = false>
 static int launch_tc(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st) {
-  using Cfg = GemmCfg<BN, SPLIT>;
+  using Cfg = GemmCfg<BN, SPLIT, WRES>;
   CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
   if (make_tmap_2d_f16(&ta_hi, a->a_hi, a->M, a->K, a->lda, BM, BK)) return 1;
   ta_lo = ta_hi;
@@ -604,7 +641,7 @@ static int launch_tc(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st)
     tw_lo = tw_hi;
     if (SPLIT == 3 && make_tmap_2d_f16(&tw_lo, a->w_lo, a->K, a->N, a->ldw, BK, 64)) return 1;
   }
-  auto kern = gemm_tc_kernel<BN, SPLIT, B_MN, EPI>;
+  auto kern = gemm_tc_kernel<BN, SPLIT, B_MN, EPI, WRES>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
@@ -662,11 +699,19 @@ extern "C" int csam_gemm(const csam_gemm_args* a, void* stream) {
   CSAM_REQUIRE((a->lda % 8) == 0 && (a->ldw % 8) == 0, "csam_gemm: lda/ldw must be multiples of 8");
   const bool split = a->a_lo != nullptr;
   const bool small_n = a->N <= 64;
+  // resident weights pay off when one CTA processes many tiles with the same (small) weight matrix
+  auto wres_ok = [&](int bn) {
+    const long long kb = (a->K + BK - 1) / BK;
+    const long long wbytes = kb * (split ? 2 : 1) * (long long)bn * BK * 2;
+    return a->N <= bn && wbytes <= WRES_MAX_BYTES && a->M >= 8 * BM * 148;
+  };
   if (a->epi == CSAM_EPI_LN) {
     CSAM_REQUIRE(a->N == 256 && a->gamma && a->beta && !a->row_map && !a->row_scale && !a->col_scale && a->act == 0,
                  "csam_gemm(EPI_LN): N must be 256 with gamma/beta and no other epilogue options");
     CSAM_REQUIRE(e.vec_ok && (!a->pe || ((a->ldpe & 3) == 0 && al16(a->pe))) && (!a->out2_hi || a->pe) &&
                      al16(a->gamma) && al16(a->beta), "csam_gemm(EPI_LN): alignment");
+    if (wres_ok(256))
+      return split ? launch_tc<256, 3, false, EPI_LN, true>(a, e, st) : launch_tc<256, 1, false, EPI_LN, true>(a, e, st);
     return split ? launch_tc<256, 3, false, EPI_LN>(a, e, st) : launch_tc<256, 1, false, EPI_LN>(a, e, st);
   }
   if (a->epi == CSAM_EPI_UP1) {
@@ -677,6 +722,8 @@ extern "C" int csam_gemm(const csam_gemm_args* a, void* stream) {
   if (a->epi == CSAM_EPI_UP2) {
     CSAM_REQUIRE(a->N == 128 && (a->M % 16384) == 0 && a->bias && a->hyper && a->masks,
                  "csam_gemm(EPI_UP2): N = 4x32, M = P*16384, bias, hyper and masks are required");
+    if (wres_ok(128))
+      return split ? launch_tc<128, 3, false, EPI_UP2, true>(a, e, st) : launch_tc<128, 1, false, EPI_UP2, true>(a, e, st);
     return split ? launch_tc<128, 3, false, EPI_UP2>(a, e, st) : launch_tc<128, 1, false, EPI_UP2>(a, e, st);
   }
   CSAM_REQUIRE(a->epi == CSAM_EPI_STD, "csam_gemm: unknown epilogue");
@@ -685,5 +732,7 @@ extern "C" int csam_gemm(const csam_gemm_args* a, void* stream) {
     return split ? launch_tc<128, 3, true>(a, e, st) : launch_tc<128, 1, true>(a, e, st);
   }
   if (small_n) return split ? launch_tc<64, 3, false>(a, e, st) : launch_tc<64, 1, false>(a, e, st);
+  if (wres_ok(128))
+    return split ? launch_tc<128, 3, false, EPI_STD, true>(a, e, st) : launch_tc<128, 1, false, EPI_STD, true>(a, e, st);
   return split ? launch_tc<128, 3, false>(a, e, st) : launch_tc<128, 1, false>(a, e, st);
 }

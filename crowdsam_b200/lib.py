@@ -48,7 +48,7 @@ class AttnArgs(C.Structure):
                 ("rel_h", vp), ("rel_w", vp), ("S", ci),
                 ("out_hi", vp), ("out_lo", vp), ("ld_out", ci),
                 ("scratch", vp), ("scratch_bytes", cll),
-                ("impl", ci)]
+                ("impl", ci), ("p_split", ci)]
 
 
 class DecAttnArgs(C.Structure):
@@ -124,7 +124,7 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.csam_abi_version() != 3:
+    if lib.csam_abi_version() != 4:
         raise RuntimeError("libcsam_sm100.so ABI version mismatch")
     _lib = lib
     return lib

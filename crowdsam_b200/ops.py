@@ -15,6 +15,8 @@ ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 # GEMM / attention implementation switches (validation only): 0 = tcgen05, 1 = SIMT
 GEMM_IMPL = int(os.environ.get("CSAM_GEMM_IMPL", "0"))
 ATTN_IMPL = int(os.environ.get("CSAM_ATTN_IMPL", "0"))
+# 1: softmax probabilities as hi+lo pair too (bit-for-bit closest to fp32, ~40% slower attention)
+ATTN_PSPLIT = int(os.environ.get("CSAM_ATTN_PSPLIT", "0"))
 
 
 class Profiler:
@@ -147,9 +149,22 @@ def gemm(a: H16, w: H16, *, bias=None, act=ACT_NONE, residual=None, res_mod=0, r
         assert g.impl == 0, "fused epilogues exist on the tcgen05 path only"
     tok = _pb()
     L.check(L.load().csam_gemm(C.byref(g), _stream()), "csam_gemm")
-    _pe("gemm", tok, 2.0 * M * N * K)
-    if tok is not None and PROFILER.detail:
-        PROFILER.end(f"gemm {M}x{N}x{K}", tok, 2.0 * M * N * K)
+    if tok is not None:
+        # classify by arithmetic intensity: the big encoder / DINOv2 GEMMs are tensor-bound, the skinny
+        # decoder ones (K <= 256, millions of rows) are HBM-bound and are accounted in bytes
+        nop = 2 if split else 1
+        nbytes = 2.0 * nop * (M * K + N * K) + (4.0 * M * N if out_f32 is not None else 0.0) \
+            + (2.0 * M * N * (2 if (out_h16 is not None and out_h16.lo is not None) else 1) if out_h16 is not None else 0.0) \
+            + (4.0 * M * N if (residual is not None and res_mod == 0) or residual_h16 is not None else 0.0) \
+            + (4.0 * masks.numel() if masks is not None else 0.0)
+        flops = 2.0 * M * N * K
+        if flops / nbytes >= 200.0:
+            PROFILER.end("gemm_tensor", tok, flops)
+        else:
+            PROFILER.end("gemm_hbm", tok, nbytes)
+        PROFILER.end("gemm", tok, flops)
+        if PROFILER.detail:
+            PROFILER.end(f"gemm {M}x{N}x{K}", tok, flops)
     return out_f32, out_h16
 
 
@@ -204,7 +219,7 @@ _attn_scratch = {}
 
 
 def vit_attention(qkv: H16, groups: int, tokens: int, heads: int, hd: int, scale: float, rel_h=None, rel_w=None,
-                  S=0, impl=None) -> H16:
+                  S=0, impl=None, p_split=None) -> H16:
     dev = qkv.hi.device
     out = H16.empty((groups * tokens, heads * hd), qkv.lo is not None, dev)
     a = L.AttnArgs()
@@ -219,6 +234,9 @@ def vit_attention(qkv: H16, groups: int, tokens: int, heads: int, hd: int, scale
             _attn_scratch[key] = torch.empty(need, dtype=torch.uint8, device=dev)
         a.scratch, a.scratch_bytes = _p(_attn_scratch[key]), need
     a.impl = ATTN_IMPL if impl is None else impl
+    a.p_split = ATTN_PSPLIT if p_split is None else int(p_split)
+    if hd != 64 and impl is None:
+        a.impl = 1          # head dim 80 (ViT-H): CUDA-core flash kernel; the tcgen05 kernel is specialised for 64
     tok = _pb()
     L.check(L.load().csam_vit_attention(C.byref(a), _stream()), "csam_vit_attention")
     _pe("vit_attention", tok, 4.0 * groups * heads * tokens * tokens * hd)

@@ -184,7 +184,7 @@ class CrowdSAM:
         self.last_counts = (n_into_nms, len(data["boxes"]))          # N masks into NMS, K detections kept
         if not encode_rle:
             return data
-        data["rles"] = amg.mask_to_rle_pytorch(data["masks"])
+        data["rles"] = amg.mask_to_rle_arrays(data["masks"])
         data["rles_info"] = [crop_box, [orig_h, orig_w]]
         del data["masks"]
         x0, y0 = crop_box[0], crop_box[1]

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSAM_ABI_VERSION 3
+#define CSAM_ABI_VERSION 4
 #if defined(__GNUC__)
 #define CSAM_API __attribute__((visibility("default")))
 #else
@@ -131,6 +131,8 @@ typedef struct {
   void* out_hi; void* out_lo; int ld_out;
   float* scratch; long long scratch_bytes;   /* >= csam_vit_attention_scratch_bytes() */
   int impl;
+  int p_split;   /* tcgen05 path: 1 = softmax probabilities also as hi+lo pair (3 MMAs for P*V); 0 = P as one
+                    fp16 (2 MMAs, relative error 2^-12 per probability) */
 } csam_attn_args;
 CSAM_API long long csam_vit_attention_scratch_bytes(int groups, int tokens, int heads, int hd, int S);
 CSAM_API int csam_vit_attention(const csam_attn_args* a, void* stream);

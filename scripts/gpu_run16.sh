@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "=== $name"; timeout 1500 "$@" > gpurun_out/$name.log 2>&1; echo "exit $? $name"; tail -n 16 gpurun_out/$name.log | cut -c1-400; }
+export PYTHONPATH=$PWD
+run gemm_micro python scripts/bench_gemm.py
+run tests python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -q -m gpu --timeout 900 -x
+run bench python bench.py --steps 5 --warmup 3 --no-cpu-baseline --gemm-shapes

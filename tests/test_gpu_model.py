@@ -161,3 +161,24 @@ def test_errors_and_state():
         pred.set_image(np.zeros((10, 10, 3), np.uint8), image_format="XYZ")
     with pytest.raises(AssertionError):
         pred.set_torch_image(torch.zeros(1, 3, 100, 100, dtype=torch.uint8), (100, 100))
+
+
+def test_full_scale_vit_l_grid32_against_oracle_run():
+    """BASELINE.json configs[1] at full size (ViT-L + DINOv2-L, 1024 prompts, recipe-v2 weights, image 3).
+    The expected values come from one run of the CPU oracle pipeline (oracle/restate.py OracleCrowdSAM,
+    95 s on 8 cores, same config as bench.test_cfg): 881 masks survive the IoU / stability filters, box NMS
+    keeps one full-image box with PWD score 1.5351906."""
+    import bench
+    from crowdsam_b200.pipeline import CrowdSAM
+
+    pred, *_ = make_predictor("vit_l", "dinov2_vitl14")
+    cfg = {"environ": {"device": DEV}, "model": {"trainfree": False}, "test": bench.test_cfg(256)}
+    model = CrowdSAM(cfg, None, predictor=pred)
+    np.random.seed(42)
+    res = model.generate(weights.synthetic_image(3))
+    n_into_nms, kept = model.last_counts
+    # a prompt sitting exactly on a filter threshold may flip: allow 1% of the count
+    assert abs(n_into_nms - 881) <= 9, n_into_nms
+    assert kept == 1
+    np.testing.assert_array_equal(res["boxes"], np.array([[0.0, 0.0, 1023.0, 1023.0]], dtype=np.float32))
+    np.testing.assert_allclose(res["scores"], [1.5351906], rtol=TOL)
