@@ -32,6 +32,7 @@ struct GemmEpi {
   float* out_f32; int ldo;
   __half* out_hi; __half* out_lo; int ldh;
   int vec_ok;   // all strides / bases allow 16-byte vector access
+  int direct;   // N % 16 == 0 and all strides / bases allow 32-byte row-per-lane access
   // fused epilogues
   const float* gamma; const float* beta; float eps;
   const float* pe; int ldpe; int pe_mod; __half* out2_hi; __half* out2_lo;
@@ -181,8 +182,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // EPI_LN keeps a 128-value row slice per epilogue thread: move the control warpgroup's registers to the
+  // two epilogue warpgroups (384 x 168 = 128 x 56 + 256 x 224)
+  // (each role executes its own setmaxnreg at the top of its branch: ptxas budgets registers per region and a
+  //  join after the instruction would force the smaller budget on everything that follows)
+  constexpr bool REGSPLIT = (EPI == EPI_LN);
+
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
+    if constexpr (REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       if (WRES) {   // the whole weight matrix (tiles_n == 1), once
@@ -223,6 +231,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    if constexpr (REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, B_MN ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
@@ -259,14 +268,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    if constexpr (REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  } else {
     // ------------------------------------------------------------------ epilogue
+    if constexpr (REGSPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int ew = warp - 4;
     const int q = ew & 3;                        // TMEM lane quadrant == warp % 4
     const int ch = ew >> 2;                      // which half of the tile's columns this warp owns
     constexpr int HALF = BN / 2;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     int local = 0;
+    if constexpr (EPI == EPI_LN) {
+      // gamma / beta / bias are read as warp-uniform (broadcast) shared loads in the row-per-lane epilogue
+      const int et = threadIdx.x - 128;          // 0..255
+      float* sg = epi_smem + 1024;
+      sg[et] = e.gamma[et];
+      sg[256 + et] = e.beta[et];
+      sg[512 + et] = e.bias ? e.bias[et] : 0.f;
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+    }
+    if constexpr (EPI == EPI_UP1) {
+      const int et = threadIdx.x - 128;
+      float* sg = epi_smem + 1024;
+      if (et < 64) { sg[et] = e.gamma[et]; sg[64 + et] = e.beta[et]; }
+      sg[128 + et] = e.bias[et];
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+    }
+    if constexpr (EPI == EPI_UP2) {
+      const int et = threadIdx.x - 128;
+      if (et < 128) epi_smem[1024 + et] = e.bias[et];
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+    }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
       const int buf = local & 1;
       const uint32_t bphase = (local >> 1) & 1;
@@ -275,11 +308,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
       if constexpr (EPI == EPI_UP2) {
         // stage the 4 x 32 hypernetwork vectors of this tile's prompt (all 128 rows share it)
         const int et = threadIdx.x - 128;
-        if (et < 128) epi_smem[buf * 128 + et] = e.hyper[(size_t)(m0 >> 14) * 128 + et];
+        if (et < 128) epi_smem[buf * 128 + (et & 31) * 4 + (et >> 5)] = e.hyper[(size_t)(m0 >> 14) * 128 + et];   // [l][j] -> [j][l]
         asm volatile("bar.sync 5, 256;" ::: "memory");
       }
-      mbar_wait(&tfull_bar[buf], bphase);
-      tc_fence_after();
+      if constexpr (EPI != EPI_LN && EPI != EPI_STD) {   // EPI_LN / EPI_STD request their residual first, then wait
+        mbar_wait(&tfull_bar[buf], bphase);
+        tc_fence_after();
+      }
       const int r = m0 + q * 32 + lane;
       const uint32_t col_addr = lane_addr + buf * BN + ch * HALF;
       float* wb = epi_smem + 1024 + ew * 512;          // this warp's 32x16 staging tile
@@ -287,6 +322,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
       if constexpr (EPI == EPI_STD) {
         const bool staged = e.vec_ok && (e.N & 3) == 0;
         const float rs = (e.row_scale && r < e.M) ? e.row_scale[r] : 1.f;
+        if (e.direct) {
+          // Row-per-lane (the TMEM layout) with whole 32-byte sectors per lane: no shared-memory transposition,
+          // and the residual of the lane's row slice is requested before the accumulator is waited for.
+          int orow = -1;
+          if (r < e.M) orow = e.row_map ? e.row_map[r] : r;
+          float res[HALF];
+          const int cbase = n0 + ch * HALF;
+          if (orow >= 0 && e.residual) {
+            const float* pr = e.residual + (size_t)(e.res_mod > 0 ? (orow % e.res_mod) : orow) * e.ldr + cbase;
+#pragma unroll
+            for (int c = 0; c < HALF; c += 8)
+              if (cbase + c < e.N) ldg256f(pr + c, res + c);
+          } else {
+#pragma unroll
+            for (int c = 0; c < HALF; ++c) res[c] = 0.f;
+          }
+          mbar_wait(&tfull_bar[buf], bphase);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < HALF; c += 16) {
+            const int col0 = cbase + c;
+            if (col0 < e.N) {                          // warp-uniform (N is a multiple of 16 here)
+              uint32_t raw[16];
+              tmem_ld16(col_addr + c, raw);
+              tmem_ld_wait();
+              float v[16];
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f), cs = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (e.bias) b = *reinterpret_cast<const float4*>(e.bias + col0 + j);
+                if (e.col_scale) cs = *reinterpret_cast<const float4*>(e.col_scale + col0 + j);
+                v[j + 0] = apply_act(__uint_as_float(raw[j + 0]) * rs + b.x, e.act) * cs.x + res[c + j + 0];
+                v[j + 1] = apply_act(__uint_as_float(raw[j + 1]) * rs + b.y, e.act) * cs.y + res[c + j + 1];
+                v[j + 2] = apply_act(__uint_as_float(raw[j + 2]) * rs + b.z, e.act) * cs.z + res[c + j + 2];
+                v[j + 3] = apply_act(__uint_as_float(raw[j + 3]) * rs + b.w, e.act) * cs.w + res[c + j + 3];
+              }
+              if (orow >= 0) {
+                if (e.out_f32) {
+                  float* po = e.out_f32 + (size_t)orow * e.ldo + col0;
+                  stg256f(po, v);
+                  stg256f(po + 8, v + 8);
+                }
+                if (e.out_hi) store_pair16(e.out_hi, e.out_lo, (size_t)orow * e.ldh + col0, v);
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[buf]);
+          continue;
+        }
+        mbar_wait(&tfull_bar[buf], bphase);
+        tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < HALF; c += 16) {
           const int col0 = n0 + ch * HALF + c;
@@ -343,11 +430,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
       } else if constexpr (EPI == EPI_LN) {
         // full-row LayerNorm: this lane owns columns [ch*128, ch*128+128) of row r
         static_assert(EPI != EPI_LN || BN == 256, "EPI_LN needs the whole 256-wide row in one tile");
+        // Row-per-lane end to end (the TMEM layout): every lane reads / writes whole 32-byte sectors of its own
+        // row, so no shared-memory transposition is needed, and ALL residual loads of the tile (1 KB per row) are
+        // issued before the accumulator is waited for -- 128 KB in flight per SM instead of one 16-column
+        // chunk at a time (the chunked version exposed one HBM round trip per chunk: 26 us per tile).
         float x[128];
-        float sum = 0.f;
+        const bool rvalid = r < e.M;
+        const int rrow = e.res_mod > 0 ? (r % e.res_mod) : r;
+        if (rvalid && e.res_hi) {
+          const __half* ph = e.res_hi + (size_t)rrow * e.ldrh + ch * 128;
+          const __half* pl = e.res_lo + (size_t)rrow * e.ldrh + ch * 128;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint32_t hw[8], lw[8];
+            ldg256(ph + i * 16, hw);
+            ldg256(pl + i * 16, lw);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[k]));
+              const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[k]));
+              x[i * 16 + 2 * k] = hf.x + lf.x;
+              x[i * 16 + 2 * k + 1] = hf.y + lf.y;
+            }
+          }
+        } else if (rvalid && e.residual) {
+          const float4* pr = reinterpret_cast<const float4*>(e.residual + (size_t)rrow * e.ldr + ch * 128);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float4 v = pr[i];
+            x[i * 4] = v.x; x[i * 4 + 1] = v.y; x[i * 4 + 2] = v.z; x[i * 4 + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 128; ++i) x[i] = 0.f;
+        }
         {
-          // pull the NEXT tile's residual rows towards L2 while this tile is normalised: the epilogue warps
-          // alone cannot keep enough loads in flight to hide HBM latency
+          // pull the NEXT tile's residual rows towards L2 while this tile is normalised
           const int tn = t + gridDim.x;
           if (tn < num_tiles && e.res_mod == 0) {
             const int prow = (tn / tiles_n) * BM + (threadIdx.x - 128) / 2;      // 256 threads -> 128 rows x 2 halves
@@ -369,48 +487,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
             }
           }
         }
+        mbar_wait(&tfull_bar[buf], bphase);
+        tc_fence_after();
+        const float* s_gamma = epi_smem + 1024;      // [256] staged once per CTA (see below the role dispatch)
+        const float* s_beta = s_gamma + 256;
+        const float* s_bias = s_gamma + 512;
+        float sum = 0.f;
 #pragma unroll
         for (int c = 0; c < 128; c += 16) {
-          const int colb = ch * 128 + c;
-          // residual tile, read coalesced, transposed to the row-per-lane layout
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int rr = it * 8 + (lane >> 2), sl = lane & 3;
-            const int row = row_base + rr;
-            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < e.M) {
-              const int rrow = e.res_mod > 0 ? (row % e.res_mod) : row;
-              if (e.residual) {
-                rv = *reinterpret_cast<const float4*>(e.residual + (size_t)rrow * e.ldr + colb + sl * 4);
-              } else if (e.res_hi) {
-                const uint2 uh = *reinterpret_cast<const uint2*>(e.res_hi + (size_t)rrow * e.ldrh + colb + sl * 4);
-                const uint2 ul = *reinterpret_cast<const uint2*>(e.res_lo + (size_t)rrow * e.ldrh + colb + sl * 4);
-                const __half2 h0 = *reinterpret_cast<const __half2*>(&uh.x), h1 = *reinterpret_cast<const __half2*>(&uh.y);
-                const __half2 l0 = *reinterpret_cast<const __half2*>(&ul.x), l1 = *reinterpret_cast<const __half2*>(&ul.y);
-                rv.x = __low2float(h0) + __low2float(l0); rv.y = __high2float(h0) + __high2float(l0);
-                rv.z = __low2float(h1) + __low2float(l1); rv.w = __high2float(h1) + __high2float(l1);
-              }
-            }
-            *reinterpret_cast<float4*>(wb + wb_off(rr, sl)) = rv;
-          }
-          __syncwarp();
-          float rv16[16];
-          stage_get(wb, lane, rv16);
-          __syncwarp();
           uint32_t raw[16];
           tmem_ld16(col_addr + c, raw);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            const float4 b = e.bias ? *reinterpret_cast<const float4*>(e.bias + colb + j) : make_float4(0, 0, 0, 0);
-            x[c + j + 0] = __uint_as_float(raw[j + 0]) + b.x + rv16[j + 0];
-            x[c + j + 1] = __uint_as_float(raw[j + 1]) + b.y + rv16[j + 1];
-            x[c + j + 2] = __uint_as_float(raw[j + 2]) + b.z + rv16[j + 2];
-            x[c + j + 3] = __uint_as_float(raw[j + 3]) + b.w + rv16[j + 3];
+            const float4 b = *reinterpret_cast<const float4*>(s_bias + ch * 128 + c + j);
+            x[c + j + 0] += __uint_as_float(raw[j + 0]) + b.x;
+            x[c + j + 1] += __uint_as_float(raw[j + 1]) + b.y;
+            x[c + j + 2] += __uint_as_float(raw[j + 2]) + b.z;
+            x[c + j + 3] += __uint_as_float(raw[j + 3]) + b.w;
             sum += (x[c + j] + x[c + j + 1]) + (x[c + j + 2] + x[c + j + 3]);
           }
         }
-        // accumulator drained: release the TMEM buffer before the (long) normalise + store phase
+        // accumulator drained: release the TMEM buffer before the normalise + store phase
         tc_fence_before();
         mbar_arrive(&tempty_bar[buf]);
         float* ex_sum = epi_smem;            // [2][128]
@@ -425,37 +523,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
         ex_sq[ch * 128 + row_in_tile] = sq;
         asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
         const float rstd = 1.0f / sqrtf((ex_sq[row_in_tile] + ex_sq[128 + row_in_tile]) * (1.0f / 256.0f) + e.eps);
+        if (rvalid) {
 #pragma unroll
-        for (int c = 0; c < 128; c += 16) {
-          const int colb = ch * 128 + c;
-          float nv[16];
+          for (int c = 0; c < 128; c += 16) {
+            const int col = ch * 128 + c;
+            float y[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) nv[j] = (x[c + j] - mean) * rstd;
-          stage_put(wb, lane, nv);
-          __syncwarp();
+            for (int j = 0; j < 16; j += 4) {
+              const float4 g = *reinterpret_cast<const float4*>(s_gamma + col + j);
+              const float4 b = *reinterpret_cast<const float4*>(s_beta + col + j);
+              y[j + 0] = (x[c + j + 0] - mean) * rstd * g.x + b.x;
+              y[j + 1] = (x[c + j + 1] - mean) * rstd * g.y + b.y;
+              y[j + 2] = (x[c + j + 2] - mean) * rstd * g.z + b.z;
+              y[j + 3] = (x[c + j + 3] - mean) * rstd * g.w + b.w;
+            }
+            if (e.out_f32) {
+              float* po = e.out_f32 + (size_t)r * e.ldo + col;
+              stg256f(po, y);
+              stg256f(po + 8, y + 8);
+            }
+            if (e.out_hi) store_pair16(e.out_hi, e.out_lo, (size_t)r * e.ldh + col, y);
+            if (e.out2_hi) {
+              const float* pp = e.pe + (size_t)(e.pe_mod > 0 ? r % e.pe_mod : r) * e.ldpe + col;
+              float z[16];
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int rr = it * 8 + (lane >> 2), sl = lane & 3;
-            const int row = row_base + rr, col = colb + sl * 4;
-            if (row < e.M) {
-              const float4 n4 = *reinterpret_cast<const float4*>(wb + wb_off(rr, sl));
-              const float4 g4 = *reinterpret_cast<const float4*>(e.gamma + col);
-              const float4 b4 = *reinterpret_cast<const float4*>(e.beta + col);
-              const float y[4] = {n4.x * g4.x + b4.x, n4.y * g4.y + b4.y, n4.z * g4.z + b4.z, n4.w * g4.w + b4.w};
-              if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ldo + col) = make_float4(y[0], y[1], y[2], y[3]);
-              if (e.out_hi) store_pair4(e.out_hi, e.out_lo, (size_t)row * e.ldh + col, y);
-              if (e.out2_hi) {
-                const float4 p4 = *reinterpret_cast<const float4*>(e.pe + (size_t)(e.pe_mod > 0 ? row % e.pe_mod : row) * e.ldpe + col);
-                const float z[4] = {y[0] + p4.x, y[1] + p4.y, y[2] + p4.z, y[3] + p4.w};
-                store_pair4(e.out2_hi, e.out2_lo, (size_t)row * e.ldh + col, z);
+              for (int j = 0; j < 16; j += 4) {
+                const float4 p4 = *reinterpret_cast<const float4*>(pp + j);
+                z[j] = y[j] + p4.x; z[j + 1] = y[j + 1] + p4.y; z[j + 2] = y[j + 2] + p4.z; z[j + 3] = y[j + 3] + p4.w;
               }
+              store_pair16(e.out2_hi, e.out2_lo, (size_t)r * e.ldh + col, z);
             }
           }
-          __syncwarp();
         }
         continue;   // tempty already signalled
       } else if constexpr (EPI == EPI_UP1) {
-        // two of the four (dy,dx) positions per warp half: pos = ch*2 + g
+        // two of the four (dy,dx) positions per warp half: pos = ch*2 + g ; row-per-lane, whole sectors per lane
+        const float* s_gamma = epi_smem + 1024;      // [64], staged once per CTA
+        const float* s_beta = s_gamma + 64;          // [64]
+        const float* s_bias = s_gamma + 128;         // [256]
+        const bool valid = r < e.M;
+        const int p = r >> 12, pix = r & 4095, yy = pix >> 6, xx = pix & 63;
 #pragma unroll 1
         for (int gI = 0; gI < 2; ++gI) {
           const int pos = ch * 2 + gI;
@@ -468,7 +575,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-              const float4 b = *reinterpret_cast<const float4*>(e.bias + pos * 64 + c + j);
+              const float4 b = *reinterpret_cast<const float4*>(s_bias + pos * 64 + c + j);
               x[c + j + 0] = __uint_as_float(raw[j + 0]) + b.x;
               x[c + j + 1] = __uint_as_float(raw[j + 1]) + b.y;
               x[c + j + 2] = __uint_as_float(raw[j + 2]) + b.z;
@@ -481,36 +588,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 64; ++j) { const float d = x[j] - mean; sq = fmaf(d, d, sq); }
           const float rstd = 1.0f / sqrtf(sq * (1.0f / 64.0f) + e.eps);
+          const size_t orow = (size_t)p * 16384 + (size_t)(2 * yy + (pos >> 1)) * 128 + (2 * xx + (pos & 1));
+          if (valid) {
 #pragma unroll
-          for (int c = 0; c < 64; c += 16) {
-            float nv[16];
+            for (int c = 0; c < 64; c += 16) {
+              float y[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) nv[j] = (x[c + j] - mean) * rstd;
-            stage_put(wb, lane, nv);
-            __syncwarp();
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int rr = it * 8 + (lane >> 2), sl = lane & 3;
-              const int row = row_base + rr, col = c + sl * 4;
-              if (row < e.M) {
-                const int p = row >> 12, pix = row & 4095, yy = pix >> 6, xx = pix & 63;
-                const size_t orow = (size_t)p * 16384 + (size_t)(2 * yy + (pos >> 1)) * 128 + (2 * xx + (pos & 1));
-                const float4 n4 = *reinterpret_cast<const float4*>(wb + wb_off(rr, sl));
-                const float4 g4 = *reinterpret_cast<const float4*>(e.gamma + col);
-                const float4 b4 = *reinterpret_cast<const float4*>(e.beta + col);
-                const float y[4] = {gelu_erf(n4.x * g4.x + b4.x), gelu_erf(n4.y * g4.y + b4.y),
-                                    gelu_erf(n4.z * g4.z + b4.z), gelu_erf(n4.w * g4.w + b4.w)};
-                store_pair4(e.out_hi, e.out_lo, orow * 64 + col, y);
+              for (int j = 0; j < 16; j += 4) {
+                const float4 g4 = *reinterpret_cast<const float4*>(s_gamma + c + j);
+                const float4 b4 = *reinterpret_cast<const float4*>(s_beta + c + j);
+                y[j + 0] = gelu_erf((x[c + j + 0] - mean) * rstd * g4.x + b4.x);
+                y[j + 1] = gelu_erf((x[c + j + 1] - mean) * rstd * g4.y + b4.y);
+                y[j + 2] = gelu_erf((x[c + j + 2] - mean) * rstd * g4.z + b4.z);
+                y[j + 3] = gelu_erf((x[c + j + 3] - mean) * rstd * g4.w + b4.w);
               }
+              store_pair16(e.out_hi, e.out_lo, orow * 64 + c, y);
             }
-            __syncwarp();
           }
         }
       } else if constexpr (EPI == EPI_UP2) {
         // row r = p*16384 + Y1*128 + X1 ; this warp half handles dy = ch, dx = 0,1 (32 channels each)
         const bool valid = r < e.M;
         const int p = r >> 14, pix = r & 16383, Y1 = pix >> 7, X1 = pix & 127;
-        const float* hy = epi_smem + buf * 128;
+        const float* hy = epi_smem + buf * 128;      // [32 channels][4 masks]
+        const float* s_bias = epi_smem + 1024;       // [128], staged once per CTA
         float mk[4][2];
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
@@ -519,10 +620,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
           tmem_ld_wait();
           float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float u = gelu_erf(__uint_as_float(raw[j]) + e.bias[(ch * 2 + dx) * 32 + j]);
-            a0 = fmaf(u, hy[j], a0); a1 = fmaf(u, hy[32 + j], a1);
-            a2 = fmaf(u, hy[64 + j], a2); a3 = fmaf(u, hy[96 + j], a3);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(s_bias + (ch * 2 + dx) * 32 + j);
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float u = gelu_erf(__uint_as_float(raw[j + k]) + bb[k]);
+              const float4 h = *reinterpret_cast<const float4*>(hy + (j + k) * 4);
+              a0 = fmaf(u, h.x, a0); a1 = fmaf(u, h.y, a1); a2 = fmaf(u, h.z, a2); a3 = fmaf(u, h.w, a3);
+            }
           }
           mk[0][dx] = a0; mk[1][dx] = a1; mk[2][dx] = a2; mk[3][dx] = a3;
         }
@@ -685,6 +791,12 @@ extern "C" int csam_gemm(const csam_gemm_args* a, void* stream) {
   if (a->residual && (!al16(a->residual) || (a->ldr & 3))) e.vec_ok = 0;
   if (a->out_f32 && (!al16(a->out_f32) || (a->ldo & 3))) e.vec_ok = 0;
   if (a->out_hi && (!al16(a->out_hi) || (a->ldh & 7) || (a->out_lo && !al16(a->out_lo)))) e.vec_ok = 0;
+  {
+    auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
+    e.direct = e.vec_ok && (a->N & 15) == 0 && al32(a->residual) && (a->ldr & 7) == 0 && al32(a->out_f32) &&
+               (a->ldo & 7) == 0 && al32(a->out_hi) && al32(a->out_lo) && (a->ldh & 15) == 0;
+    if (const char* env = getenv("CSAM_GEMM_DIRECT")) e.direct = e.direct && atoi(env) != 0;
+  }
 
   if (a->impl == CSAM_GEMM_SIMT) {
     dim3 grid((a->M + 63) / 64, (a->N + 63) / 64);
@@ -709,7 +821,13 @@ extern "C" int csam_gemm(const csam_gemm_args* a, void* stream) {
     CSAM_REQUIRE(a->N == 256 && a->gamma && a->beta && !a->row_map && !a->row_scale && !a->col_scale && a->act == 0,
                  "csam_gemm(EPI_LN): N must be 256 with gamma/beta and no other epilogue options");
     CSAM_REQUIRE(e.vec_ok && (!a->pe || ((a->ldpe & 3) == 0 && al16(a->pe))) && (!a->out2_hi || a->pe) &&
-                     al16(a->gamma) && al16(a->beta), "csam_gemm(EPI_LN): alignment");
+                     al16(a->gamma) && al16(a->beta),
+                 "csam_gemm(EPI_LN): alignment");
+    auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
+    CSAM_REQUIRE((a->ldh & 15) == 0 && al32(a->out_hi) && al32(a->out_lo) && al32(a->out2_hi) && al32(a->out2_lo) &&
+                     al32(a->out_f32) && (a->ldo & 7) == 0 &&
+                     (!a->res_hi || ((a->ldrh & 15) == 0 && al32(a->res_hi) && al32(a->res_lo))),
+                 "csam_gemm(EPI_LN): outputs and the h16 residual need 32-byte aligned rows");
     if (wres_ok(256))
       return split ? launch_tc<256, 3, false, EPI_LN, true>(a, e, st) : launch_tc<256, 1, false, EPI_LN, true>(a, e, st);
     return split ? launch_tc<256, 3, false, EPI_LN>(a, e, st) : launch_tc<256, 1, false, EPI_LN>(a, e, st);
@@ -717,6 +835,8 @@ extern "C" int csam_gemm(const csam_gemm_args* a, void* stream) {
   if (a->epi == CSAM_EPI_UP1) {
     CSAM_REQUIRE(a->N == 256 && (a->M % 4096) == 0 && a->bias && a->gamma && a->beta && a->out_hi,
                  "csam_gemm(EPI_UP1): N = 4x64, M = P*4096, bias/gamma/beta and an h16 output are required");
+    CSAM_REQUIRE((reinterpret_cast<uintptr_t>(a->out_hi) & 31) == 0 && (reinterpret_cast<uintptr_t>(a->out_lo) & 31) == 0,
+                 "csam_gemm(EPI_UP1): the h16 output must be 32-byte aligned");
     return split ? launch_tc<256, 3, false, EPI_UP1>(a, e, st) : launch_tc<256, 1, false, EPI_UP1>(a, e, st);
   }
   if (a->epi == CSAM_EPI_UP2) {

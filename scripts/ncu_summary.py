@@ -13,7 +13,7 @@ WANT = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
 w = csv.writer(sys.stdout)
 first = True
 for rep in sys.argv[1:]:
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = [hdr.index(x) for x in WANT if x in hdr]
