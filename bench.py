@@ -244,7 +244,6 @@ def main():
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    ops.PROFILER = ops.Profiler(detail=args.gemm_shapes)
     l0 = lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dets, nk = [], (0, 0)
@@ -261,6 +260,19 @@ def main():
     print(f"[bench rank {rank}] resident leg: {ms_total / args.steps:.1f} ms/step, masks into NMS {nk[0]}, kept {nk[1]}",
           file=sys.stderr)
     launches = lib.launch_count() - l0
+    clocks = sampler.stop()
+    # Per-kernel-class CUDA-event timing (the roofline numbers) runs as a SECOND pass over the same K images:
+    # two event records around each of ~460 launches cost ~5 ms per step, which must not sit inside `value`.
+    # Same kernels, same inputs, same stream; each class's share is taken against this pass's own step time.
+    ops.PROFILER = ops.Profiler(detail=args.gemm_shapes)
+    pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pv0.record()
+    for i in range(args.steps):
+        np.random.seed(42)
+        model.run_resident(resident[args.warmup + i])
+    pv1.record()
+    torch.cuda.synchronize()
+    prof_ms_total = pv0.elapsed_time(pv1)
     prof = ops.PROFILER.summary()
     ops.PROFILER = None
     if args.gemm_shapes and rank == 0:
@@ -270,7 +282,6 @@ def main():
             print(f"[gemm] {k:28s} n/step={v['launches'] / args.steps:6.1f} ms/step={v['total_ms'] / args.steps:8.3f} "
                   f"avg_us={1e3 * v['total_ms'] / v['launches']:8.1f} TFLOP/s={tf:7.1f}", file=sys.stderr)
         prof = {k: v for k, v in prof.items() if not k.startswith("gemm ")}
-    clocks = sampler.stop()
     t = torch.tensor([ms_total], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -349,7 +360,7 @@ def main():
             peak, unit = peaks["hbm_gbs"], "GB/s"
         return {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                 "traffic": None, "launches_per_step": r["launches"] / args.steps, "avg_launch_ms": per_launch_ms,
-                "share_of_step": r["total_ms"] / ms_total, "peak_source": peaks["source"]}
+                "share_of_step": r["total_ms"] / prof_ms_total, "peak_source": peaks["source"]}
 
     roofs = [x for x in (roof("gemm_tensor", "tensor"), roof("gemm_hbm", "hbm"), roof("vit_attention", "tensor"),
                          roof("mask_post_write", "hbm"), roof("mask_post_stats", "hbm")) if x]
@@ -385,6 +396,7 @@ def main():
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": dominant, "rooflines": roofs,
             "kernel_ms_per_step": {k: v["total_ms"] / args.steps for k, v in prof.items()},
+            "profiled_pass_ms_per_step": prof_ms_total / args.steps,
             "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:

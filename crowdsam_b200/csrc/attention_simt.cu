@@ -154,13 +154,17 @@ __global__ void __launch_bounds__(128) attn_few_keys_kernel(csam_dec_attn_args a
   float* ks = sm;
   float* vs = sm + a.nk * C;
   const int b = blockIdx.y;
-  const float* kb = a.k + (size_t)(a.Bk == 1 ? 0 : b) * a.nk * C;
-  const float* vb = a.v + (size_t)(a.Bk == 1 ? 0 : b) * a.nk * C;
-  for (int i = threadIdx.x; i < a.nk * C; i += 128) { ks[i] = kb[i]; vs[i] = vb[i]; }
+  const int ldq = a.ldq ? a.ldq : C, ldk = a.ldk ? a.ldk : C, ldv = a.ldv ? a.ldv : C;
+  const float* kb = a.k + (size_t)(a.Bk == 1 ? 0 : b) * a.nk * ldk;
+  const float* vb = a.v + (size_t)(a.Bk == 1 ? 0 : b) * a.nk * ldv;
+  for (int i = threadIdx.x; i < a.nk * C; i += 128) {
+    ks[i] = kb[(size_t)(i / C) * ldk + (i % C)];
+    vs[i] = vb[(size_t)(i / C) * ldv + (i % C)];
+  }
   __syncthreads();
   const int qi = blockIdx.x * 128 + threadIdx.x;
   if (qi >= a.nq) return;
-  const float* q = a.q + ((size_t)(a.Bq == 1 ? 0 : b) * a.nq + qi) * C;
+  const float* q = a.q + ((size_t)(a.Bq == 1 ? 0 : b) * a.nq + qi) * ldq;
   const float scale = 1.0f / sqrtf((float)a.hd);
   const size_t oo = ((size_t)b * a.nq + qi) * C;
   for (int h = 0; h < a.heads; ++h) {
@@ -195,11 +199,12 @@ __global__ void __launch_bounds__(256) attn_few_queries_kernel(csam_dec_attn_arg
   float* sc = sm;                       // [nq][nk]
   float* qs = sc + (size_t)nq * nk;     // [nq][hd]
   float* red = qs + nq * hd;            // [8 warps][nq] then partial outputs [16][nq][hd]
-  const float* qb = a.q + (size_t)(a.Bq == 1 ? 0 : b) * nq * C + h * hd;
-  const float* kb = a.k + (size_t)(a.Bk == 1 ? 0 : b) * nk * C + h * hd;
-  const float* vb = a.v + (size_t)(a.Bk == 1 ? 0 : b) * nk * C + h * hd;
+  const int ldq = a.ldq ? a.ldq : C, ldk = a.ldk ? a.ldk : C, ldv = a.ldv ? a.ldv : C;
+  const float* qb = a.q + (size_t)(a.Bq == 1 ? 0 : b) * nq * ldq + h * hd;
+  const float* kb = a.k + (size_t)(a.Bk == 1 ? 0 : b) * nk * ldk + h * hd;
+  const float* vb = a.v + (size_t)(a.Bk == 1 ? 0 : b) * nk * ldv + h * hd;
   const float scale = 1.0f / sqrtf((float)hd);
-  for (int i = threadIdx.x; i < nq * hd; i += 256) qs[i] = qb[(size_t)(i / hd) * C + (i % hd)];
+  for (int i = threadIdx.x; i < nq * hd; i += 256) qs[i] = qb[(size_t)(i / hd) * ldq + (i % hd)];
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float mx[8];
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(256) attn_few_queries_kernel(csam_dec_attn_arg
   for (int key = threadIdx.x; key < nk; key += 256) {
     float kv[32];
     for (int d = 0; d < hd; d += 4) {
-      const float4 t = *reinterpret_cast<const float4*>(kb + (size_t)key * C + d);
+      const float4 t = *reinterpret_cast<const float4*>(kb + (size_t)key * ldk + d);
       kv[d] = t.x; kv[d + 1] = t.y; kv[d + 2] = t.z; kv[d + 3] = t.w;
     }
 #pragma unroll
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(256) attn_few_queries_kernel(csam_dec_attn_arg
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     if (dd < hd) {
       for (int key = kg; key < nk; key += 16) {
-        const float vv = vb[(size_t)key * C + dd];
+        const float vv = vb[(size_t)key * ldv + dd];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           if (i < nq) acc[i] = fmaf(sc[(size_t)i * nk + key], vv, acc[i]);
@@ -360,21 +365,22 @@ int vit_attention_simt(const csam_attn_args* a, cudaStream_t st) {
 template <int NK>
 __global__ void __launch_bounds__(256) attn_i2t_kernel(csam_dec_attn_args a, int rows_per_block) {
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* kb = a.k + (size_t)(a.Bk == 1 ? 0 : b) * NK * 128 + lane * 4;
-  const float* vb = a.v + (size_t)(a.Bk == 1 ? 0 : b) * NK * 128 + lane * 4;
+  const int ldq = a.ldq ? a.ldq : 128, ldk = a.ldk ? a.ldk : 128, ldv = a.ldv ? a.ldv : 128;
+  const float* kb = a.k + (size_t)(a.Bk == 1 ? 0 : b) * NK * ldk + lane * 4;
+  const float* vb = a.v + (size_t)(a.Bk == 1 ? 0 : b) * NK * ldv + lane * 4;
   float4 kr[NK], vr[NK];
 #pragma unroll
   for (int j = 0; j < NK; ++j) {
-    kr[j] = *reinterpret_cast<const float4*>(kb + j * 128);
-    vr[j] = *reinterpret_cast<const float4*>(vb + j * 128);
+    kr[j] = *reinterpret_cast<const float4*>(kb + j * ldk);
+    vr[j] = *reinterpret_cast<const float4*>(vb + j * ldv);
   }
-  const float* qb = a.q + (size_t)(a.Bq == 1 ? 0 : b) * a.nq * 128;
+  const float* qb = a.q + (size_t)(a.Bq == 1 ? 0 : b) * a.nq * ldq;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(r0 + rows_per_block, a.nq);
   __half* ohi = static_cast<__half*>(a.out_hi);
   __half* olo = static_cast<__half*>(a.out_lo);
   for (int r = r0 + warp; r < r1; r += 8) {
-    const float4 q = *reinterpret_cast<const float4*>(qb + (size_t)r * 128 + lane * 4);
+    const float4 q = *reinterpret_cast<const float4*>(qb + (size_t)r * ldq + lane * 4);
     float s[NK];
     float m = -INFINITY;
 #pragma unroll
@@ -409,15 +415,16 @@ __global__ void __launch_bounds__(512) attn_t2i_kernel(csam_dec_attn_args a) {
   extern __shared__ float sm[];
   constexpr int NW = 16;
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* qb = a.q + (size_t)(a.Bq == 1 ? 0 : b) * NQ * 128 + lane * 4;
-  const float* kb = a.k + (size_t)(a.Bk == 1 ? 0 : b) * a.nk * 128 + lane * 4;
-  const float* vb = a.v + (size_t)(a.Bk == 1 ? 0 : b) * a.nk * 128 + lane * 4;
+  const int ldq = a.ldq ? a.ldq : 128, ldk = a.ldk ? a.ldk : 128, ldv = a.ldv ? a.ldv : 128;
+  const float* qb = a.q + (size_t)(a.Bq == 1 ? 0 : b) * NQ * ldq + lane * 4;
+  const float* kb = a.k + (size_t)(a.Bk == 1 ? 0 : b) * a.nk * ldk + lane * 4;
+  const float* vb = a.v + (size_t)(a.Bk == 1 ? 0 : b) * a.nk * ldv + lane * 4;
   float4 qr[NQ];
   float m[NQ], l[NQ];
   float4 acc[NQ];
 #pragma unroll
   for (int i = 0; i < NQ; ++i) {
-    qr[i] = *reinterpret_cast<const float4*>(qb + i * 128);
+    qr[i] = *reinterpret_cast<const float4*>(qb + i * ldq);
     qr[i].x *= 0.25f; qr[i].y *= 0.25f; qr[i].z *= 0.25f; qr[i].w *= 0.25f;
     m[i] = -INFINITY; l[i] = 0.f; acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -426,8 +433,8 @@ __global__ void __launch_bounds__(512) attn_t2i_kernel(csam_dec_attn_args a) {
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int key = min(k0 + t, a.nk - 1);
-      kk[t] = *reinterpret_cast<const float4*>(kb + (size_t)key * 128);
-      vv[t] = *reinterpret_cast<const float4*>(vb + (size_t)key * 128);
+      kk[t] = *reinterpret_cast<const float4*>(kb + (size_t)key * ldk);
+      vv[t] = *reinterpret_cast<const float4*>(vb + (size_t)key * ldv);
     }
 #pragma unroll
     for (int i = 0; i < NQ; ++i) {
@@ -497,6 +504,8 @@ extern "C" long long csam_vit_attention_scratch_bytes(int groups, int tokens, in
 extern "C" int csam_attn_few_keys(const csam_dec_attn_args* a, void* stream) {
   CSAM_REQUIRE(a && a->q && a->k && a->v && (a->out_f32 || a->out_hi), "csam_attn_few_keys: bad args");
   CSAM_REQUIRE(a->nk >= 1 && a->nk <= 8 && a->hd <= 32 && a->B <= 65535, "csam_attn_few_keys: nk <= 8, hd <= 32");
+  CSAM_REQUIRE(((a->ldq | a->ldk | a->ldv) & 3) == 0 && a->ldq >= 0 && a->ldk >= 0 && a->ldv >= 0,
+               "csam_attn_few_keys: row strides must be multiples of 4 floats");
   const int C = a->heads * a->hd;
   if (a->heads == 8 && a->hd == 16 && a->nk == 7) {   // image -> token cross attention
     const int rows_per_block = 256;
@@ -513,6 +522,8 @@ extern "C" int csam_attn_few_queries(const csam_dec_attn_args* a, void* stream) 
   CSAM_REQUIRE(a && a->q && a->k && a->v && (a->out_f32 || a->out_hi), "csam_attn_few_queries: bad args");
   CSAM_REQUIRE(a->nq >= 1 && a->nq <= 8 && a->hd <= 32 && (a->hd % 4) == 0 && a->B <= 65535,
                "csam_attn_few_queries: nq <= 8, hd <= 32");
+  CSAM_REQUIRE(((a->ldq | a->ldk | a->ldv) & 3) == 0 && a->ldq >= 0 && a->ldk >= 0 && a->ldv >= 0,
+               "csam_attn_few_queries: row strides must be multiples of 4 floats");
   if (a->heads == 8 && a->hd == 16 && a->nq == 7) {   // token -> image cross attention
     const size_t sm = (size_t)16 * 7 * (8 + 8 + 128) * sizeof(float);
     static bool attr2 = false;

@@ -33,6 +33,7 @@ struct GemmEpi {
   __half* out_hi; __half* out_lo; int ldh;
   int vec_ok;   // all strides / bases allow 16-byte vector access
   int direct;   // N % 16 == 0 and all strides / bases allow 32-byte row-per-lane access
+  int l2_prefetch;   // resident-weight mode: tiles of look-ahead for the A operand's L2 prefetch (0 = off)
   // fused epilogues
   const float* gamma; const float* beta; float eps;
   const float* pe; int ldpe; int pe_mod; __half* out2_hi; __half* out2_lo;
@@ -172,7 +173,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 256); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); }   // tempty: one elected lane per epilogue warp
     mbar_init(w_bar, 1);
     fence_barrier_init();
   }
@@ -193,17 +194,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
     if constexpr (REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      if (WRES) {   // the whole weight matrix (tiles_n == 1), once
+      if (WRES) {
+        // this CTA's slice of the weight matrix, once: the grid is a multiple of tiles_n, so every tile of a
+        // CTA (t = blockIdx.x + i * gridDim.x) has the same n index blockIdx.x % tiles_n
+        const int wn0 = (blockIdx.x % tiles_n) * BN;
         mbar_expect_tx(w_bar, num_kb * Cfg::NOPS * Cfg::W_BYTES);
         for (int kb = 0; kb < num_kb; ++kb) {
           uint8_t* swr = smem + kb * Cfg::NOPS * Cfg::W_BYTES;
-          tma_load_2d(swr, &tw_hi, w_bar, kb * BK, 0);
-          if (SPLIT == 3) tma_load_2d(swr + Cfg::W_BYTES, &tw_lo, w_bar, kb * BK, 0);
+          tma_load_2d(swr, &tw_hi, w_bar, kb * BK, wn0);
+          if (SPLIT == 3) tma_load_2d(swr + Cfg::W_BYTES, &tw_lo, w_bar, kb * BK, wn0);
         }
       }
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m0 = (t / tiles_n) * BM;     // n-fastest: the CTAs sharing an A tile run back to back (L2)
         const int n0 = (t % tiles_n) * BN;
+        if (WRES && e.l2_prefetch) {
+          // Tall streaming GEMMs: with the weights resident only 64 KB of ring is left, i.e. <= 48 KB in flight
+          // per SM -- not enough to cover HBM latency at 44 B/ns per SM (measured 3.9 of 6.5 TB/s).  Ask L2 for
+          // the A tile this CTA will need `l2_prefetch` tiles from now; the ring then only has to cover L2 latency.
+          const int tp = t + e.l2_prefetch * gridDim.x;
+          if (tp < num_tiles && (tp % tiles_n) == 0 || (tp < num_tiles && tiles_n == 1)) {
+            const int mp = (tp / tiles_n) * BM;
+            for (int kb = 0; kb < num_kb; ++kb) {
+              tma_prefetch_l2_2d(&ta_hi, kb * BK, mp);
+              if (SPLIT == 3) tma_prefetch_l2_2d(&ta_lo, kb * BK, mp);
+            }
+          }
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
@@ -369,7 +386,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
             }
           }
           tc_fence_before();
-          mbar_arrive(&tempty_bar[buf]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
           continue;
         }
         mbar_wait(&tfull_bar[buf], bphase);
@@ -510,7 +528,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
         }
         // accumulator drained: release the TMEM buffer before the normalise + store phase
         tc_fence_before();
-        mbar_arrive(&tempty_bar[buf]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
         float* ex_sum = epi_smem;            // [2][128]
         float* ex_sq = epi_smem + 256;       // [2][128]
         const int row_in_tile = q * 32 + lane;
@@ -640,7 +659,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
     }
   }
   tc_fence_before();
@@ -756,7 +776,8 @@ static int launch_tc(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st)
   }
   const int tiles_m = (a->M + BM - 1) / BM;
   const int tiles_n = (a->N + BN - 1) / BN;
-  const int grid = min(tiles_m * tiles_n, num_sms());
+  int grid = min(tiles_m * tiles_n, num_sms());
+  if (WRES) grid = (grid / tiles_n) * tiles_n;      // fixed n index per CTA (see the producer)
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, e, a->K, tiles_m, tiles_n);
   return check_launch("gemm_tc_kernel");
 }
@@ -796,6 +817,8 @@ extern "C" int csam_gemm(const csam_gemm_args* a, void* stream) {
     e.direct = e.vec_ok && (a->N & 15) == 0 && al32(a->residual) && (a->ldr & 7) == 0 && al32(a->out_f32) &&
                (a->ldo & 7) == 0 && al32(a->out_hi) && al32(a->out_lo) && (a->ldh & 15) == 0;
     if (const char* env = getenv("CSAM_GEMM_DIRECT")) e.direct = e.direct && atoi(env) != 0;
+    static const int l2pf = getenv("CSAM_GEMM_L2PF") ? atoi(getenv("CSAM_GEMM_L2PF")) : 2;
+    e.l2_prefetch = l2pf;
   }
 
   if (a->impl == CSAM_GEMM_SIMT) {
@@ -815,7 +838,8 @@ extern "C" int csam_gemm(const csam_gemm_args* a, void* stream) {
   auto wres_ok = [&](int bn) {
     const long long kb = (a->K + BK - 1) / BK;
     const long long wbytes = kb * (split ? 2 : 1) * (long long)bn * BK * 2;
-    return a->N <= bn && wbytes <= WRES_MAX_BYTES && a->M >= 8 * BM * 148;
+    const int tn = (a->N + bn - 1) / bn;
+    return tn <= 4 && wbytes <= WRES_MAX_BYTES && a->M >= 8 * BM * 148;   // wbytes: one n-tile's slice of W
   };
   if (a->epi == CSAM_EPI_LN) {
     CSAM_REQUIRE(a->N == 256 && a->gamma && a->beta && !a->row_map && !a->row_scale && !a->col_scale && a->act == 0,

@@ -243,6 +243,22 @@ class MaskDecoderEngine:
         self.pe_k = [pe_proj(f"{t}.layers.{i}.cross_attn_token_to_image.k_proj") for i in range(2)]
         self.pe_qi = [pe_proj(f"{t}.layers.{i}.cross_attn_image_to_token.q_proj") for i in range(2)]
         self.pe_kf = pe_proj(f"{t}.final_attn_token_to_image.k_proj")
+        # Projections that read the same keys are one GEMM: layer 1 needs k, v (token->image) and q (image->
+        # token) of keys1, the final attention k, v of keys2.  One pass over the [P*4096, 256] operand
+        # instead of three / two; the attention kernels read column slices of the fused output.
+        # Row-periodic residual = (pe_k | b_v | pe_qi) resp. (pe_kf | b_v).
+        def cat_w(names):
+            return H16.from_f32(torch.cat([sd[n + ".weight"].detach().float() for n in names], 0).contiguous().to(dev), split)
+
+        L1 = f"{t}.layers.1"
+        fin = f"{t}.final_attn_token_to_image"
+        self.w_kvq1 = cat_w([L1 + ".cross_attn_token_to_image.k_proj", L1 + ".cross_attn_token_to_image.v_proj",
+                             L1 + ".cross_attn_image_to_token.q_proj"])
+        bv1 = sd[L1 + ".cross_attn_token_to_image.v_proj.bias"].detach().float().to(dev)
+        self.res_kvq1 = torch.cat([self.pe_k[1], bv1[None, :].expand(4096, -1), self.pe_qi[1]], 1).contiguous()
+        self.w_kvf = cat_w([fin + ".k_proj", fin + ".v_proj"])
+        bvf = sd[fin + ".v_proj.bias"].detach().float().to(dev)
+        self.res_kvf = torch.cat([self.pe_kf, bvf[None, :].expand(4096, -1)], 1).contiguous()
         # ConvTranspose2d(k2,s2) as GEMM: N index = (dy*2+dx)*C_out + o   (mask_decoder.py:56-62)
         w1 = sd[f"{m}.output_upscaling.0.weight"].detach().float().permute(2, 3, 1, 0).reshape(256, 256)
         b1 = sd[f"{m}.output_upscaling.0.bias"].detach().float().repeat(4)
@@ -323,9 +339,9 @@ class MaskDecoderEngine:
             if li == 0:
                 kc, vc = I["k0"], I["v0"]
             else:
-                kc, _ = ops.gemm(keys_h, ta.k.w, residual=self.pe_k[li], res_mod=4096, want_f32=True)
-                vc, _ = ta.v(keys_h, want_f32=True)
-                kc, vc = kc.view(P, 4096, 128), vc.view(P, 4096, 128)
+                kvq, _ = ops.gemm(keys_h, self.w_kvq1, residual=self.res_kvq1, res_mod=4096, want_f32=True)
+                kvq = kvq.view(P, 4096, 384)
+                kc, vc, qi1 = kvq[:, :, 0:128], kvq[:, :, 128:256], kvq[:, :, 256:384]
             _, a = ops.attn_few_queries(qc.view(P, 7, 128), kc, vc, P, 7, 4096, 8, 16, want_h16=True, split=split)
             pre, _ = ta.o(a.view(T, 128), residual=queries, want_f32=True)
             queries, q_h, _ = ln(pre, Lr["n2"][0], Lr["n2"][1], 1e-5, want_f32=True, want_h16=True, split=split)
@@ -338,11 +354,7 @@ class MaskDecoderEngine:
             ia = Lr["i2t"]
             kt, _ = ia.k(q_pe_h, want_f32=True)
             vt, _ = ia.v(q_h, want_f32=True)
-            if li == 0:
-                qi = I["q0"]
-            else:
-                qi, _ = ops.gemm(keys_h, ia.q.w, residual=self.pe_qi[li], res_mod=4096, want_f32=True)
-                qi = qi.view(P, 4096, 128)
+            qi = I["q0"] if li == 0 else qi1
             _, a = ops.attn_few_keys(qi, kt.view(P, 7, 128), vt.view(P, 7, 128), P, 4096, 7, 8, 16,
                                      want_h16=True, split=split)
             # out_proj + residual + norm4 in one GEMM epilogue.  The new keys are stored once, as an h16 pair:
@@ -364,13 +376,13 @@ class MaskDecoderEngine:
         # final token -> image attention (transformer.py:104-112)
         fa = self.final
         qc, _ = fa.q(q_pe_h, want_f32=True)
-        kc, _ = ops.gemm(keys_h, fa.k.w, residual=self.pe_kf, res_mod=4096, want_f32=True)
-        vc, _ = fa.v(keys_h, want_f32=True)
-        _, a = ops.attn_few_queries(qc.view(P, 7, 128), kc.view(P, 4096, 128), vc.view(P, 4096, 128), P, 7, 4096, 8, 16,
-                                    want_h16=True, split=split)
+        kv, _ = ops.gemm(keys_h, self.w_kvf, residual=self.res_kvf, res_mod=4096, want_f32=True)
+        kv = kv.view(P, 4096, 256)
+        kc, vc = kv[:, :, 0:128], kv[:, :, 128:256]
+        _, a = ops.attn_few_queries(qc.view(P, 7, 128), kc, vc, P, 7, 4096, 8, 16, want_h16=True, split=split)
         pre, _ = fa.o(a.view(T, 128), residual=queries, want_f32=True)
         hs, hs_h, _ = ln(pre, self.nf[0], self.nf[1], 1e-5, want_f32=True, want_h16=True, split=split)
-        del kc, vc, keys_f32, pre
+        del kc, vc, kv, keys_f32, pre
         hs2 = hs_h.view(P, 7 * 256)
 
         def cols(h: H16, c0: int, c1: int) -> H16:

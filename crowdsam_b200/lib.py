@@ -54,7 +54,8 @@ class AttnArgs(C.Structure):
 class DecAttnArgs(C.Structure):
     _fields_ = [("q", vp), ("Bq", ci), ("k", vp), ("v", vp), ("Bk", ci),
                 ("B", ci), ("nq", ci), ("nk", ci), ("heads", ci), ("hd", ci),
-                ("out_f32", vp), ("out_hi", vp), ("out_lo", vp)]
+                ("out_f32", vp), ("out_hi", vp), ("out_lo", vp),
+                ("ldq", ci), ("ldk", ci), ("ldv", ci)]
 
 
 class PostArgs(C.Structure):
@@ -124,7 +125,7 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.csam_abi_version() != 4:
+    if lib.csam_abi_version() != 5:
         raise RuntimeError("libcsam_sm100.so ABI version mismatch")
     _lib = lib
     return lib

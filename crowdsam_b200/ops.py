@@ -285,6 +285,14 @@ def _dec_attn(fn_name, q, k, v, B, nq, nk, heads, hd, want_f32, want_h16, split)
     a.q, a.Bq = _p(q), (1 if q.shape[0] == 1 and B > 1 else B)
     a.k, a.v, a.Bk = _p(k), _p(v), (1 if k.shape[0] == 1 and B > 1 else B)
     a.B, a.nq, a.nk, a.heads, a.hd = B, nq, nk, heads, hd
+
+    def ld(t, n):      # row stride of a [B, n, C] view (e.g. a column slice of a fused projection output)
+        assert t.dim() == 3 and t.shape[1] == n and t.shape[2] == Cc and t.stride(2) == 1, "q/k/v must be [B, n, C] views"
+        s = t.stride(1) if n > 1 else Cc
+        assert t.shape[0] == 1 or t.stride(0) == n * s, "batch stride must equal n * row stride"
+        return 0 if s == Cc else s
+
+    a.ldq, a.ldk, a.ldv = ld(q, nq), ld(k, nk), ld(v, nk)
     of = torch.empty((B, nq, Cc), dtype=torch.float32, device=dev) if want_f32 else None
     oh = H16.empty((B, nq, Cc), split, dev) if want_h16 else None
     a.out_f32 = _p(of)

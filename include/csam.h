@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSAM_ABI_VERSION 4
+#define CSAM_ABI_VERSION 5
 #if defined(__GNUC__)
 #define CSAM_API __attribute__((visibility("default")))
 #else
@@ -172,6 +172,8 @@ typedef struct {
   const float* q; int Bq; const float* k; const float* v; int Bk;
   int B, nq, nk, heads, hd;
   float* out_f32; void* out_hi; void* out_lo;
+  int ldq, ldk, ldv;   /* row strides in floats (multiples of 4); 0 = dense rows of C floats.  Lets the attention
+                          read column slices of one fused projection output [rows, (k|v|q)]. */
 } csam_dec_attn_args;
 CSAM_API int csam_attn_few_keys(const csam_dec_attn_args* a, void* stream);
 CSAM_API int csam_attn_few_queries(const csam_dec_attn_args* a, void* stream);

@@ -20,7 +20,10 @@ def run(name, groups, tokens, heads, S, split):
     fl = 4.0 * groups * heads * tokens * tokens * 64
     print(f"{name:8s} split={split} {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s (algorithmic)")
 
+only = sys.argv[1] if len(sys.argv) > 1 else None
 for split in (True, False):
     run("dino", 1, 5330, 16, 0, split)
+    if only == "dino":
+        continue
     run("global", 1, 4096, 16, 64, split)
     run("window", 25, 196, 16, 14, split)

@@ -121,6 +121,73 @@ def test_gemm_b_mn_major(split):
     assert _rel(out, ref) < 2e-5
 
 
+def test_gemm_resident_weights_partitioned_n():
+    """Tall GEMMs (M >= 8*128*148 rows) keep the weights resident in shared memory; with N = 384 each CTA keeps
+    the slice of its own n-tile.  Fused k|v|q projection of the decoder + strided attention inputs."""
+    o = ops()
+    g = torch.Generator().manual_seed(31)
+    M, N, K = 160000 + 77, 384, 256
+    a = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) * 0.1).to(DEV)
+    res = torch.randn(4096, N, generator=g).to(DEV)
+    ah, wh = o.H16.from_f32(a, True), o.H16.from_f32(w, True)
+    ref = ah.float().double() @ wh.float().double().T + res.double()[torch.arange(M, device=DEV) % 4096]
+    out, _ = o.gemm(ah, wh, residual=res, res_mod=4096, want_f32=True)
+    assert _rel(out, ref) < 1e-5, _rel(out, ref)
+    # LN-256 epilogue with an h16-pair residual, resident weights
+    K2 = 128
+    a2 = o.H16.from_f32(torch.randn(M, K2, generator=g).to(DEV), True)
+    w2 = o.H16.from_f32((torch.randn(256, K2, generator=g) * 0.2).to(DEV), True)
+    r2 = o.H16.from_f32(torch.randn(M, 256, generator=g).to(DEV), True)
+    bias, gam, bet = (torch.randn(256, generator=g).to(DEV) for _ in range(3))
+    x = a2.float().double() @ w2.float().double().T + bias.double() + r2.float().double()
+    ref2 = torch.nn.functional.layer_norm(x, (256,), gam.double(), bet.double(), 1e-5)
+    outh = o.H16.empty((M, 256), True, DEV)
+    o.gemm(a2, w2, bias=bias, epi=1, gamma=gam, beta=bet, eps=1e-5, out_h16=outh, residual_h16=r2)
+    assert _rel(outh.float(), ref2) < 1e-5, _rel(outh.float(), ref2)
+    # in place: the output pair aliases the residual pair (every thread reads its row slice before writing it)
+    o.gemm(a2, w2, bias=bias, epi=1, gamma=gam, beta=bet, eps=1e-5, out_h16=r2, residual_h16=r2)
+    assert _rel(r2.float(), ref2) < 1e-5
+
+
+def test_decoder_attentions_strided_slices():
+    """q/k/v given as column slices of one fused projection output (row stride 384 / 256 floats)."""
+    o = ops()
+    g = torch.Generator().manual_seed(33)
+    P = 3
+    kvq = torch.randn(P, 4096, 384, generator=g).to(DEV)
+    qt = torch.randn(P, 7, 128, generator=g).to(DEV)
+    kt, vt = torch.randn(P, 7, 128, generator=g).to(DEV), torch.randn(P, 7, 128, generator=g).to(DEV)
+
+    def ref(q, k, v):
+        B, nq, _ = q.shape
+        qh, kh, vh = (t.double().view(B, -1, 8, 16).transpose(1, 2) for t in (q, k, v))
+        att = torch.softmax(qh @ kh.transpose(-1, -2) / 4.0, dim=-1)
+        return (att @ vh).transpose(1, 2).reshape(B, nq, 128)
+
+    kc, vc, qi = kvq[:, :, 0:128], kvq[:, :, 128:256], kvq[:, :, 256:384]
+    f, _ = o.attn_few_queries(qt, kc, vc, P, 7, 4096, 8, 16, want_f32=True)
+    assert _rel(f, ref(qt, kc, vc)) < 1e-5
+    f, _ = o.attn_few_keys(qi, kt, vt, P, 4096, 7, 8, 16, want_f32=True)
+    assert _rel(f, ref(qi, kt, vt)) < 1e-5
+    # generic kernels (heads x hd other than 8 x 16) with strides
+    kv2 = torch.randn(P, 50, 192, generator=g).to(DEV)
+    q2 = torch.randn(P, 5, 64, generator=g).to(DEV)
+
+    def ref2(q, k, v):
+        B, nq, _ = q.shape
+        qh, kh, vh = (t.double().view(B, -1, 2, 32).transpose(1, 2) for t in (q, k, v))
+        att = torch.softmax(qh @ kh.transpose(-1, -2) / 32 ** 0.5, dim=-1)
+        return (att @ vh).transpose(1, 2).reshape(B, nq, 64)
+
+    f, _ = o.attn_few_queries(q2, kv2[:, :, 0:64], kv2[:, :, 128:192], P, 5, 50, 2, 32, want_f32=True)
+    assert _rel(f, ref2(q2, kv2[:, :, 0:64], kv2[:, :, 128:192])) < 1e-5
+    q3 = kv2[:, :, 64:128]
+    k3, v3 = torch.randn(P, 6, 64, generator=g).to(DEV), torch.randn(P, 6, 64, generator=g).to(DEV)
+    f, _ = o.attn_few_keys(q3, k3, v3, P, 50, 6, 2, 32, want_f32=True)
+    assert _rel(f, ref2(q3, k3, v3)) < 1e-5
+
+
 def test_gemm_strided_views():
     o = ops()
     g = torch.Generator().manual_seed(4)
@@ -260,6 +327,21 @@ def test_vit_attention_plain_ragged(tokens, impl):
     assert _rel(out.float(), ref) < 1e-5, _rel(out.float(), ref)
     out = o.vit_attention(qh, 1, tokens, heads, hd, hd ** -0.5, impl=impl, p_split=0)
     assert _rel(out.float(), ref) < 5e-4, _rel(out.float(), ref)
+
+
+@pytest.mark.parametrize("split", [True, False])
+@pytest.mark.parametrize("groups,tokens", [(3, 300), (2, 129), (2, 640)])
+def test_vit_attention_plain_groups_two_query_tiles(groups, tokens, split):
+    """bias-free attention over several groups: the two-query-tile CTA variant (tokens > 128), including a
+    second tile that is partly or wholly past the end of its group (rows of the NEXT group are loaded, unused)."""
+    o = ops()
+    g = torch.Generator().manual_seed(21)
+    heads, hd = 2, 64
+    qkv = torch.randn(groups * tokens, 3 * heads * hd, generator=g) * 1.5
+    qh = _h16(qkv, split)
+    ref = _attn_ref(qh.float().cpu(), groups, tokens, heads, hd)
+    out = o.vit_attention(qh, groups, tokens, heads, hd, hd ** -0.5, impl=0, p_split=0)
+    assert _rel(out.float(), ref) < (5e-4 if split else 2e-3), _rel(out.float(), ref)
 
 
 def test_decoder_attentions():
