@@ -2,13 +2,15 @@
 //
 // One CTA = 128 queries of one (group, head); keys stream through in tiles of 64.
 //   warp 0      TMA producer   Q once, then K/V tiles into a 3-stage ring (128B-swizzled boxes)
-//   warp 1      MMA issuer     S = Q K^T  (M128 N64 K64, both operands K-major)  -> TMEM S[2]
-//                              O_j = P V  (M128 N64 K64, V is the MN-major B operand) -> TMEM O[2]
+//   warp 3      MMA issuer #1  S = Q K^T  (M128 N64 K64, both operands K-major)  -> TMEM S[2]
+//   warp 1      MMA issuer #2  O += P V   (M128 N64 K64, V is the MN-major B operand) -> TMEM O
 //   warp 2      TMEM allocator
-//   warps 4..7  softmax        one thread per query row: tcgen05.ld S, scale + decomposed rel-pos
-//                              bias, online softmax in fp32, P written to shared memory as an fp16
-//                              hi/lo pair in the UMMA K-major swizzled layout, O accumulated in
-//                              registers with the usual rescale.
+//   warps 4..   softmax        one warpgroup per query tile (NQ = 1 or 2 tiles per CTA share the K/V ring);
+//                              one thread per query row: tcgen05.ld S, scale + decomposed rel-pos bias, online
+//                              softmax in fp32, P written to shared memory as fp16 (optionally hi/lo) in the UMMA
+//                              K-major swizzled layout.  O accumulates in TMEM across key tiles; the row maximum
+//                              may lag by 2^8 and O is rescaled in place (tcgen05.ld -> * alpha -> tcgen05.st) only
+//                              when a row really outgrows it.
 // S(j+1) is issued before softmax(j) finishes (two S buffers), so the tensor pipe overlaps the
 // exponentials.  With the hi/lo split every product is 3 MMAs (fp32-level accuracy).
 // Reference: image_encoder.py:224-240,325-361; dinov2/layers/attention.py:56-69.
@@ -30,6 +32,10 @@ template <int SPLIT, int BIAS, bool PLO, int NQ>
 struct AttnCfg {
   static constexpr int NOPS = (SPLIT == 3) ? 2 : 1;
   static constexpr int PNOPS = (SPLIT == 3 && PLO) ? 2 : 1;
+  // P buffers per query tile.  With two query tiles per CTA the probabilities are single-buffered (the
+  // softmax warpgroup folds O(j-1) into its accumulator -- which proves P V(j-1) has retired -- BEFORE it
+  // stores P(j)), which leaves room for a 4-stage K/V ring next to two Q tiles.
+  static constexpr int PBUF = (NQ == 2) ? 1 : 2;
   static constexpr int THREADS = 128 + 128 * NQ;
   static constexpr int Q_BYTES = AT_BM * AT_HD * 2;          // 16 KB per operand half per query tile
   static constexpr int KV_TILE = AT_BN * AT_HD * 2;          // 8 KB
@@ -38,14 +44,14 @@ struct AttnCfg {
   // K/V ring depth = whatever shared memory is left (<= 8).  A stage is released when P V of its tile has
   // retired and S of the NEXT tile is issued one tile early, so a ring of n stages gives the TMA only n - 2
   // tile times to land: with 3 stages the kernel ran at TMA latency (0.92 us per key tile with all math removed).
-  static constexpr int FIXED_BYTES = NQ * NOPS * Q_BYTES + NQ * 2 * PNOPS * P_BYTES +
+  static constexpr int FIXED_BYTES = NQ * NOPS * Q_BYTES + NQ * PBUF * PNOPS * P_BYTES +
                                      (BIAS == 1 ? NQ * AT_BM * AT_REL_LD * 4 : 0) + 512 + 1024;
   static constexpr int STAGES_FIT = (227 * 1024 - FIXED_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static_assert(STAGES >= 2, "attention K/V ring");
   static constexpr int OFF_KV = NQ * NOPS * Q_BYTES;
   static constexpr int OFF_P = OFF_KV + STAGES * STAGE_BYTES;
-  static constexpr int OFF_REL = OFF_P + NQ * 2 * PNOPS * P_BYTES;
+  static constexpr int OFF_REL = OFF_P + NQ * PBUF * PNOPS * P_BYTES;
   static constexpr int OFF_BAR = OFF_REL + (BIAS == 1 ? NQ * AT_BM * AT_REL_LD * 4 : 0);
   static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
   static constexpr int TMEM_COLS = 256 * NQ;                 // per query tile: S0 S1 O0 O1, 64 columns each
@@ -55,7 +61,7 @@ struct AttnCfg {
 struct AttnBars {
   uint64_t q_full;
   uint64_t kv_full[8], kv_empty[8];
-  uint64_t s_full[2][2], s_empty[2][2], p_full[2][2], o_full[2][2], o_empty[2][2];   // [query tile][buffer]
+  uint64_t s_full[2][2], s_empty[2][2], p_full[2][2], pv_done[2][2];   // [query tile][key tile parity]
   uint32_t tmem_slot;
 };
 
@@ -65,13 +71,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// The running maximum is allowed to lag the true row maximum by up to 2^AT_TAU (probabilities stay <= 256, well
+// inside fp16): O then accumulates IN TMEM across key tiles and is only read back when a row's maximum really
+// grows -- a handful of times per row instead of once per key tile.  TMEM reads were the bound of the previous
+// version (S and O read back every tile: 64 KB per key tile per SM at 64 B/clk = 1024 of ~2400 cycles).
+constexpr float AT_TAU = 8.f;
+
 // BIAS: 0 none, 1 window (S = 14, table in shared memory), 2 global (S = 64 == key tile, registers)
 template <int SPLIT, int BIAS, bool PLO, int NQ>
 __global__ void __launch_bounds__(128 + 128 * NQ, 1)
 vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_constant__ CUtensorMap t_lo,
-                        csam_attn_args a, const float* __restrict__ rel, int dbg) {
+                        csam_attn_args a, const float* __restrict__ rel) {
   using Cfg = AttnCfg<SPLIT, BIAS, PLO, NQ>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int PBUF = Cfg::PBUF;
   // Dynamic shared memory is the only shared allocation of this kernel, so it starts at the (1024-byte
   // aligned) base of the CTA's window; keeping `smem` a plain __shared__ array (no integer round-trip) lets
   // the compiler emit LDS/STS instead of generic LD/ST for every staging access.
@@ -96,11 +109,10 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
     for (int t = 0; t < NQ; ++t)
       for (int b = 0; b < 2; ++b) {
         // softmax-side arrivals are one elected lane per warp (4 per warpgroup): 128 threads arriving on one
-        // mbarrier serialise as shared-memory atomics -- three of those per key tile cost 0.9 us, more than
-        // the math (measured: removing ALL softmax math did not change the kernel time)
+        // mbarrier serialise as shared-memory atomics (measured 0.3 us per barrier)
         mbar_init(&bars->s_full[t][b], 1); mbar_init(&bars->s_empty[t][b], 4);
         mbar_init(&bars->p_full[t][b], 4);
-        mbar_init(&bars->o_full[t][b], 1); mbar_init(&bars->o_empty[t][b], 4);
+        mbar_init(&bars->pv_done[t][b], 1);
       }
     fence_barrier_init();
   }
@@ -108,7 +120,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = bars->tmem_slot;   // per query tile t: S0 [0,64) S1 [64,128) O0 [128,192) O1 [192,256) + 256 t
+  const uint32_t tmem_base = bars->tmem_slot;   // per query tile t: S0 [0,64) S1 [64,128) O [128,192), + 256 t
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -137,79 +149,77 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ MMA issuer #1: S = Q K^T
+    // Two issuing threads (this one and warp 1 for P V): a narrow MMA (N = 64) executes in 32 cycles, less than
+    // one thread needs to issue it, so a single issuer held the tensor pipe back (x3: 20 MMAs per key tile).
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_f16(AT_BM, AT_BN, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(AT_BM, AT_HD, 0, 1);
-      auto issue_s = [&](int j) {          // S(j) of every query tile of this CTA
+      mbar_wait(&bars->q_full, 0);
+      tc_fence_after();
+      uint32_t qd[NQ];
+#pragma unroll
+      for (int t = 0; t < NQ; ++t) qd[t] = umma_desc_lo(smem_u32(smem + t * Cfg::NOPS * Cfg::Q_BYTES), 16);
+      for (int j = 0; j < n_tiles; ++j) {
         const int st = j % STAGES;
         mbar_wait(&bars->kv_full[st], (j / STAGES) & 1);
-        const uint32_t sk = smem_u32(smem + Cfg::OFF_KV + st * Cfg::STAGE_BYTES);
+        const uint32_t kd = umma_desc_lo(smem_u32(smem + Cfg::OFF_KV + st * Cfg::STAGE_BYTES), 16);
 #pragma unroll
         for (int t = 0; t < NQ; ++t) {
           mbar_wait(&bars->s_empty[t][j & 1], ((j >> 1) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t sq = smem_u32(smem + t * Cfg::NOPS * Cfg::Q_BYTES);
           const uint32_t d = tmem_base + t * 256 + (j & 1) * AT_BN;
 #pragma unroll
-          for (int k = 0; k < ((dbg & 64) && j > 1 ? 0 : AT_HD / 16); ++k) {
-            const uint64_t q_hi = umma_desc_sw128(sq + k * 32, 16, 1024);
-            const uint64_t k_hi = umma_desc_sw128(sk + k * 32, 16, 1024);
-            umma_f16(d, q_hi, k_hi, idesc_s, k ? 1u : 0u);
+          for (int k = 0; k < AT_HD / 16; ++k) {
+            umma_f16_w(d, qd[t] + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
             if (SPLIT == 3) {
-              const uint64_t q_lo = umma_desc_sw128(sq + Cfg::Q_BYTES + k * 32, 16, 1024);
-              const uint64_t k_lo = umma_desc_sw128(sk + Cfg::KV_TILE + k * 32, 16, 1024);
-              umma_f16(d, q_lo, k_hi, idesc_s, 1u);
-              umma_f16(d, q_hi, k_lo, idesc_s, 1u);
+              umma_f16_w(d, qd[t] + (Cfg::Q_BYTES >> 4) + 2 * k, kd + 2 * k, idesc_s, 1u);
+              umma_f16_w(d, qd[t] + 2 * k, kd + (Cfg::KV_TILE >> 4) + 2 * k, idesc_s, 1u);
             }
           }
           umma_commit(&bars->s_full[t][j & 1]);
         }
-      };
-      mbar_wait(&bars->q_full, 0);
-      tc_fence_after();
-      issue_s(0);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer #2: O += P V
+    if (lane == 0) {
+      constexpr uint32_t idesc_pv = umma_idesc_f16(AT_BM, AT_HD, 0, 1);
       for (int j = 0; j < n_tiles; ++j) {
         const int b = j & 1;
         const uint32_t use = (j >> 1) & 1;
-        if (j + 1 < n_tiles) issue_s(j + 1);
         const int st = j % STAGES;
-        const uint32_t sv = smem_u32(smem + Cfg::OFF_KV + st * Cfg::STAGE_BYTES + Cfg::NOPS * Cfg::KV_TILE);
+        const uint32_t vd = umma_desc_lo(smem_u32(smem + Cfg::OFF_KV + st * Cfg::STAGE_BYTES + Cfg::NOPS * Cfg::KV_TILE), 8192);
 #pragma unroll
         for (int t = 0; t < NQ; ++t) {
-          mbar_wait(&bars->p_full[t][b], use);
-          mbar_wait(&bars->o_empty[t][b], use ^ 1);
+          mbar_wait(&bars->p_full[t][b], use);      // P(j) stored (so S(j), K(j), V(j) have landed), any rescale of O finished
           tc_fence_after();
-          const uint32_t sp = smem_u32(smem + Cfg::OFF_P + (t * 2 + b) * Cfg::PNOPS * Cfg::P_BYTES);
-          const uint32_t d = tmem_base + t * 256 + 128 + b * AT_HD;
+          const uint32_t pd = umma_desc_lo(smem_u32(smem + Cfg::OFF_P + (t * PBUF + (PBUF == 2 ? b : 0)) * Cfg::PNOPS * Cfg::P_BYTES), 16);
+          const uint32_t d = tmem_base + t * 256 + 128;      // O accumulates across key tiles
 #pragma unroll
-          for (int k = 0; k < ((dbg & 32) && j > 1 ? 0 : AT_BN / 16); ++k) {
-            const uint64_t p_hi = umma_desc_sw128(sp + k * 32, 16, 1024);
-            const uint64_t v_hi = umma_desc_sw128(sv + k * 2048, 8192, 1024);
-            umma_f16(d, p_hi, v_hi, idesc_pv, k ? 1u : 0u);
+          for (int k = 0; k < AT_BN / 16; ++k) {
+            umma_f16_w(d, pd + 2 * k, vd + 128 * k, idesc_pv, (j | k) ? 1u : 0u);
             if (SPLIT == 3) {
-              const uint64_t v_lo = umma_desc_sw128(sv + Cfg::KV_TILE + k * 2048, 8192, 1024);
-              umma_f16(d, p_hi, v_lo, idesc_pv, 1u);
-              if (PLO) {
-                const uint64_t p_lo = umma_desc_sw128(sp + Cfg::P_BYTES + k * 32, 16, 1024);
-                umma_f16(d, p_lo, v_hi, idesc_pv, 1u);
-              }
+              umma_f16_w(d, pd + 2 * k, vd + (Cfg::KV_TILE >> 4) + 128 * k, idesc_pv, 1u);
+              if (PLO) umma_f16_w(d, pd + (Cfg::P_BYTES >> 4) + 2 * k, vd + 128 * k, idesc_pv, 1u);
             }
           }
-          umma_commit(&bars->o_full[t][b]);
+          umma_commit(&bars->pv_done[t][b]);
         }
+        // K(j) was consumed by S(j), which completed before softmax(j) could publish P(j): this thread's commit
+        // (tracking only its own P V MMAs) therefore also covers the K half of the stage
         umma_commit(&bars->kv_empty[st]);
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ softmax / accumulate
+    // ------------------------------------------------------------------ softmax
     const int qt = (warp - 4) >> 2;                // query tile of this warpgroup
     const int wq = (warp - 4) & 3;                 // TMEM lane quadrant == warp % 4
     const int r = wq * 32 + lane;                  // query row in the tile == TMEM lane
     const int q = q0 + qt * AT_BM + r;
     const int qc = min(q, a.tokens - 1);
     const uint32_t lane_addr = tmem_base + qt * 256 + ((uint32_t)(wq * 32) << 16);
+    const uint32_t o_addr = lane_addr + 128;
     constexpr float LOG2E = 1.4426950408889634f;
     const float scale2 = a.scale * LOG2E;
     float relw[BIAS == 2 ? 64 : 1];
@@ -223,25 +233,10 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
     if (BIAS == 1) {
       for (int i = 0; i < 28; ++i) rel_r[i] = relq[i] * LOG2E;
     }
-    float acc[AT_HD];
-#pragma unroll
-    for (int d = 0; d < AT_HD; ++d) acc[d] = 0.f;
-    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-
-    auto accumulate_o = [&](int j, float alpha) {
-      const int b = j & 1;
-      mbar_wait(&bars->o_full[qt][b], (j >> 1) & 1);
+    float m = -INFINITY, l = 0.f;      // m: the (possibly stale) maximum the probabilities are taken against
+    auto wait_pv = [&](int j) {        // P V(j) retired: O holds tiles 0..j, the P buffer of tile j is free
+      mbar_wait(&bars->pv_done[qt][j & 1], (j >> 1) & 1);
       tc_fence_after();
-      if (dbg & 4) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&bars->o_empty[qt][b]); acc[0] += alpha; return; }
-      uint32_t o[64];
-      tmem_ld32(lane_addr + 128 + b * AT_HD, o);
-      tmem_ld32(lane_addr + 128 + b * AT_HD + 32, o + 32);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->o_empty[qt][b]);
-#pragma unroll
-      for (int d = 0; d < AT_HD; ++d) acc[d] = fmaf(acc[d], alpha, __uint_as_float(o[d]));
     };
 
     for (int j = 0; j < n_tiles; ++j) {
@@ -249,14 +244,9 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
       mbar_wait(&bars->s_full[qt][b], (j >> 1) & 1);
       tc_fence_after();
       uint32_t raw[64];
-      if (dbg & 8) {
-#pragma unroll
-        for (int c = 0; c < 64; ++c) raw[c] = __float_as_uint(0.01f * (float)(c + j));
-      } else {
-        tmem_ld32(lane_addr + b * AT_BN, raw);
-        tmem_ld32(lane_addr + b * AT_BN + 32, raw + 32);
-        tmem_ld_wait();
-      }
+      tmem_ld32(lane_addr + b * AT_BN, raw);
+      tmem_ld32(lane_addr + b * AT_BN + 32, raw + 32);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->s_empty[qt][b]);
@@ -288,54 +278,78 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
 #pragma unroll
       for (int c = 0; c < 64; ++c) tmax = fmaxf(tmax, s[c]);
       if (BIAS == 0) tmax *= scale2;                 // scale2 > 0: max commutes with the scaling
-      const float m_new = fmaxf(m, tmax);
-      const float alpha = ex2_approx(m - m_new);
-      float psum = 0.f;
-      uint8_t* pb = smem + Cfg::OFF_P + (qt * 2 + b) * Cfg::PNOPS * Cfg::P_BYTES + r * 128;
+      if (j == 0) {
+        m = tmax;
+      } else if (__any_sync(0xffffffffu, tmax > m + AT_TAU)) {
+        // some row of this warp outgrew its stale maximum: every row of the warp moves to its true maximum and
+        // rescales its O row in TMEM (tcgen05.ld / .st are warp-wide).  O must hold all of tiles 0..j-1 first.
+        const float m_new = fmaxf(m, tmax);
+        const float alpha = ex2_approx(m - m_new);
+        wait_pv(j - 1);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        float pv[8];
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t o[32];
+          tmem_ld32(o_addr + hh * 32, o);
+          tmem_ld_wait();
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          pv[t] = (BIAS == 0) ? fmaf(s[u * 8 + t], scale2, -m_new) : s[u * 8 + t] - m_new;
-          if (!(dbg & 1)) pv[t] = ex2_approx(pv[t]);
-          psum += pv[t];
+          for (int d = 0; d < 32; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * alpha);
+          tmem_st32(o_addr + hh * 32, o);
         }
-        __align__(16) __half2 hi2[4];
+        tmem_st_wait();
+        l *= alpha;
+        m = m_new;
+      }
+      float psum = 0.f;
+      uint32_t ph[32];
+      uint32_t pl[(SPLIT == 3 && PLO) ? 32 : 1];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) hi2[t] = __floats2half2_rn(pv[2 * t], pv[2 * t + 1]);   // one packed cvt per pair
-        const int off = (u ^ (r & 7)) << 4;
-        if (!(dbg & 2) || u == (j & 7)) *reinterpret_cast<uint4*>(pb + off) = *reinterpret_cast<const uint4*>(hi2);
+      for (int c = 0; c < 64; c += 2) {
+        float p0 = (BIAS == 0) ? fmaf(s[c], scale2, -m) : s[c] - m;
+        float p1 = (BIAS == 0) ? fmaf(s[c + 1], scale2, -m) : s[c + 1] - m;
+        p0 = ex2_approx(p0);
+        p1 = ex2_approx(p1);
+        psum += p0 + p1;
+        const __half2 h2 = __floats2half2_rn(p0, p1);   // one packed cvt per pair
+        ph[c >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
         if (SPLIT == 3 && PLO) {
-          __align__(16) __half2 lo2[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float2 hf = __half22float2(hi2[t]);
-            lo2[t] = __floats2half2_rn(pv[2 * t] - hf.x, pv[2 * t + 1] - hf.y);
-          }
-          *reinterpret_cast<uint4*>(pb + Cfg::P_BYTES + off) = *reinterpret_cast<const uint4*>(lo2);
+          const float2 hf = __half22float2(h2);
+          const __half2 l2 = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+          pl[c >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
         }
       }
-      l = fmaf(l, alpha, psum);
-      m = m_new;
+      l += psum;
+      if (j >= PBUF) wait_pv(j - PBUF);              // the P buffer about to be overwritten has been consumed
+      uint8_t* pb = smem + Cfg::OFF_P + (qt * PBUF + (PBUF == 2 ? b : 0)) * Cfg::PNOPS * Cfg::P_BYTES + r * 128;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int off = (u ^ (r & 7)) << 4;
+        *reinterpret_cast<uint4*>(pb + off) = make_uint4(ph[4 * u], ph[4 * u + 1], ph[4 * u + 2], ph[4 * u + 3]);
+        if (SPLIT == 3 && PLO)
+          *reinterpret_cast<uint4*>(pb + Cfg::P_BYTES + off) = make_uint4(pl[4 * u], pl[4 * u + 1], pl[4 * u + 2], pl[4 * u + 3]);
+      }
       fence_proxy_async();                 // generic-proxy writes of P -> visible to the tensor core
+      tc_fence_before();                   // orders this warp's tcgen05.st (rescale) before the issuer's MMA
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->p_full[qt][b]);
-      if (j > 0) accumulate_o(j - 1, alpha_prev);
-      alpha_prev = alpha;
     }
-    accumulate_o(n_tiles - 1, alpha_prev);
-    if (q < a.tokens) {
-      const float inv = 1.0f / l;
-      __half* ohi = static_cast<__half*>(a.out_hi);
-      __half* olo = static_cast<__half*>(a.out_lo);
-      const size_t oo = ((size_t)row_base + q) * a.ld_out + (size_t)h * AT_HD;
+    wait_pv(n_tiles - 1);
+    const float inv = 1.0f / l;
+    __half* ohi = static_cast<__half*>(a.out_hi);
+    __half* olo = static_cast<__half*>(a.out_lo);
+    const size_t oo = ((size_t)row_base + q) * a.ld_out + (size_t)h * AT_HD;
 #pragma unroll
-      for (int d = 0; d < AT_HD; d += 8) {
-        float v8[8];
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t o[32];
+      tmem_ld32(o_addr + hh * 32, o);
+      tmem_ld_wait();
+      if (q < a.tokens) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) v8[t] = acc[d + t] * inv;
-        store_pair8(ohi, olo, oo + d, v8);
+        for (int d = 0; d < 32; d += 8) {
+          float v8[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v8[t] = __uint_as_float(o[d + t]) * inv;
+          store_pair8(ohi, olo, oo + hh * 32 + d, v8);
+        }
       }
     }
   }
@@ -361,15 +375,19 @@ static int launch_attn_tc(const csam_attn_args* a, const float* rel, cudaStream_
     attr = true;
   }
   dim3 grid((a->tokens + AT_BM * NQ - 1) / (AT_BM * NQ), a->heads, a->groups);
-  static const int dbg = getenv("CSAM_ATTN_DBG") ? atoi(getenv("CSAM_ATTN_DBG")) : 0;   // timing experiments only
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(t_hi, t_lo, *a, rel, dbg);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(t_hi, t_lo, *a, rel);
   return check_launch("vit_attention_tc_kernel");
 }
 
-// two query tiles per CTA when there is more than one tile and the kernel variant fits the register file
-static bool use_nq2(const csam_attn_args* a) {
-  if (const char* env = getenv("CSAM_ATTN_NQ")) return atoi(env) == 2 && a->tokens > AT_BM;
-  return false;   // measured on B200 (DINOv2 shape): 723 us with two tiles vs 528 us with one -- see DESIGN.md section 7
+// Two query tiles per CTA (two softmax warpgroups sharing one K/V ring) when there is more than one tile.
+// One softmax warp per scheduler is latency-bound (~2400 cycles per key tile against 640 cycles of MMA); a second
+// warpgroup overlaps those chains.  CSAM_ATTN_NQ=1 forces the single-tile kernel (measurement only).
+static bool use_nq2(const csam_attn_args* a, int bias) {
+  static const int env = getenv("CSAM_ATTN_NQ") ? atoi(getenv("CSAM_ATTN_NQ")) : 0;
+  static const int env_win = getenv("CSAM_ATTN_WIN_NQ") ? atoi(getenv("CSAM_ATTN_WIN_NQ")) : 0;
+  if (a->tokens <= AT_BM) return false;
+  if (bias == 1) return env_win != 1;      // window blocks: 196 tokens = exactly the two query tiles of one CTA
+  return env != 1;
 }
 
 int vit_attention_tc(const csam_attn_args* a, cudaStream_t st) {
@@ -393,12 +411,12 @@ int vit_attention_tc(const csam_attn_args* a, cudaStream_t st) {
     return launch_attn_tc<3, 2, true, 1>(a, rel, st);
   }
   if (split) {
-    if (bias == 0) return use_nq2(a) ? launch_attn_tc<3, 0, false, 2>(a, rel, st) : launch_attn_tc<3, 0, false, 1>(a, rel, st);
-    if (bias == 1) return launch_attn_tc<3, 1, false, 1>(a, rel, st);
+    if (bias == 0) return use_nq2(a, 0) ? launch_attn_tc<3, 0, false, 2>(a, rel, st) : launch_attn_tc<3, 0, false, 1>(a, rel, st);
+    if (bias == 1) return use_nq2(a, 1) ? launch_attn_tc<3, 1, false, 2>(a, rel, st) : launch_attn_tc<3, 1, false, 1>(a, rel, st);
     return launch_attn_tc<3, 2, false, 1>(a, rel, st);
   }
-  if (bias == 0) return use_nq2(a) ? launch_attn_tc<1, 0, false, 2>(a, rel, st) : launch_attn_tc<1, 0, false, 1>(a, rel, st);
-  if (bias == 1) return launch_attn_tc<1, 1, false, 1>(a, rel, st);
+  if (bias == 0) return use_nq2(a, 0) ? launch_attn_tc<1, 0, false, 2>(a, rel, st) : launch_attn_tc<1, 0, false, 1>(a, rel, st);
+  if (bias == 1) return use_nq2(a, 1) ? launch_attn_tc<1, 1, false, 2>(a, rel, st) : launch_attn_tc<1, 1, false, 1>(a, rel, st);
   return launch_attn_tc<1, 2, false, 1>(a, rel, st);
 }
 

@@ -1,0 +1,438 @@
+// decoder_fused.cu — K-I2T: the image->token half of a two-way transformer layer as ONE kernel.
+//
+// Reference (transformer.py:184-190, Attention.forward :228-254), per prompt p and image token x (4096 per prompt):
+//     q = q_proj(x + pe);  a = softmax(q k_t^T / 4) v_t  over the 7 prompt tokens, 8 heads x 16;
+//     x' = LayerNorm(x + out_proj(a))
+// The 7 tokens are tiny, so both projections are folded into per-prompt operands (csam_dec_fold_i2t):
+//     scores[x, (h,j)] = x . B1[(h,j), 0:256] + peq[x] . B1[(h,j), 256:384]      B1 = log2e/4 * (Wq_h^T k_t[j,h] | blockdiag k_t)
+//     out_proj(a)[x]   = P[x, (h,j)] . B2[:, (h,j)] + b_o                        B2 = Wo_h v_t[j,h]
+// with peq = pe Wq^T + b_q a constant of the weights.  One CTA then does, per 128-row tile:
+//     MMA1  S[128,64]  = [X | PEQ] (K = 384) * B1^T          (tcgen05, 3 MMAs per k-step: hi/lo split operands)
+//     E1    P = softmax over the 7 tokens of each head       (fp32, one row per thread pair, P stored as an h16 pair)
+//     MMA2  O[128,256] = P (K = 64) * B2^T
+//     E2    x' = LayerNorm(x + O + b_o) -> h16 pair          (residual x re-read from L2, where MMA1's TMA left it)
+// so the [P*4096,128] q and attention-output streams and the separate out_proj GEMM of the unfused path never
+// exist: the layer reads X once (1 KB per row) and writes X' once (1 KB per row).
+//   warp 0       TMA producer  (A / B1 k-blocks through a 2-stage ring; B2 once per prompt)
+//   warp 1       MMA issuer    (MMA1 of tile i+1 is issued before MMA2 of tile i)
+//   warp 2       TMEM allocator (S0 S1 O = 64 + 64 + 256 columns)
+//   warps 4..11  epilogue: drain O(i) -> E1(i+1) -> normalise + store (i), so MMA2(i+1) runs under the stores
+#include "common.cuh"
+
+namespace csam {
+
+constexpr int I2T_BM = 128;
+constexpr int I2T_THREADS = 384;
+constexpr int I2T_KB1 = 6;                       // 4 k-blocks of X (256) + 2 of PEQ (128)
+constexpr int I2T_STAGES = 2;
+constexpr int I2T_A_BYTES = 128 * 64 * 2;        // 16 KB per operand half
+constexpr int I2T_B1_BYTES = 64 * 64 * 2;        // 8 KB
+constexpr int I2T_STAGE_BYTES = 2 * I2T_A_BYTES + 2 * I2T_B1_BYTES;   // 48 KB
+constexpr int I2T_B2_BYTES = 256 * 64 * 2;       // 32 KB per half
+constexpr int I2T_P_BYTES = 128 * 64 * 2;        // 16 KB per half
+constexpr int I2T_OFF_B2 = I2T_STAGES * I2T_STAGE_BYTES;
+constexpr int I2T_OFF_P = I2T_OFF_B2 + 2 * I2T_B2_BYTES;
+constexpr int I2T_OFF_BAR = I2T_OFF_P + 2 * I2T_P_BYTES;
+constexpr int I2T_OFF_EPI = I2T_OFF_BAR + 256;
+constexpr int I2T_SMEM_BYTES = I2T_OFF_EPI + (4 * 128 + 3 * 256) * 4;
+static_assert(I2T_SMEM_BYTES <= 227 * 1024, "i2t layer shared memory budget");
+
+struct I2TBars {
+  uint64_t full[I2T_STAGES], empty[I2T_STAGES];
+  uint64_t s_full[2], s_empty[2];
+  uint64_t p_full, o_full, o_empty, b2_full, b2_empty;
+  uint32_t tmem_slot;
+};
+
+struct I2TParams {
+  int x_shared;              // 1: the same 4096 key rows for every prompt (layer 0)
+  int tiles;                 // P * 32
+  const __half* x_hi; const __half* x_lo;     // residual = the keys themselves (hi + lo is fp32-accurate)
+  const float* bias; const float* gamma; const float* beta; float eps;
+  __half* out_hi; __half* out_lo;
+};
+
+__device__ __forceinline__ float ex2f_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(I2T_THREADS, 1)
+dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant__ CUtensorMap tx_lo,
+                     const __grid_constant__ CUtensorMap tq_hi, const __grid_constant__ CUtensorMap tq_lo,
+                     const __grid_constant__ CUtensorMap tb1_hi, const __grid_constant__ CUtensorMap tb1_lo,
+                     const __grid_constant__ CUtensorMap tb2_hi, const __grid_constant__ CUtensorMap tb2_lo,
+                     I2TParams a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  I2TBars* bars = reinterpret_cast<I2TBars*>(smem + I2T_OFF_BAR);
+  float* epi = reinterpret_cast<float*>(smem + I2T_OFF_EPI);   // ex_sum[2][128] ex_sq[2][128] gamma beta bias
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // contiguous tile range per CTA: consecutive tiles share a prompt, so B2 is loaded about once per 32 tiles
+  const int t0 = (int)((long long)a.tiles * blockIdx.x / gridDim.x);
+  const int t1 = (int)((long long)a.tiles * (blockIdx.x + 1) / gridDim.x);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tx_hi); tma_prefetch_desc(&tx_lo); tma_prefetch_desc(&tq_hi); tma_prefetch_desc(&tq_lo);
+    tma_prefetch_desc(&tb1_hi); tma_prefetch_desc(&tb1_lo); tma_prefetch_desc(&tb2_hi); tma_prefetch_desc(&tb2_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < I2T_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars->s_full[b], 1); mbar_init(&bars->s_empty[b], 8); }
+    mbar_init(&bars->p_full, 8);
+    mbar_init(&bars->o_full, 1);
+    mbar_init(&bars->o_empty, 8);
+    mbar_init(&bars->b2_full, 1);
+    mbar_init(&bars->b2_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(&bars->tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_slot;      // S0 [0,64) S1 [64,128) O [128,384)
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0; int b2_cnt = 0;
+      for (int t = t0; t < t1; ++t) {
+        const int p = t >> 5, mrow = (t & 31) * I2T_BM;
+        const int arow = a.x_shared ? mrow : t * I2T_BM;
+        for (int kb = 0; kb < I2T_KB1; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * I2T_STAGE_BYTES;
+          uint8_t* sb = sa + 2 * I2T_A_BYTES;
+          mbar_expect_tx(&bars->full[stage], I2T_STAGE_BYTES);
+          if (kb < 4) {
+            tma_load_2d(sa, &tx_hi, &bars->full[stage], kb * 64, arow);
+            tma_load_2d(sa + I2T_A_BYTES, &tx_lo, &bars->full[stage], kb * 64, arow);
+          } else {
+            tma_load_2d(sa, &tq_hi, &bars->full[stage], (kb - 4) * 64, mrow);
+            tma_load_2d(sa + I2T_A_BYTES, &tq_lo, &bars->full[stage], (kb - 4) * 64, mrow);
+          }
+          tma_load_2d(sb, &tb1_hi, &bars->full[stage], kb * 64, p * 64);
+          tma_load_2d(sb + I2T_B1_BYTES, &tb1_lo, &bars->full[stage], kb * 64, p * 64);
+          if (++stage == I2T_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (t == t0 || (t & 31) == 0) {
+          // first tile of a prompt in this CTA: its B2 (needed by MMA2 only) replaces the previous prompt's
+          mbar_wait(&bars->b2_empty, (b2_cnt & 1) ^ 1);
+          mbar_expect_tx(&bars->b2_full, 2 * I2T_B2_BYTES);
+          tma_load_2d(smem + I2T_OFF_B2, &tb2_hi, &bars->b2_full, 0, p * 256);
+          tma_load_2d(smem + I2T_OFF_B2 + I2T_B2_BYTES, &tb2_lo, &bars->b2_full, 0, p * 256);
+          ++b2_cnt;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = umma_idesc_f16(I2T_BM, 64, 0, 0);
+      constexpr uint32_t idesc2 = umma_idesc_f16(I2T_BM, 256, 0, 0);
+      int stage = 0; uint32_t phase = 0; int b2_cnt = 0;
+      auto mma1 = [&](int li) {
+        const int b = li & 1;
+        mbar_wait(&bars->s_empty[b], ((li >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + b * 64;
+        for (int kb = 0; kb < I2T_KB1; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * I2T_STAGE_BYTES);
+          const uint32_t ad = umma_desc_lo(sa, 16);
+          const uint32_t bd = umma_desc_lo(sa + 2 * I2T_A_BYTES, 16);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_f16_w(d, ad + 2 * k, bd + 2 * k, idesc1, (kb | k) ? 1u : 0u);
+            umma_f16_w(d, ad + (I2T_A_BYTES >> 4) + 2 * k, bd + 2 * k, idesc1, 1u);
+            umma_f16_w(d, ad + 2 * k, bd + (I2T_B1_BYTES >> 4) + 2 * k, idesc1, 1u);
+          }
+          umma_commit(&bars->empty[stage]);
+          if (++stage == I2T_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&bars->s_full[b]);
+      };
+      if (t0 < t1) mma1(0);
+      int li = 0;
+      for (int t = t0; t < t1; ++t, ++li) {
+        if (t + 1 < t1) mma1(li + 1);
+        if (t == t0 || (t & 31) == 0) { mbar_wait(&bars->b2_full, b2_cnt & 1); ++b2_cnt; }
+        mbar_wait(&bars->p_full, li & 1);
+        mbar_wait(&bars->o_empty, (li & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t pd = umma_desc_lo(smem_u32(smem + I2T_OFF_P), 16);
+        const uint32_t bd = umma_desc_lo(smem_u32(smem + I2T_OFF_B2), 16);
+        const uint32_t d = tmem_base + 128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          umma_f16_w(d, pd + 2 * k, bd + 2 * k, idesc2, k ? 1u : 0u);
+          umma_f16_w(d, pd + (I2T_P_BYTES >> 4) + 2 * k, bd + 2 * k, idesc2, 1u);
+          umma_f16_w(d, pd + 2 * k, bd + (I2T_B2_BYTES >> 4) + 2 * k, idesc2, 1u);
+        }
+        umma_commit(&bars->o_full);
+        if (t + 1 == t1 || ((t + 1) & 31) == 0) umma_commit(&bars->b2_empty);   // last tile of this prompt here
+      }
+    }
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int ew = warp - 4;
+    const int q = ew & 3;                        // TMEM lane quadrant == warp % 4
+    const int ch = ew >> 2;                      // which half of the columns (S: 32 of 64, O: 128 of 256)
+    const int r = q * 32 + lane;                 // row of the tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int et = threadIdx.x - 128;            // 0..255
+    float* ex_sum = epi;                         // [2][128]
+    float* ex_sq = epi + 256;                    // [2][128]
+    float* s_gamma = epi + 512;
+    float* s_beta = s_gamma + 256;
+    float* s_bias = s_gamma + 512;
+    s_gamma[et] = a.gamma[et];
+    s_beta[et] = a.beta[et];
+    s_bias[et] = a.bias ? a.bias[et] : 0.f;
+    asm volatile("bar.sync 5, 256;" ::: "memory");
+
+    // E1: softmax over the 7 tokens of each of this thread's 4 heads -> P (hi/lo) in the UMMA K-major layout
+    auto softmax_tile = [&](int li) {
+      const int b = li & 1;
+      mbar_wait(&bars->s_full[b], (li >> 1) & 1);
+      tc_fence_after();
+      uint32_t raw[32];
+      tmem_ld32(lane_addr + b * 64 + ch * 32, raw);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->s_empty[b]);
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        float s[7];
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) { s[j] = __uint_as_float(raw[hh * 8 + j]); m = fmaxf(m, s[j]); }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) { s[j] = ex2f_approx(s[j] - m); sum += s[j]; }
+        const float inv = 1.0f / sum;
+        float pr[8];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) pr[j] = s[j] * inv;
+        pr[7] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          __half2 h2, l2;
+          split_h2(pr[j], pr[j + 1], h2, l2);
+          hi[hh * 4 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&h2);
+          lo[hh * 4 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+      }
+      uint8_t* pb = smem + I2T_OFF_P + r * 128;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int off = ((ch * 4 + u) ^ (r & 7)) << 4;
+        *reinterpret_cast<uint4*>(pb + off) = make_uint4(hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
+        *reinterpret_cast<uint4*>(pb + I2T_P_BYTES + off) = make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->p_full);
+    };
+
+    if (t0 < t1) softmax_tile(0);
+    int li = 0;
+    for (int t = t0; t < t1; ++t, ++li) {
+      // residual rows (this lane's 128 columns), requested before the accumulator is waited for
+      const size_t xrow = (size_t)(a.x_shared ? (t & 31) * I2T_BM + r : t * I2T_BM + r);
+      const __half* ph = a.x_hi + xrow * 256 + ch * 128;
+      const __half* pl = a.x_lo + xrow * 256 + ch * 128;
+      float x[128];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint32_t hw[8], lw[8];
+        ldg256(ph + i * 16, hw);
+        ldg256(pl + i * 16, lw);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[k]));
+          const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[k]));
+          x[i * 16 + 2 * k] = hf.x + lf.x;
+          x[i * 16 + 2 * k + 1] = hf.y + lf.y;
+        }
+      }
+      mbar_wait(&bars->o_full, li & 1);
+      tc_fence_after();
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 128; c += 16) {
+        uint32_t raw[16];
+        tmem_ld16(lane_addr + 128 + ch * 128 + c, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(s_bias + ch * 128 + c + j);
+          x[c + j + 0] += __uint_as_float(raw[j + 0]) + bb.x;
+          x[c + j + 1] += __uint_as_float(raw[j + 1]) + bb.y;
+          x[c + j + 2] += __uint_as_float(raw[j + 2]) + bb.z;
+          x[c + j + 3] += __uint_as_float(raw[j + 3]) + bb.w;
+          sum += (x[c + j] + x[c + j + 1]) + (x[c + j + 2] + x[c + j + 3]);
+        }
+      }
+      // O drained (and MMA2(li) has finished reading P): release both before the long normalise + store phase
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->o_empty);
+      if (t + 1 < t1) softmax_tile(li + 1);
+      ex_sum[ch * 128 + r] = sum;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      const float mean = (ex_sum[r] + ex_sum[128 + r]) * (1.0f / 256.0f);
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 128; ++j) { const float d = x[j] - mean; sq = fmaf(d, d, sq); }
+      ex_sq[ch * 128 + r] = sq;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      const float rstd = 1.0f / sqrtf((ex_sq[r] + ex_sq[128 + r]) * (1.0f / 256.0f) + a.eps);
+      const size_t orow = (size_t)t * I2T_BM + r;
+#pragma unroll
+      for (int c = 0; c < 128; c += 16) {
+        const int col = ch * 128 + c;
+        float y[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 g = *reinterpret_cast<const float4*>(s_gamma + col + j);
+          const float4 bt = *reinterpret_cast<const float4*>(s_beta + col + j);
+          y[j + 0] = (x[c + j + 0] - mean) * rstd * g.x + bt.x;
+          y[j + 1] = (x[c + j + 1] - mean) * rstd * g.y + bt.y;
+          y[j + 2] = (x[c + j + 2] - mean) * rstd * g.z + bt.z;
+          y[j + 3] = (x[c + j + 3] - mean) * rstd * g.w + bt.w;
+        }
+        store_pair16(a.out_hi, a.out_lo, orow * 256 + col, y);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+// ---- per-prompt folded operands -------------------------------------------------------------------------
+// B1 [P*64, 384], row n = h*8 + j (j = 7 is a zero row): cols 0..255 = s * sum_d Wq[h*16+d][c] k_t[j][h*16+d],
+// cols 256 + h'*16 + d = (h' == h) ? s * k_t[j][h*16+d] : 0, s = log2(e) / sqrt(16).
+// B2 [P*256, 64], row c: col n = h*8 + j = sum_d Wo[c][h*16+d] v_t[j][h*16+d] (zero for j = 7).
+__global__ void __launch_bounds__(256)
+dec_fold_i2t_kernel(const float* __restrict__ kt, const float* __restrict__ vt, const float* __restrict__ wq,
+                    const float* __restrict__ wo, __half* b1_hi, __half* b1_lo, __half* b2_hi, __half* b2_lo) {
+  __shared__ float ks[7][128];
+  __shared__ float vs[7][128];
+  const int p = blockIdx.x, c = threadIdx.x;
+  constexpr float SC = 0.25f * 1.4426950408889634f;
+  for (int i = c; i < 7 * 128; i += 256) {
+    ks[i >> 7][i & 127] = kt[(size_t)p * 896 + i] * SC;
+    vs[i >> 7][i & 127] = vt[(size_t)p * 896 + i];
+  }
+  __syncthreads();
+  __half* r1h = b1_hi + (size_t)p * 64 * 384;
+  __half* r1l = b1_lo + (size_t)p * 64 * 384;
+  for (int h = 0; h < 8; ++h) {
+    float w[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) w[d] = wq[(size_t)(h * 16 + d) * 256 + c];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float acc = 0.f;
+      if (j < 7) {
+#pragma unroll
+        for (int d = 0; d < 16; ++d) acc = fmaf(w[d], ks[j][h * 16 + d], acc);
+      }
+      store_pair(r1h, r1l, (size_t)(h * 8 + j) * 384 + c, acc);
+      if (c < 128) {
+        const float v = (j < 7 && (c >> 4) == h) ? ks[j][c] : 0.f;
+        store_pair(r1h, r1l, (size_t)(h * 8 + j) * 384 + 256 + c, v);
+      }
+    }
+  }
+  float o[64];
+  const float* wrow = wo + (size_t)c * 128;
+#pragma unroll
+  for (int h = 0; h < 8; ++h) {
+    float w[16];
+#pragma unroll
+    for (int d = 0; d < 16; d += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(wrow + h * 16 + d);
+      w[d] = t.x; w[d + 1] = t.y; w[d + 2] = t.z; w[d + 3] = t.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float acc = 0.f;
+      if (j < 7) {
+#pragma unroll
+        for (int d = 0; d < 16; ++d) acc = fmaf(w[d], vs[j][h * 16 + d], acc);
+      }
+      o[h * 8 + j] = acc;
+    }
+  }
+  const size_t ob = ((size_t)p * 256 + c) * 64;
+#pragma unroll
+  for (int i = 0; i < 64; i += 8) store_pair8(b2_hi, b2_lo, ob + i, o + i);
+}
+
+}  // namespace csam
+
+using namespace csam;
+
+extern "C" int csam_dec_fold_i2t(const float* kt, const float* vt, int P, const float* wq, const float* wo,
+                                 void* b1_hi, void* b1_lo, void* b2_hi, void* b2_lo, void* stream) {
+  CSAM_REQUIRE(kt && vt && wq && wo && b1_hi && b1_lo && b2_hi && b2_lo && P > 0, "csam_dec_fold_i2t: bad args");
+  CSAM_REQUIRE((reinterpret_cast<uintptr_t>(wo) & 15) == 0 && (reinterpret_cast<uintptr_t>(b2_hi) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(b2_lo) & 15) == 0,
+               "csam_dec_fold_i2t: 16-byte alignment");
+  dec_fold_i2t_kernel<<<P, 256, 0, (cudaStream_t)stream>>>(kt, vt, wq, wo, static_cast<__half*>(b1_hi),
+                                                           static_cast<__half*>(b1_lo), static_cast<__half*>(b2_hi),
+                                                           static_cast<__half*>(b2_lo));
+  return check_launch("dec_fold_i2t_kernel");
+}
+
+extern "C" int csam_dec_i2t_layer(const csam_i2t_layer_args* a, void* stream) {
+  CSAM_REQUIRE(a && a->x_hi && a->x_lo && a->peq_hi && a->peq_lo && a->b1_hi && a->b1_lo && a->b2_hi && a->b2_lo &&
+                   a->gamma && a->beta && a->out_hi && a->out_lo,
+               "csam_dec_i2t_layer: null operand (h16 pairs with both halves are required)");
+  CSAM_REQUIRE(a->P > 0 && a->P <= (1 << 16), "csam_dec_i2t_layer: prompt count");
+  auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
+  CSAM_REQUIRE(al32(a->x_hi) && al32(a->x_lo) && al32(a->out_hi) && al32(a->out_lo) && al32(a->peq_hi) &&
+                   al32(a->peq_lo) && al32(a->b1_hi) && al32(a->b1_lo) && al32(a->b2_hi) && al32(a->b2_lo),
+               "csam_dec_i2t_layer: 32-byte alignment");
+  const uint64_t xrows = a->x_shared ? 4096ull : (uint64_t)a->P * 4096ull;
+  CUtensorMap tx_hi, tx_lo, tq_hi, tq_lo, tb1_hi, tb1_lo, tb2_hi, tb2_lo;
+  if (make_tmap_2d_f16(&tx_hi, a->x_hi, xrows, 256, 256, 128, 64)) return 1;
+  if (make_tmap_2d_f16(&tx_lo, a->x_lo, xrows, 256, 256, 128, 64)) return 1;
+  if (make_tmap_2d_f16(&tq_hi, a->peq_hi, 4096, 128, 128, 128, 64)) return 1;
+  if (make_tmap_2d_f16(&tq_lo, a->peq_lo, 4096, 128, 128, 128, 64)) return 1;
+  if (make_tmap_2d_f16(&tb1_hi, a->b1_hi, (uint64_t)a->P * 64, 384, 384, 64, 64)) return 1;
+  if (make_tmap_2d_f16(&tb1_lo, a->b1_lo, (uint64_t)a->P * 64, 384, 384, 64, 64)) return 1;
+  if (make_tmap_2d_f16(&tb2_hi, a->b2_hi, (uint64_t)a->P * 256, 64, 64, 256, 64)) return 1;
+  if (make_tmap_2d_f16(&tb2_lo, a->b2_lo, (uint64_t)a->P * 256, 64, 64, 256, 64)) return 1;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(dec_i2t_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I2T_SMEM_BYTES) != cudaSuccess)
+      return fail("%s", "cudaFuncSetAttribute(smem) failed for dec_i2t_layer_kernel");
+    attr = true;
+  }
+  I2TParams p;
+  p.x_shared = a->x_shared ? 1 : 0;
+  p.tiles = a->P * 32;
+  p.x_hi = static_cast<const __half*>(a->x_hi); p.x_lo = static_cast<const __half*>(a->x_lo);
+  p.bias = a->bias; p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps;
+  p.out_hi = static_cast<__half*>(a->out_hi); p.out_lo = static_cast<__half*>(a->out_lo);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.tiles < sms ? p.tiles : sms;
+  dec_i2t_layer_kernel<<<grid, I2T_THREADS, I2T_SMEM_BYTES, (cudaStream_t)stream>>>(tx_hi, tx_lo, tq_hi, tq_lo, tb1_hi,
+                                                                                   tb1_lo, tb2_hi, tb2_lo, p);
+  return check_launch("dec_i2t_layer_kernel");
+}

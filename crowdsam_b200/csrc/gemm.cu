@@ -265,18 +265,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(ring + stage * Cfg::STAGE_BYTES);
           const uint32_t sw = WRES ? smem_u32(smem + kb * Cfg::NOPS * Cfg::W_BYTES) : sa + Cfg::NOPS * Cfg::A_BYTES;
+          // descriptor low words once per k-block; each k-step is one integer add (see umma_desc_lo)
+          const uint32_t ad = umma_desc_lo(sa, 16);
+          const uint32_t wd = B_MN ? umma_desc_lo(sw, 8192) : umma_desc_lo(sw, 16);
+          constexpr uint32_t WSTEP = B_MN ? (2048 >> 4) : (32 >> 4);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t a_hi = umma_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t w_hi = B_MN ? umma_desc_sw128(sw + k * 2048, 8192, 1024)
-                                       : umma_desc_sw128(sw + k * 32, 16, 1024);
-            umma_f16(d_addr, a_hi, w_hi, idesc, (kb | k) ? 1u : 0u);
+            umma_f16_w(d_addr, ad + 2 * k, wd + WSTEP * k, idesc, (kb | k) ? 1u : 0u);
             if (SPLIT == 3) {
-              const uint64_t a_lo = umma_desc_sw128(sa + Cfg::A_BYTES + k * 32, 16, 1024);
-              const uint64_t w_lo = B_MN ? umma_desc_sw128(sw + Cfg::W_BYTES + k * 2048, 8192, 1024)
-                                         : umma_desc_sw128(sw + Cfg::W_BYTES + k * 32, 16, 1024);
-              umma_f16(d_addr, a_lo, w_hi, idesc, 1u);
-              umma_f16(d_addr, a_hi, w_lo, idesc, 1u);
+              umma_f16_w(d_addr, ad + (Cfg::A_BYTES >> 4) + 2 * k, wd + WSTEP * k, idesc, 1u);
+              umma_f16_w(d_addr, ad + 2 * k, wd + (Cfg::W_BYTES >> 4) + WSTEP * k, idesc, 1u);
             }
           }
           umma_commit(&empty_bar[stage]);            // smem slot reusable once these MMAs retire

@@ -256,6 +256,16 @@ class MaskDecoderEngine:
                              L1 + ".cross_attn_image_to_token.q_proj"])
         bv1 = sd[L1 + ".cross_attn_token_to_image.v_proj.bias"].detach().float().to(dev)
         self.res_kvq1 = torch.cat([self.pe_k[1], bv1[None, :].expand(4096, -1), self.pe_qi[1]], 1).contiguous()
+        # Fused image->token layer (csam_dec_i2t_layer, split precision only): q_proj / out_proj are folded into
+        # per-prompt operands, so layer 1 needs only k | v of keys1 and the raw fp32 projection weights.
+        self.fused_i2t = split and os.environ.get("CSAM_DEC_FUSED_I2T", "1") != "0"
+        self.w_kv1 = cat_w([L1 + ".cross_attn_token_to_image.k_proj", L1 + ".cross_attn_token_to_image.v_proj"])
+        self.res_kv1 = torch.cat([self.pe_k[1], bv1[None, :].expand(4096, -1)], 1).contiguous()
+        for i, Lr in enumerate(self.layers):
+            Lp = f"{t}.layers.{i}.cross_attn_image_to_token"
+            Lr["i2t_wq"] = _f(sd, Lp + ".q_proj.weight", dev)
+            Lr["i2t_wo"] = _f(sd, Lp + ".out_proj.weight", dev)
+            Lr["peq_h"] = H16.from_f32(self.pe_qi[i], True)
         self.w_kvf = cat_w([fin + ".k_proj", fin + ".v_proj"])
         bvf = sd[fin + ".v_proj.bias"].detach().float().to(dev)
         self.res_kvf = torch.cat([self.pe_kf, bvf[None, :].expand(4096, -1)], 1).contiguous()
@@ -292,7 +302,7 @@ class MaskDecoderEngine:
         planes = ops.transpose_f32(dproj).view(256, 73, 73)
         dmap = ops.bilinear(planes, 256, 256, chlast=False)                            # [256,256,256]
         _, dmap_h, _ = ops.layernorm(dmap.view(256 * 32, 2048), normalize=False, want_h16=True, split=split)
-        self.img = dict(keys0=keys0, k0=k0.view(1, 4096, 128), v0=v0.view(1, 4096, 128), q0=q0.view(1, 4096, 128),
+        self.img = dict(keys0=keys0, keys0_h=keys0_h, k0=k0.view(1, 4096, 128), v0=v0.view(1, 4096, 128), q0=q0.view(1, 4096, 128),
                         dproj_h=dproj_h, dmap_h=dmap_h.view(256, 65536))
 
     def fg_logits(self) -> torch.Tensor:
@@ -338,6 +348,10 @@ class MaskDecoderEngine:
             qc, _ = ta.q(q_pe_h, want_f32=True)
             if li == 0:
                 kc, vc = I["k0"], I["v0"]
+            elif self.fused_i2t:
+                kv1, _ = ops.gemm(keys_h, self.w_kv1, residual=self.res_kv1, res_mod=4096, want_f32=True)
+                kv1 = kv1.view(P, 4096, 256)
+                kc, vc = kv1[:, :, 0:128], kv1[:, :, 128:256]
             else:
                 kvq, _ = ops.gemm(keys_h, self.w_kvq1, residual=self.res_kvq1, res_mod=4096, want_f32=True)
                 kvq = kvq.view(P, 4096, 384)
@@ -354,6 +368,14 @@ class MaskDecoderEngine:
             ia = Lr["i2t"]
             kt, _ = ia.k(q_pe_h, want_f32=True)
             vt, _ = ia.v(q_h, want_f32=True)
+            if self.fused_i2t:
+                # q_proj, the 7-key softmax, out_proj, the residual and norm4 in ONE kernel: reads the keys once,
+                # writes the new keys once (as the h16 pair that is both next operand and next residual)
+                b1, b2 = ops.dec_fold_i2t(kt.view(P, 7, 128), vt.view(P, 7, 128), Lr["i2t_wq"], Lr["i2t_wo"])
+                keys_h = ops.dec_i2t_layer(I["keys0_h"] if li == 0 else keys_h, li == 0, Lr["peq_h"], b1, b2, P,
+                                           ia.o.b, Lr["n4"][0], Lr["n4"][1], 1e-5)
+                keys_f32 = None
+                continue
             qi = I["q0"] if li == 0 else qi1
             _, a = ops.attn_few_keys(qi, kt.view(P, 7, 128), vt.view(P, 7, 128), P, 4096, 7, 8, 16,
                                      want_h16=True, split=split)

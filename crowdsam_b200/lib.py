@@ -58,6 +58,13 @@ class DecAttnArgs(C.Structure):
                 ("ldq", ci), ("ldk", ci), ("ldv", ci)]
 
 
+class I2TArgs(C.Structure):
+    _fields_ = [("x_hi", vp), ("x_lo", vp), ("x_shared", ci),
+                ("peq_hi", vp), ("peq_lo", vp), ("b1_hi", vp), ("b1_lo", vp), ("b2_hi", vp), ("b2_lo", vp),
+                ("P", ci), ("bias", vp), ("gamma", vp), ("beta", vp), ("eps", cf),
+                ("out_hi", vp), ("out_lo", vp)]
+
+
 class PostArgs(C.Structure):
     _fields_ = [("low", vp), ("P", ci), ("sel", vp), ("planes", ci),
                 ("in_h", ci), ("in_w", ci), ("out_h", ci), ("out_w", ci),
@@ -82,6 +89,8 @@ _SIGS = {
     "csam_prompt_tokens": (ci, [vp, vp, ci, vp, vp, vp, vp, vp, vp]),
     "csam_attn_few_keys": (ci, [C.POINTER(DecAttnArgs), vp]),
     "csam_attn_few_queries": (ci, [C.POINTER(DecAttnArgs), vp]),
+    "csam_dec_fold_i2t": (ci, [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp]),
+    "csam_dec_i2t_layer": (ci, [C.POINTER(I2TArgs), vp]),
     "csam_upscale_shuffle_ln_gelu": (ci, [vp, ci, vp, vp, cf, vp, vp, vp]),
     "csam_upscale_hyper_masks": (ci, [vp, ci, vp, vp, vp]),
     "csam_softmax_weights": (ci, [vp, ci, ci, vp, vp, vp, vp]),
@@ -125,7 +134,7 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.csam_abi_version() != 5:
+    if lib.csam_abi_version() != 6:
         raise RuntimeError("libcsam_sm100.so ABI version mismatch")
     _lib = lib
     return lib

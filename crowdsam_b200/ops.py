@@ -312,6 +312,43 @@ def attn_few_queries(q, k, v, B, nq, nk, heads, hd, want_f32=False, want_h16=Fal
     return _dec_attn("csam_attn_few_queries", q, k, v, B, nq, nk, heads, hd, want_f32, want_h16, split)
 
 
+def dec_fold_i2t(kt: torch.Tensor, vt: torch.Tensor, wq: torch.Tensor, wo: torch.Tensor):
+    """kt, vt fp32 [P,7,128]; wq fp32 [128,256]; wo fp32 [256,128] -> (B1 H16 [P*64,384], B2 H16 [P*256,64])
+    (csam_dec_fold_i2t: the 7 prompt tokens folded into the operands of the fused image->token layer)."""
+    P = kt.shape[0]
+    assert kt.shape == (P, 7, 128) and vt.shape == (P, 7, 128) and kt.is_contiguous() and vt.is_contiguous()
+    assert wq.shape == (128, 256) and wo.shape == (256, 128) and wq.is_contiguous() and wo.is_contiguous()
+    b1 = H16.empty((P * 64, 384), True, kt.device)
+    b2 = H16.empty((P * 256, 64), True, kt.device)
+    tok = _pb()
+    L.check(L.load().csam_dec_fold_i2t(_p(kt), _p(vt), P, _p(wq), _p(wo), _p(b1.hi), _p(b1.lo), _p(b2.hi), _p(b2.lo),
+                                       _stream()), "csam_dec_fold_i2t")
+    _pe("dec_fold_i2t", tok, 0.0)
+    return b1, b2
+
+
+def dec_i2t_layer(x: H16, x_shared: bool, peq: H16, b1: H16, b2: H16, P: int, bias, gamma, beta, eps: float,
+                  out: Optional[H16] = None) -> H16:
+    """x' = LayerNorm(x + out_proj(softmax(q_proj(x + pe) k_t^T / 4) v_t)) for every image token of every prompt
+    (csam_dec_i2t_layer).  x: H16 [P*4096,256] or [4096,256] when x_shared.  Split (hi + lo) operands only."""
+    assert x.lo is not None and peq.lo is not None and b1.lo is not None and b2.lo is not None
+    assert x.hi.shape == ((4096 if x_shared else P * 4096), 256) and x.hi.is_contiguous() and x.lo.is_contiguous()
+    if out is None:
+        out = H16.empty((P * 4096, 256), True, x.hi.device)
+    g = L.I2TArgs()
+    g.x_hi, g.x_lo, g.x_shared = _p(x.hi), _p(x.lo), 1 if x_shared else 0
+    g.peq_hi, g.peq_lo = _p(peq.hi), _p(peq.lo)
+    g.b1_hi, g.b1_lo, g.b2_hi, g.b2_lo = _p(b1.hi), _p(b1.lo), _p(b2.hi), _p(b2.lo)
+    g.P = P
+    g.bias, g.gamma, g.beta, g.eps = _p(bias), _p(gamma), _p(beta), eps
+    g.out_hi, g.out_lo = _p(out.hi), _p(out.lo)
+    tok = _pb()
+    L.check(L.load().csam_dec_i2t_layer(C.byref(g), _stream()), "csam_dec_i2t_layer")
+    # algorithmic bytes: read x (hi+lo) once, write x' once
+    _pe("dec_i2t_layer", tok, float(P) * 4096 * 256 * 4 * (1 if x_shared else 2))
+    return out
+
+
 def upscale_shuffle_ln_gelu(y1: torch.Tensor, P: int, gamma, beta, eps: float, split: bool) -> H16:
     out = H16.empty((P * 16384, 64), split, y1.device)
     L.check(L.load().csam_upscale_shuffle_ln_gelu(_p(y1), P, _p(gamma), _p(beta), eps, _p(out.hi), _p(out.lo),

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSAM_ABI_VERSION 5
+#define CSAM_ABI_VERSION 6
 #if defined(__GNUC__)
 #define CSAM_API __attribute__((visibility("default")))
 #else
@@ -177,6 +177,32 @@ typedef struct {
 } csam_dec_attn_args;
 CSAM_API int csam_attn_few_keys(const csam_dec_attn_args* a, void* stream);
 CSAM_API int csam_attn_few_queries(const csam_dec_attn_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K-I2T  the image->token half of a two-way layer as ONE kernel (transformer.py:184-190 with
+ * Attention.forward :228-254):  x' = LayerNorm(x + out_proj(softmax(q_proj(x + pe) k_t^T / 4) v_t)).
+ * The 7 prompt tokens are folded into per-prompt operands first (csam_dec_fold_i2t):
+ *   kt, vt: fp32 [P,7,128] = k_proj(tokens + pe), v_proj(tokens) of the layer's image->token attention;
+ *   wq fp32 [128,256] (q_proj.weight), wo fp32 [256,128] (out_proj.weight);
+ *   b1: h16 pair [P*64, 384], row h*8+j: (log2e/4) * (Wq_h^T kt[j,h] | block-diagonal kt[j,h]);
+ *   b2: h16 pair [P*256, 64], column h*8+j: Wo_h vt[j,h].
+ * csam_dec_i2t_layer: x h16 pair [P*4096,256] (or [4096,256] when x_shared: layer 0, where every prompt
+ * starts from the same image embedding), peq h16 pair [4096,128] = pe Wq^T + b_q, bias = out_proj.bias,
+ * gamma/beta/eps = norm4 -> out h16 pair [P*4096,256].  Reads x once and writes x' once; the q and
+ * attention-output streams of the unfused path never exist.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* x_hi; const void* x_lo; int x_shared;
+  const void* peq_hi; const void* peq_lo;
+  const void* b1_hi; const void* b1_lo;
+  const void* b2_hi; const void* b2_lo;
+  int P;
+  const float* bias; const float* gamma; const float* beta; float eps;
+  void* out_hi; void* out_lo;
+} csam_i2t_layer_args;
+CSAM_API int csam_dec_fold_i2t(const float* kt, const float* vt, int P, const float* wq, const float* wo,
+                      void* b1_hi, void* b1_lo, void* b2_hi, void* b2_lo, void* stream);
+CSAM_API int csam_dec_i2t_layer(const csam_i2t_layer_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Mask upscaling tail (mask_decoder.py:56-62,173-181).

@@ -579,3 +579,36 @@ def test_gemm_epilogue_upscaling():
     z = torch.nn.functional.gelu(torch.nn.functional.conv_transpose2d(up1q, w2q, b2.double(), stride=2))   # [P,32,256,256]
     refm = torch.einsum("plc,pchw->plhw", hyper.double(), z)
     assert _rel(masks, refm) < 1e-5
+
+
+@pytest.mark.parametrize("shared,P", [(True, 3), (False, 2), (False, 40)])
+def test_decoder_fused_i2t_layer(shared, P):
+    """csam_dec_fold_i2t + csam_dec_i2t_layer against the reference formulation of the image->token half layer
+    (transformer.py:184-190, 228-254) in fp64: q_proj(x + pe), 8 heads x 16 over the 7 prompt tokens, out_proj,
+    residual, LayerNorm.  P = 40 spans several CTAs' tile ranges and prompt changes inside a range."""
+    o = ops()
+    g = torch.Generator().manual_seed(31 + P)
+    rows = 4096 if shared else P * 4096
+    x = torch.randn(rows, 256, generator=g)
+    pe = torch.randn(4096, 256, generator=g)
+    wq, bq = torch.randn(128, 256, generator=g) * 0.08, torch.randn(128, generator=g) * 0.1
+    wo, bo = torch.randn(256, 128, generator=g) * 0.1, torch.randn(256, generator=g) * 0.1
+    kt, vt = torch.randn(P, 7, 128, generator=g), torch.randn(P, 7, 128, generator=g)
+    gam, bet = torch.randn(256, generator=g), torch.randn(256, generator=g)
+    xh = _h16(x, True)
+    peq = (pe.double() @ wq.double().T + bq.double()).float()
+    peq_h = _h16(peq, True)
+    b1, b2 = o.dec_fold_i2t(kt.to(DEV), vt.to(DEV), wq.to(DEV).contiguous(), wo.to(DEV).contiguous())
+    out = o.dec_i2t_layer(xh, shared, peq_h, b1, b2, P, bo.to(DEV), gam.to(DEV), bet.to(DEV), 1e-5)
+    torch.cuda.synchronize()
+    # reference in fp64 on the exact operand values the kernel saw (hi + lo of x and of peq)
+    xd = xh.float().cpu().double()
+    xd = xd.expand(P, 4096, 256) if shared else xd.view(P, 4096, 256)
+    q = xd @ wq.double().T + peq_h.float().cpu().double()[None]                      # [P,4096,128]
+    qh = q.view(P, 4096, 8, 16).permute(0, 2, 1, 3)
+    kh = kt.double().view(P, 7, 8, 16).permute(0, 2, 1, 3)
+    vh = vt.double().view(P, 7, 8, 16).permute(0, 2, 1, 3)
+    att = torch.softmax(qh @ kh.transpose(-1, -2) / 4.0, dim=-1) @ vh                # [P,8,4096,16]
+    a = att.permute(0, 2, 1, 3).reshape(P, 4096, 128)
+    y = torch.nn.functional.layer_norm(xd + a @ wo.double().T + bo.double(), (256,), gam.double(), bet.double(), 1e-5)
+    assert _rel(out.float().view(P, 4096, 256), y) < 2e-5
