@@ -115,6 +115,25 @@ __device__ __forceinline__ void store_pair16(__half* hi, __half* lo, size_t i, c
   if (lo) stg256(lo + i, l);
 }
 
+// streaming variant: the stores bypass L1 and are first in line for L2 eviction (outputs nobody re-reads soon)
+__device__ __forceinline__ void stg256_stream(void* p, const uint32_t* r) {
+  asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void store_pair16_stream(__half* hi, __half* lo, size_t i, const float* v) {
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    __half2 hh, ll;
+    split_h2(v[2 * j], v[2 * j + 1], hh, ll);
+    h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  stg256_stream(hi + i, h);
+  if (lo) stg256_stream(lo + i, l);
+}
+
 // Branch-free erf: odd rational x*P(x^2)/Q(x^2) on [-4, 4] (|erf| rounds to 1 beyond), max abs error 4.5e-7
 // against a double-precision erf over [-6, 6] (checked on the host).  17 instructions
 // instead of libdevice erff's two divergent branches: GELU is what bounds the ConvTranspose / fc1 epilogues.
@@ -194,6 +213,19 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// L2 eviction-priority hints: a stream that is read again soon (evict_last) next to one that is written once
+// and never read by this kernel (evict_first stores below)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
       : "memory");
 }
 // pull one box of a tensor map into L2 (no shared memory, no barrier): decouples HBM latency from the smem ring

@@ -8,7 +8,7 @@
 //     out_proj(a)[x]   = P[x, (h,j)] . B2[:, (h,j)] + b_o                        B2 = Wo_h v_t[j,h]
 // with peq = pe Wq^T + b_q a constant of the weights.  One CTA then does, per 128-row tile:
 //     MMA1  S[128,64]  = [X | PEQ] (K = 384) * B1^T          (tcgen05, 3 MMAs per k-step: hi/lo split operands)
-//     E1    P = softmax over the 7 tokens of each head       (fp32, one row per thread pair, P stored as an h16 pair)
+//     E1    P = softmax over the 7 tokens of each head       (fp32, four threads per row, P stored as an h16 pair)
 //     MMA2  O[128,256] = P (K = 64) * B2^T
 //     E2    x' = LayerNorm(x + O + b_o) -> h16 pair          (residual x re-read from L2, where MMA1's TMA left it)
 // so the [P*4096,128] q and attention-output streams and the separate out_proj GEMM of the unfused path never
@@ -16,13 +16,15 @@
 //   warp 0       TMA producer  (A / B1 k-blocks through a 2-stage ring; B2 once per prompt)
 //   warp 1       MMA issuer    (MMA1 of tile i+1 is issued before MMA2 of tile i)
 //   warp 2       TMEM allocator (S0 S1 O = 64 + 64 + 256 columns)
-//   warps 4..11  epilogue: drain O(i) -> E1(i+1) -> normalise + store (i), so MMA2(i+1) runs under the stores
+//   warps 4..19  epilogue: drain O(i) -> E1(i+1) -> normalise + store (i), so MMA2(i+1) runs under the stores;
+//                four threads per row (64 columns each): 16 warps hide the load / TMEM / barrier latencies that
+//                8 warps could not (ncu: issue slots 22 % active, long-scoreboard + barrier stalls dominant)
 #include "common.cuh"
 
 namespace csam {
 
 constexpr int I2T_BM = 128;
-constexpr int I2T_THREADS = 384;
+constexpr int I2T_THREADS = 640;                 // 4 control warps + 16 epilogue warps (4 per TMEM lane quadrant)
 constexpr int I2T_KB1 = 6;                       // 4 k-blocks of X (256) + 2 of PEQ (128)
 constexpr int I2T_STAGES = 2;
 constexpr int I2T_A_BYTES = 128 * 64 * 2;        // 16 KB per operand half
@@ -34,7 +36,7 @@ constexpr int I2T_OFF_B2 = I2T_STAGES * I2T_STAGE_BYTES;
 constexpr int I2T_OFF_P = I2T_OFF_B2 + 2 * I2T_B2_BYTES;
 constexpr int I2T_OFF_BAR = I2T_OFF_P + 2 * I2T_P_BYTES;
 constexpr int I2T_OFF_EPI = I2T_OFF_BAR + 256;
-constexpr int I2T_SMEM_BYTES = I2T_OFF_EPI + (4 * 128 + 3 * 256) * 4;
+constexpr int I2T_SMEM_BYTES = I2T_OFF_EPI + (8 * 128 + 3 * 256) * 4;
 static_assert(I2T_SMEM_BYTES <= 227 * 1024, "i2t layer shared memory budget");
 
 struct I2TBars {
@@ -67,7 +69,7 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   I2TBars* bars = reinterpret_cast<I2TBars*>(smem + I2T_OFF_BAR);
-  float* epi = reinterpret_cast<float*>(smem + I2T_OFF_EPI);   // ex_sum[2][128] ex_sq[2][128] gamma beta bias
+  float* epi = reinterpret_cast<float*>(smem + I2T_OFF_EPI);   // ex_sum[4][128] ex_sq[4][128] gamma beta bias
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // contiguous tile range per CTA: consecutive tiles share a prompt, so B2 is loaded about once per 32 tiles
   const int t0 = (int)((long long)a.tiles * blockIdx.x / gridDim.x);
@@ -79,10 +81,10 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < I2T_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&bars->s_full[b], 1); mbar_init(&bars->s_empty[b], 8); }
-    mbar_init(&bars->p_full, 8);
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars->s_full[b], 1); mbar_init(&bars->s_empty[b], 16); }
+    mbar_init(&bars->p_full, 16);
     mbar_init(&bars->o_full, 1);
-    mbar_init(&bars->o_empty, 8);
+    mbar_init(&bars->o_empty, 16);
     mbar_init(&bars->b2_full, 1);
     mbar_init(&bars->b2_empty, 1);
     fence_barrier_init();
@@ -95,9 +97,9 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0; int b2_cnt = 0;
+      const uint64_t keep = l2_policy_evict_last();
       for (int t = t0; t < t1; ++t) {
         const int p = t >> 5, mrow = (t & 31) * I2T_BM;
         const int arow = a.x_shared ? mrow : t * I2T_BM;
@@ -107,8 +109,8 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
           uint8_t* sb = sa + 2 * I2T_A_BYTES;
           mbar_expect_tx(&bars->full[stage], I2T_STAGE_BYTES);
           if (kb < 4) {
-            tma_load_2d(sa, &tx_hi, &bars->full[stage], kb * 64, arow);
-            tma_load_2d(sa + I2T_A_BYTES, &tx_lo, &bars->full[stage], kb * 64, arow);
+            tma_load_2d_hint(sa, &tx_hi, &bars->full[stage], kb * 64, arow, keep);
+            tma_load_2d_hint(sa + I2T_A_BYTES, &tx_lo, &bars->full[stage], kb * 64, arow, keep);
           } else {
             tma_load_2d(sa, &tq_hi, &bars->full[stage], (kb - 4) * 64, mrow);
             tma_load_2d(sa + I2T_A_BYTES, &tq_lo, &bars->full[stage], (kb - 4) * 64, mrow);
@@ -129,7 +131,6 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (lane == 0) {
       constexpr uint32_t idesc1 = umma_idesc_f16(I2T_BM, 64, 0, 0);
       constexpr uint32_t idesc2 = umma_idesc_f16(I2T_BM, 256, 0, 0);
@@ -177,41 +178,40 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
         if (t + 1 == t1 || ((t + 1) & 31) == 0) umma_commit(&bars->b2_empty);   // last tile of this prompt here
       }
     }
-  } else if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  } else {
-    // ------------------------------------------------------------------ epilogue (8 warps)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (16 warps)
     const int ew = warp - 4;
     const int q = ew & 3;                        // TMEM lane quadrant == warp % 4
-    const int ch = ew >> 2;                      // which half of the columns (S: 32 of 64, O: 128 of 256)
+    const int cq = ew >> 2;                      // column quarter (S: 16 of 64 columns, O: 64 of 256)
     const int r = q * 32 + lane;                 // row of the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int et = threadIdx.x - 128;            // 0..255
-    float* ex_sum = epi;                         // [2][128]
-    float* ex_sq = epi + 256;                    // [2][128]
-    float* s_gamma = epi + 512;
+    const int et = threadIdx.x - 128;            // 0..511
+    float* ex_sum = epi;                         // [4][128]
+    float* ex_sq = epi + 512;                    // [4][128]
+    float* s_gamma = epi + 1024;
     float* s_beta = s_gamma + 256;
     float* s_bias = s_gamma + 512;
-    s_gamma[et] = a.gamma[et];
-    s_beta[et] = a.beta[et];
-    s_bias[et] = a.bias ? a.bias[et] : 0.f;
-    asm volatile("bar.sync 5, 256;" ::: "memory");
+    if (et < 256) {
+      s_gamma[et] = a.gamma[et];
+      s_beta[et] = a.beta[et];
+      s_bias[et] = a.bias ? a.bias[et] : 0.f;
+    }
+    asm volatile("bar.sync 5, 512;" ::: "memory");
 
-    // E1: softmax over the 7 tokens of each of this thread's 4 heads -> P (hi/lo) in the UMMA K-major layout
+    // E1: softmax over the 7 tokens of each of this thread's 2 heads -> P (hi/lo) in the UMMA K-major layout
     auto softmax_tile = [&](int li) {
       const int b = li & 1;
       mbar_wait(&bars->s_full[b], (li >> 1) & 1);
       tc_fence_after();
-      uint32_t raw[32];
-      tmem_ld32(lane_addr + b * 64 + ch * 32, raw);
+      uint32_t raw[16];
+      tmem_ld16(lane_addr + b * 64 + cq * 16, raw);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->s_empty[b]);
-      uint32_t hi[16], lo[16];
+      uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int hh = 0; hh < 4; ++hh) {
+      for (int hh = 0; hh < 2; ++hh) {
         float s[7];
         float m = -INFINITY;
 #pragma unroll
@@ -234,8 +234,8 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
       }
       uint8_t* pb = smem + I2T_OFF_P + r * 128;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int off = ((ch * 4 + u) ^ (r & 7)) << 4;
+      for (int u = 0; u < 2; ++u) {
+        const int off = ((cq * 2 + u) ^ (r & 7)) << 4;
         *reinterpret_cast<uint4*>(pb + off) = make_uint4(hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
         *reinterpret_cast<uint4*>(pb + I2T_P_BYTES + off) = make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
       }
@@ -247,13 +247,15 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
     if (t0 < t1) softmax_tile(0);
     int li = 0;
     for (int t = t0; t < t1; ++t, ++li) {
-      // residual rows (this lane's 128 columns), requested before the accumulator is waited for
+      // residual rows (this lane's 64 columns), requested before the accumulator is waited for.  The TMA producer
+      // brought the same bytes through L2 about one tile ago: evict-last on that load and evict-first on this
+      // kernel's output stores keep them there (without the hints ncu showed every residual byte re-read from HBM).
       const size_t xrow = (size_t)(a.x_shared ? (t & 31) * I2T_BM + r : t * I2T_BM + r);
-      const __half* ph = a.x_hi + xrow * 256 + ch * 128;
-      const __half* pl = a.x_lo + xrow * 256 + ch * 128;
-      float x[128];
+      const __half* ph = a.x_hi + xrow * 256 + cq * 64;
+      const __half* pl = a.x_lo + xrow * 256 + cq * 64;
+      float x[64];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         uint32_t hw[8], lw[8];
         ldg256(ph + i * 16, hw);
         ldg256(pl + i * 16, lw);
@@ -269,13 +271,13 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
       tc_fence_after();
       float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 128; c += 16) {
+      for (int c = 0; c < 64; c += 16) {
         uint32_t raw[16];
-        tmem_ld16(lane_addr + 128 + ch * 128 + c, raw);
+        tmem_ld16(lane_addr + 128 + cq * 64 + c, raw);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          const float4 bb = *reinterpret_cast<const float4*>(s_bias + ch * 128 + c + j);
+          const float4 bb = *reinterpret_cast<const float4*>(s_bias + cq * 64 + c + j);
           x[c + j + 0] += __uint_as_float(raw[j + 0]) + bb.x;
           x[c + j + 1] += __uint_as_float(raw[j + 1]) + bb.y;
           x[c + j + 2] += __uint_as_float(raw[j + 2]) + bb.z;
@@ -288,19 +290,19 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->o_empty);
       if (t + 1 < t1) softmax_tile(li + 1);
-      ex_sum[ch * 128 + r] = sum;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-      const float mean = (ex_sum[r] + ex_sum[128 + r]) * (1.0f / 256.0f);
+      ex_sum[cq * 128 + r] = sum;
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+      const float mean = ((ex_sum[r] + ex_sum[128 + r]) + (ex_sum[256 + r] + ex_sum[384 + r])) * (1.0f / 256.0f);
       float sq = 0.f;
 #pragma unroll
-      for (int j = 0; j < 128; ++j) { const float d = x[j] - mean; sq = fmaf(d, d, sq); }
-      ex_sq[ch * 128 + r] = sq;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-      const float rstd = 1.0f / sqrtf((ex_sq[r] + ex_sq[128 + r]) * (1.0f / 256.0f) + a.eps);
+      for (int j = 0; j < 64; ++j) { const float d = x[j] - mean; sq = fmaf(d, d, sq); }
+      ex_sq[cq * 128 + r] = sq;
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+      const float rstd = 1.0f / sqrtf(((ex_sq[r] + ex_sq[128 + r]) + (ex_sq[256 + r] + ex_sq[384 + r])) * (1.0f / 256.0f) + a.eps);
       const size_t orow = (size_t)t * I2T_BM + r;
 #pragma unroll
-      for (int c = 0; c < 128; c += 16) {
-        const int col = ch * 128 + c;
+      for (int c = 0; c < 64; c += 16) {
+        const int col = cq * 64 + c;
         float y[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
@@ -311,7 +313,7 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
           y[j + 2] = (x[c + j + 2] - mean) * rstd * g.z + bt.z;
           y[j + 3] = (x[c + j + 3] - mean) * rstd * g.w + bt.w;
         }
-        store_pair16(a.out_hi, a.out_lo, orow * 256 + col, y);
+        store_pair16_stream(a.out_hi, a.out_lo, orow * 256 + col, y);
       }
     }
   }
@@ -333,7 +335,7 @@ dec_fold_i2t_kernel(const float* __restrict__ kt, const float* __restrict__ vt, 
   constexpr float SC = 0.25f * 1.4426950408889634f;
   for (int i = c; i < 7 * 128; i += 256) {
     ks[i >> 7][i & 127] = kt[(size_t)p * 896 + i] * SC;
-    vs[i >> 7][i & 127] = vt[(size_t)p * 896 + i];
+    vs[i >> 7][i & 127] = vt ? vt[(size_t)p * 896 + i] : 0.f;
   }
   __syncthreads();
   __half* r1h = b1_hi + (size_t)p * 64 * 384;
@@ -356,6 +358,7 @@ dec_fold_i2t_kernel(const float* __restrict__ kt, const float* __restrict__ vt, 
       }
     }
   }
+  if (!vt) return;                     // token -> image folding needs B1 only
   float o[64];
   const float* wrow = wo + (size_t)c * 128;
 #pragma unroll
@@ -379,6 +382,318 @@ dec_fold_i2t_kernel(const float* __restrict__ kt, const float* __restrict__ vt, 
   const size_t ob = ((size_t)p * 256 + c) * 64;
 #pragma unroll
   for (int i = 0; i < 64; i += 8) store_pair8(b2_hi, b2_lo, ob + i, o + i);
+}
+
+
+// =====================================================================================================
+// K-T2I: token -> image cross attention with the k / v projections folded away (transformer.py:171-176,
+// 104-112; Attention.forward :228-254).  Reference, per prompt: k = k_proj(x + pe), v = v_proj(x) for the 4096
+// image tokens x; the 7 prompt tokens attend over them with 8 heads x 16.  Here
+//     scores[x, (h,i)] = x . B1[(h,i), 0:256] + pek[x] . B1[(h,i), 256:384]     (B1 from csam_dec_fold_t2i: q tokens, Wk)
+//     xbar[(h,i), :]   = sum_x softmax_x(scores)[x, (h,i)] * x                  (a 256-vector per head and token)
+//     out[i, h*16+d]   = Wv[h*16+d, :] . xbar[(h,i), :] + b_v                   (csam_dec_t2i_out, tiny)
+// so the kernel reads the keys once (1 KB per row) and the [P*4096, 256] k | v stream of the unfused path
+// (4 KB per row written + read) never exists.  One CTA owns a prompt; per 128-key tile:
+//     MMA1  S[128 keys, 64] = [X | PEK] (K = 384) * B1^T
+//     softmax over KEYS: one thread per key row; the column maxima live in shared memory and may lag by
+//           2^8, so the common path is exp2(s - m[c]) and a block-wide vote; a violated bound triggers
+//           an exact column maximum (warp shuffles) and a rescale of the accumulator in TMEM
+//     MMA2  XBAR^T[256, 64] += X^T (MN-major A straight from the resident X tile) * P (MN-major B, h16 pair)
+// The X tile (128 KB as hi + lo) stays in shared memory from MMA1 to MMA2, so tiles are processed one
+// at a time; the next tile is prefetched into L2 meanwhile.
+constexpr int T2I_THREADS = 256;
+constexpr int T2I_SLOT = 32768;                  // one X / PEK k-block: hi 16 KB | lo 16 KB
+constexpr int T2I_OFF_PEK = 4 * T2I_SLOT;
+constexpr int T2I_OFF_B1 = T2I_OFF_PEK + T2I_SLOT;             // 2-stage ring of B1 k-blocks (hi 8 KB | lo 8 KB)
+constexpr int T2I_OFF_P = T2I_OFF_B1 + 2 * 2 * I2T_B1_BYTES;   // P [128 keys][64] fp16, hi then lo
+constexpr int T2I_OFF_BAR = T2I_OFF_P + 2 * 16384;            // P hi | P lo
+constexpr int T2I_OFF_ST = T2I_OFF_BAR + 256;                  // m[64] l[64] alpha[64] wmax[4][64]
+constexpr int T2I_SMEM_BYTES = T2I_OFF_ST + (3 * 64 + 4 * 64) * 4;
+static_assert(T2I_SMEM_BYTES <= 227 * 1024, "t2i shared memory budget");
+constexpr float T2I_TAU = 8.f;
+
+struct T2IBars {
+  uint64_t x_full[4], x_empty, pek_full, pek_empty, b_full[2], b_empty[2];
+  uint64_t s_full, s_empty, p_full, pv_done;
+  uint32_t tmem_slot;
+};
+
+struct T2IParams {
+  int x_shared, P;
+  float* xbar;               // [P, 64, 256]
+};
+
+__global__ void __launch_bounds__(T2I_THREADS, 1)
+dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant__ CUtensorMap tx_lo,
+               const __grid_constant__ CUtensorMap tk_hi, const __grid_constant__ CUtensorMap tk_lo,
+               const __grid_constant__ CUtensorMap tb1_hi, const __grid_constant__ CUtensorMap tb1_lo, T2IParams a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  T2IBars* bars = reinterpret_cast<T2IBars*>(smem + T2I_OFF_BAR);
+  float* st_m = reinterpret_cast<float*>(smem + T2I_OFF_ST);
+  float* st_l = st_m + 64;
+  float* st_alpha = st_m + 128;
+  float* st_wmax = st_m + 192;                     // [4][64]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tx_hi); tma_prefetch_desc(&tx_lo); tma_prefetch_desc(&tk_hi); tma_prefetch_desc(&tk_lo);
+    tma_prefetch_desc(&tb1_hi); tma_prefetch_desc(&tb1_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bars->x_full[i], 1);
+    mbar_init(&bars->x_empty, 1);
+    mbar_init(&bars->pek_full, 1); mbar_init(&bars->pek_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
+    mbar_init(&bars->s_full, 1); mbar_init(&bars->s_empty, 4);
+    mbar_init(&bars->p_full, 4); mbar_init(&bars->pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<256>(&bars->tmem_slot);
+  if (threadIdx.x < 64) { st_m[threadIdx.x] = -INFINITY; st_l[threadIdx.x] = 0.f; }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_slot;      // S [0,64)  XBAR^T features 0..127 [64,128)  128..255 [128,192)
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int tl = 0, bcnt = 0, pcnt = 0;
+      for (int p = blockIdx.x; p < a.P; p += gridDim.x) {
+        for (int ti = 0; ti < 32; ++ti, ++tl) {
+          const int mrow = ti * 128;
+          const int arow = a.x_shared ? mrow : p * 4096 + mrow;
+          for (int kb = 0; kb < 6; ++kb) {
+            if (kb == 0) mbar_wait(&bars->x_empty, (tl & 1) ^ 1);      // MMA2 of the previous tile has retired
+            if (kb < 4) {
+              uint8_t* sx = smem + kb * T2I_SLOT;
+              mbar_expect_tx(&bars->x_full[kb], T2I_SLOT);
+              tma_load_2d(sx, &tx_hi, &bars->x_full[kb], kb * 64, arow);
+              tma_load_2d(sx + 16384, &tx_lo, &bars->x_full[kb], kb * 64, arow);
+            } else {
+              mbar_wait(&bars->pek_empty, (pcnt & 1) ^ 1);
+              uint8_t* sx = smem + T2I_OFF_PEK;
+              mbar_expect_tx(&bars->pek_full, T2I_SLOT);
+              tma_load_2d(sx, &tk_hi, &bars->pek_full, (kb - 4) * 64, mrow);
+              tma_load_2d(sx + 16384, &tk_lo, &bars->pek_full, (kb - 4) * 64, mrow);
+              ++pcnt;
+            }
+            const int bs = bcnt & 1;
+            mbar_wait(&bars->b_empty[bs], ((bcnt >> 1) & 1) ^ 1);
+            uint8_t* sb = smem + T2I_OFF_B1 + bs * 2 * I2T_B1_BYTES;
+            mbar_expect_tx(&bars->b_full[bs], 2 * I2T_B1_BYTES);
+            tma_load_2d(sb, &tb1_hi, &bars->b_full[bs], kb * 64, p * 64);
+            tma_load_2d(sb + I2T_B1_BYTES, &tb1_lo, &bars->b_full[bs], kb * 64, p * 64);
+            ++bcnt;
+          }
+          // pull the next tile of X towards L2 while this one is being consumed
+          if (ti + 1 < 32) {
+            for (int kb = 0; kb < 4; ++kb) {
+              tma_prefetch_l2_2d(&tx_hi, kb * 64, arow + 128);
+              tma_prefetch_l2_2d(&tx_lo, kb * 64, arow + 128);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = umma_idesc_f16(128, 64, 0, 0);
+      constexpr uint32_t idesc2 = umma_idesc_f16(128, 64, 1, 1);     // A = X^T and B = P, both MN-major
+      int tl = 0, bcnt = 0, pcnt = 0;
+      for (int p = blockIdx.x; p < a.P; p += gridDim.x) {
+        for (int ti = 0; ti < 32; ++ti, ++tl) {
+          mbar_wait(&bars->s_empty, (tl & 1) ^ 1);
+          tc_fence_after();
+          for (int kb = 0; kb < 6; ++kb) {
+            uint32_t sa;
+            if (kb < 4) {
+              mbar_wait(&bars->x_full[kb], tl & 1);
+              sa = smem_u32(smem + kb * T2I_SLOT);
+            } else {
+              mbar_wait(&bars->pek_full, pcnt & 1);
+              sa = smem_u32(smem + T2I_OFF_PEK);
+            }
+            const int bs = bcnt & 1;
+            mbar_wait(&bars->b_full[bs], (bcnt >> 1) & 1);
+            tc_fence_after();
+            const uint32_t ad = umma_desc_lo(sa, 16);
+            const uint32_t bd = umma_desc_lo(smem_u32(smem + T2I_OFF_B1 + bs * 2 * I2T_B1_BYTES), 16);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_f16_w(tmem_base, ad + 2 * k, bd + 2 * k, idesc1, (kb | k) ? 1u : 0u);
+              umma_f16_w(tmem_base, ad + (16384 >> 4) + 2 * k, bd + 2 * k, idesc1, 1u);
+              umma_f16_w(tmem_base, ad + 2 * k, bd + (I2T_B1_BYTES >> 4) + 2 * k, idesc1, 1u);
+            }
+            umma_commit(&bars->b_empty[bs]);
+            ++bcnt;
+            if (kb >= 4) { umma_commit(&bars->pek_empty); ++pcnt; }
+          }
+          umma_commit(&bars->s_full);
+          mbar_wait(&bars->p_full, tl & 1);        // P stored, accumulator rescaled if the maxima moved
+          tc_fence_after();
+          const uint32_t pd = umma_desc_lo(smem_u32(smem + T2I_OFF_P), 8192);
+#pragma unroll
+          for (int fb = 0; fb < 2; ++fb) {
+            const uint32_t xd = umma_desc_lo(smem_u32(smem + 2 * fb * T2I_SLOT), T2I_SLOT);   // LBO: next 64 features
+            const uint32_t d = tmem_base + 64 + fb * 64;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {           // 16 keys per step = 16 rows of 128 B
+              umma_f16_w(d, xd + 128 * k, pd + 128 * k, idesc2, (ti | k) ? 1u : 0u);
+              umma_f16_w(d, xd + (16384 >> 4) + 128 * k, pd + 128 * k, idesc2, 1u);
+              umma_f16_w(d, xd + 128 * k, pd + (16384 >> 4) + 128 * k, idesc2, 1u);
+            }
+          }
+          umma_commit(&bars->x_empty);
+          umma_commit(&bars->pv_done);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax over keys (4 warps, one key row per thread)
+    const int wq = warp - 4;                       // TMEM lane quadrant == warp % 4
+    const int r = wq * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
+    int tl = 0;
+    for (int p = blockIdx.x; p < a.P; p += gridDim.x) {
+      float lsum[64];
+#pragma unroll
+      for (int c = 0; c < 64; ++c) lsum[c] = 0.f;
+      for (int ti = 0; ti < 32; ++ti, ++tl) {
+        mbar_wait(&bars->s_full, tl & 1);
+        tc_fence_after();
+        uint32_t raw[64];
+        tmem_ld32(lane_addr, raw);
+        tmem_ld32(lane_addr + 32, raw + 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->s_empty);
+        bool waited_pv = false;
+        while (true) {
+          // cheap pass first: does any score exceed its column's (stale) maximum by more than 2^TAU ?
+          int viol = 0;
+#pragma unroll
+          for (int c = 0; c < 64; c += 2) {
+            const float2 mm = *reinterpret_cast<const float2*>(st_m + c);
+            viol |= (__uint_as_float(raw[c]) > mm.x + T2I_TAU) | (__uint_as_float(raw[c + 1]) > mm.y + T2I_TAU);
+          }
+          int any;
+          asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %1, 0;\n\tbar.red.or.pred q, 2, 128, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                       : "=r"(any) : "r"(viol) : "memory");
+          if (!any) break;
+          // some column outgrew its (stale) maximum: exact column maxima of this tile, new m, rescale factors
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const float v = warp_max(__uint_as_float(raw[c]));
+            if (lane == 0) st_wmax[wq * 64 + c] = v;
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (r < 64) {
+            const float mo = st_m[r];
+            const float mn = fmaxf(fmaxf(mo, fmaxf(st_wmax[r], st_wmax[64 + r])), fmaxf(st_wmax[128 + r], st_wmax[192 + r]));
+            st_alpha[r] = ex2f_approx(mo - mn);      // first tile of a prompt: exp2(-inf) = 0
+            st_m[r] = mn;
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (ti > 0) {
+            if (!waited_pv) { mbar_wait(&bars->pv_done, (tl - 1) & 1); tc_fence_after(); waited_pv = true; }
+#pragma unroll
+            for (int hh = 0; hh < 4; ++hh) {         // this lane's feature row of both accumulator halves
+              uint32_t o[32];
+              tmem_ld32(lane_addr + 64 + hh * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * st_alpha[(hh & 1) * 32 + c]);
+              tmem_st32(lane_addr + 64 + hh * 32, o);
+            }
+            tmem_st_wait();
+#pragma unroll
+            for (int c = 0; c < 64; ++c) lsum[c] *= st_alpha[c];
+          }
+        }
+        uint32_t ph[32], pl[32];
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) {
+          const float2 mm = *reinterpret_cast<const float2*>(st_m + c);
+          const float p0 = ex2f_approx(__uint_as_float(raw[c]) - mm.x);
+          const float p1 = ex2f_approx(__uint_as_float(raw[c + 1]) - mm.y);
+          lsum[c] += p0;
+          lsum[c + 1] += p1;
+          __half2 h2, l2;
+          split_h2(p0, p1, h2, l2);
+          ph[c >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+          pl[c >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        if (tl > 0 && !waited_pv) { mbar_wait(&bars->pv_done, (tl - 1) & 1); tc_fence_after(); }   // P buffer free
+        uint8_t* pb = smem + T2I_OFF_P + r * 128;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int off = (u ^ (r & 7)) << 4;
+          *reinterpret_cast<uint4*>(pb + off) = make_uint4(ph[4 * u], ph[4 * u + 1], ph[4 * u + 2], ph[4 * u + 3]);
+          *reinterpret_cast<uint4*>(pb + 16384 + off) = make_uint4(pl[4 * u], pl[4 * u + 1], pl[4 * u + 2], pl[4 * u + 3]);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->p_full);
+      }
+      // ---- end of prompt: column sums over all keys, then XBAR = accumulator / l
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        const float v = warp_sum(lsum[c]);
+        if (lane == 0) atomicAdd(&st_l[c], v);
+      }
+      mbar_wait(&bars->pv_done, (tl - 1) & 1);
+      tc_fence_after();
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      float* xo = a.xbar + (size_t)p * 64 * 256;
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        uint32_t o[32];
+        tmem_ld32(lane_addr + 64 + hh * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int col = (hh & 1) * 32 + c;
+          xo[(size_t)col * 256 + (hh >> 1) * 128 + r] = __uint_as_float(o[c]) / st_l[col];
+        }
+      }
+      tc_fence_before();
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (r < 64) { st_m[r] = -INFINITY; st_l[r] = 0.f; }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<256>(tmem_base);
+}
+
+// out[p, i, o] = Wv[o, :] . xbar[p, (o/16)*8 + i, :] + bv[o]   (the v projection applied to the pooled keys)
+__global__ void __launch_bounds__(128)
+dec_t2i_out_kernel(const float* __restrict__ xbar, const float* __restrict__ wv_t /*[256,128]*/, const float* __restrict__ bv,
+                   float* out_f32, __half* out_hi, __half* out_lo) {
+  const int p = blockIdx.x, o = threadIdx.x, h = o >> 4;
+  const float* xb = xbar + ((size_t)p * 64 + h * 8) * 256;
+  float acc[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) acc[i] = 0.f;
+  for (int c = 0; c < 256; ++c) {
+    const float w = wv_t[c * 128 + o];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) acc[i] = fmaf(w, xb[i * 256 + c], acc[i]);
+  }
+  const float b = bv ? bv[o] : 0.f;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const size_t oo = ((size_t)p * 7 + i) * 128 + o;
+    const float v = acc[i] + b;
+    if (out_f32) out_f32[oo] = v;
+    if (out_hi) store_pair(out_hi, out_lo, oo, v);
+  }
 }
 
 }  // namespace csam
@@ -435,4 +750,48 @@ extern "C" int csam_dec_i2t_layer(const csam_i2t_layer_args* a, void* stream) {
   dec_i2t_layer_kernel<<<grid, I2T_THREADS, I2T_SMEM_BYTES, (cudaStream_t)stream>>>(tx_hi, tx_lo, tq_hi, tq_lo, tb1_hi,
                                                                                    tb1_lo, tb2_hi, tb2_lo, p);
   return check_launch("dec_i2t_layer_kernel");
+}
+
+extern "C" int csam_dec_fold_t2i(const float* qt, int P, const float* wk, void* b1_hi, void* b1_lo, void* stream) {
+  CSAM_REQUIRE(qt && wk && b1_hi && b1_lo && P > 0, "csam_dec_fold_t2i: bad args");
+  dec_fold_i2t_kernel<<<P, 256, 0, (cudaStream_t)stream>>>(qt, nullptr, wk, nullptr, static_cast<__half*>(b1_hi),
+                                                           static_cast<__half*>(b1_lo), nullptr, nullptr);
+  return check_launch("dec_fold_i2t_kernel");
+}
+
+extern "C" int csam_dec_t2i(const csam_t2i_args* a, void* stream) {
+  CSAM_REQUIRE(a && a->x_hi && a->x_lo && a->pek_hi && a->pek_lo && a->b1_hi && a->b1_lo && a->xbar && a->wv_t &&
+                   (a->out_f32 || a->out_hi),
+               "csam_dec_t2i: null operand (h16 pairs with both halves are required)");
+  CSAM_REQUIRE(a->P > 0 && a->P <= (1 << 16), "csam_dec_t2i: prompt count");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  CSAM_REQUIRE(al16(a->x_hi) && al16(a->x_lo) && al16(a->pek_hi) && al16(a->pek_lo) && al16(a->b1_hi) && al16(a->b1_lo),
+               "csam_dec_t2i: 16-byte alignment");
+  const uint64_t xrows = a->x_shared ? 4096ull : (uint64_t)a->P * 4096ull;
+  CUtensorMap tx_hi, tx_lo, tk_hi, tk_lo, tb1_hi, tb1_lo;
+  if (make_tmap_2d_f16(&tx_hi, a->x_hi, xrows, 256, 256, 128, 64)) return 1;
+  if (make_tmap_2d_f16(&tx_lo, a->x_lo, xrows, 256, 256, 128, 64)) return 1;
+  if (make_tmap_2d_f16(&tk_hi, a->pek_hi, 4096, 128, 128, 128, 64)) return 1;
+  if (make_tmap_2d_f16(&tk_lo, a->pek_lo, 4096, 128, 128, 128, 64)) return 1;
+  if (make_tmap_2d_f16(&tb1_hi, a->b1_hi, (uint64_t)a->P * 64, 384, 384, 64, 64)) return 1;
+  if (make_tmap_2d_f16(&tb1_lo, a->b1_lo, (uint64_t)a->P * 64, 384, 384, 64, 64)) return 1;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(dec_t2i_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2I_SMEM_BYTES) != cudaSuccess)
+      return fail("%s", "cudaFuncSetAttribute(smem) failed for dec_t2i_kernel");
+    attr = true;
+  }
+  T2IParams p;
+  p.x_shared = a->x_shared ? 1 : 0;
+  p.P = a->P;
+  p.xbar = a->xbar;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = a->P < sms ? a->P : sms;
+  dec_t2i_kernel<<<grid, T2I_THREADS, T2I_SMEM_BYTES, (cudaStream_t)stream>>>(tx_hi, tx_lo, tk_hi, tk_lo, tb1_hi, tb1_lo, p);
+  if (check_launch("dec_t2i_kernel")) return 1;
+  dec_t2i_out_kernel<<<a->P, 128, 0, (cudaStream_t)stream>>>(a->xbar, a->wv_t, a->bv, a->out_f32,
+                                                             static_cast<__half*>(a->out_hi), static_cast<__half*>(a->out_lo));
+  return check_launch("dec_t2i_out_kernel");
 }

@@ -266,6 +266,15 @@ class MaskDecoderEngine:
             Lr["i2t_wq"] = _f(sd, Lp + ".q_proj.weight", dev)
             Lr["i2t_wo"] = _f(sd, Lp + ".out_proj.weight", dev)
             Lr["peq_h"] = H16.from_f32(self.pe_qi[i], True)
+        # Fused token->image attention (csam_dec_t2i): k_proj is folded into the query side, v_proj is applied to
+        # the softmax-pooled keys, so no [P,4096,256] k | v stream is produced at all.
+        self.fused_t2i = self.fused_i2t and os.environ.get("CSAM_DEC_FUSED_T2I", "1") != "0"
+        self.t2i_fold = []
+        for name, pek in ((f"{t}.layers.0.cross_attn_token_to_image", self.pe_k[0]),
+                          (f"{t}.layers.1.cross_attn_token_to_image", self.pe_k[1]), (fin, self.pe_kf)):
+            self.t2i_fold.append(dict(wk=_f(sd, name + ".k_proj.weight", dev),
+                                      wv_t=_f(sd, name + ".v_proj.weight", dev).t().contiguous(),
+                                      bv=_f(sd, name + ".v_proj.bias", dev), pek_h=H16.from_f32(pek, True)))
         self.w_kvf = cat_w([fin + ".k_proj", fin + ".v_proj"])
         bvf = sd[fin + ".v_proj.bias"].detach().float().to(dev)
         self.res_kvf = torch.cat([self.pe_kf, bvf[None, :].expand(4096, -1)], 1).contiguous()
@@ -295,14 +304,19 @@ class MaskDecoderEngine:
         L0 = self.layers[0]
         keys0, keys0_h, _ = ops.layernorm(feat_tok, normalize=False, add=self.no_mask, add_mod=1,
                                           want_f32=True, want_h16=True, split=split)
-        k0, _ = ops.gemm(keys0_h, L0["t2i"].k.w, residual=self.pe_k[0], want_f32=True)
-        v0, _ = L0["t2i"].v(keys0_h, want_f32=True)
-        q0, _ = ops.gemm(keys0_h, L0["i2t"].q.w, residual=self.pe_qi[0], want_f32=True)
+        k0 = v0 = q0 = None
+        if not self.fused_t2i:
+            k0, _ = ops.gemm(keys0_h, L0["t2i"].k.w, residual=self.pe_k[0], want_f32=True)
+            v0, _ = L0["t2i"].v(keys0_h, want_f32=True)
+            k0, v0 = k0.view(1, 4096, 128), v0.view(1, 4096, 128)
+        if not self.fused_i2t:
+            q0, _ = ops.gemm(keys0_h, L0["i2t"].q.w, residual=self.pe_qi[0], want_f32=True)
+            q0 = q0.view(1, 4096, 128)
         dproj, dproj_h = self.dino_proj(dino_tok_h, want_f32=True, want_h16=True)      # [5329,256]
         planes = ops.transpose_f32(dproj).view(256, 73, 73)
         dmap = ops.bilinear(planes, 256, 256, chlast=False)                            # [256,256,256]
         _, dmap_h, _ = ops.layernorm(dmap.view(256 * 32, 2048), normalize=False, want_h16=True, split=split)
-        self.img = dict(keys0=keys0, keys0_h=keys0_h, k0=k0.view(1, 4096, 128), v0=v0.view(1, 4096, 128), q0=q0.view(1, 4096, 128),
+        self.img = dict(keys0=keys0, keys0_h=keys0_h, k0=k0, v0=v0, q0=q0,
                         dproj_h=dproj_h, dmap_h=dmap_h.view(256, 65536))
 
     def fg_logits(self) -> torch.Tensor:
@@ -346,7 +360,11 @@ class MaskDecoderEngine:
             # (2) token -> image cross attention (transformer.py:171-176)
             ta = Lr["t2i"]
             qc, _ = ta.q(q_pe_h, want_f32=True)
-            if li == 0:
+            if self.fused_t2i:
+                F = self.t2i_fold[li]
+                b1t = ops.dec_fold_t2i(qc.view(P, 7, 128), F["wk"])
+                _, a = ops.dec_t2i(I["keys0_h"] if li == 0 else keys_h, li == 0, F["pek_h"], b1t, P, F["wv_t"], F["bv"])
+            elif li == 0:
                 kc, vc = I["k0"], I["v0"]
             elif self.fused_i2t:
                 kv1, _ = ops.gemm(keys_h, self.w_kv1, residual=self.res_kv1, res_mod=4096, want_f32=True)
@@ -356,7 +374,8 @@ class MaskDecoderEngine:
                 kvq, _ = ops.gemm(keys_h, self.w_kvq1, residual=self.res_kvq1, res_mod=4096, want_f32=True)
                 kvq = kvq.view(P, 4096, 384)
                 kc, vc, qi1 = kvq[:, :, 0:128], kvq[:, :, 128:256], kvq[:, :, 256:384]
-            _, a = ops.attn_few_queries(qc.view(P, 7, 128), kc, vc, P, 7, 4096, 8, 16, want_h16=True, split=split)
+            if not self.fused_t2i:
+                _, a = ops.attn_few_queries(qc.view(P, 7, 128), kc, vc, P, 7, 4096, 8, 16, want_h16=True, split=split)
             pre, _ = ta.o(a.view(T, 128), residual=queries, want_f32=True)
             queries, q_h, _ = ln(pre, Lr["n2"][0], Lr["n2"][1], 1e-5, want_f32=True, want_h16=True, split=split)
             # (3) MLP (transformer.py:178-182)
@@ -398,13 +417,19 @@ class MaskDecoderEngine:
         # final token -> image attention (transformer.py:104-112)
         fa = self.final
         qc, _ = fa.q(q_pe_h, want_f32=True)
-        kv, _ = ops.gemm(keys_h, self.w_kvf, residual=self.res_kvf, res_mod=4096, want_f32=True)
-        kv = kv.view(P, 4096, 256)
-        kc, vc = kv[:, :, 0:128], kv[:, :, 128:256]
-        _, a = ops.attn_few_queries(qc.view(P, 7, 128), kc, vc, P, 7, 4096, 8, 16, want_h16=True, split=split)
+        if self.fused_t2i:
+            F = self.t2i_fold[2]
+            b1t = ops.dec_fold_t2i(qc.view(P, 7, 128), F["wk"])
+            _, a = ops.dec_t2i(keys_h, False, F["pek_h"], b1t, P, F["wv_t"], F["bv"])
+        else:
+            kv, _ = ops.gemm(keys_h, self.w_kvf, residual=self.res_kvf, res_mod=4096, want_f32=True)
+            kv = kv.view(P, 4096, 256)
+            kc, vc = kv[:, :, 0:128], kv[:, :, 128:256]
+            _, a = ops.attn_few_queries(qc.view(P, 7, 128), kc, vc, P, 7, 4096, 8, 16, want_h16=True, split=split)
+            del kc, vc, kv
         pre, _ = fa.o(a.view(T, 128), residual=queries, want_f32=True)
         hs, hs_h, _ = ln(pre, self.nf[0], self.nf[1], 1e-5, want_f32=True, want_h16=True, split=split)
-        del kc, vc, kv, keys_f32, pre
+        del keys_f32, pre
         hs2 = hs_h.view(P, 7 * 256)
 
         def cols(h: H16, c0: int, c1: int) -> H16:

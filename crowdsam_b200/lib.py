@@ -65,6 +65,12 @@ class I2TArgs(C.Structure):
                 ("out_hi", vp), ("out_lo", vp)]
 
 
+class T2IArgs(C.Structure):
+    _fields_ = [("x_hi", vp), ("x_lo", vp), ("x_shared", ci), ("pek_hi", vp), ("pek_lo", vp),
+                ("b1_hi", vp), ("b1_lo", vp), ("P", ci), ("xbar", vp), ("wv_t", vp), ("bv", vp),
+                ("out_f32", vp), ("out_hi", vp), ("out_lo", vp)]
+
+
 class PostArgs(C.Structure):
     _fields_ = [("low", vp), ("P", ci), ("sel", vp), ("planes", ci),
                 ("in_h", ci), ("in_w", ci), ("out_h", ci), ("out_w", ci),
@@ -91,6 +97,8 @@ _SIGS = {
     "csam_attn_few_queries": (ci, [C.POINTER(DecAttnArgs), vp]),
     "csam_dec_fold_i2t": (ci, [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp]),
     "csam_dec_i2t_layer": (ci, [C.POINTER(I2TArgs), vp]),
+    "csam_dec_fold_t2i": (ci, [vp, ci, vp, vp, vp, vp]),
+    "csam_dec_t2i": (ci, [C.POINTER(T2IArgs), vp]),
     "csam_upscale_shuffle_ln_gelu": (ci, [vp, ci, vp, vp, cf, vp, vp, vp]),
     "csam_upscale_hyper_masks": (ci, [vp, ci, vp, vp, vp]),
     "csam_softmax_weights": (ci, [vp, ci, ci, vp, vp, vp, vp]),

@@ -349,6 +349,39 @@ def dec_i2t_layer(x: H16, x_shared: bool, peq: H16, b1: H16, b2: H16, P: int, bi
     return out
 
 
+def dec_fold_t2i(qt: torch.Tensor, wk: torch.Tensor) -> H16:
+    """qt fp32 [P,7,128] = q_proj(tokens + pe), wk fp32 [128,256] -> B1 H16 [P*64,384] (csam_dec_fold_t2i)."""
+    P = qt.shape[0]
+    assert qt.shape == (P, 7, 128) and qt.is_contiguous() and wk.shape == (128, 256) and wk.is_contiguous()
+    b1 = H16.empty((P * 64, 384), True, qt.device)
+    tok = _pb()
+    L.check(L.load().csam_dec_fold_t2i(_p(qt), P, _p(wk), _p(b1.hi), _p(b1.lo), _stream()), "csam_dec_fold_t2i")
+    _pe("dec_fold_t2i", tok, 0.0)
+    return b1
+
+
+def dec_t2i(x: H16, x_shared: bool, pek: H16, b1: H16, P: int, wv_t: torch.Tensor, bv, want_f32=False, want_h16=True):
+    """Token->image cross attention of P prompts over their 4096 image tokens with k_proj / v_proj folded away
+    (csam_dec_t2i) -> (fp32 [P,7,128] or None, H16 [P,7,128] or None): the attention output before out_proj."""
+    assert x.lo is not None and pek.lo is not None and b1.lo is not None
+    assert x.hi.shape == ((4096 if x_shared else P * 4096), 256) and x.hi.is_contiguous() and x.lo.is_contiguous()
+    assert wv_t.shape == (256, 128) and wv_t.is_contiguous()
+    dev = x.hi.device
+    xbar = torch.empty((P, 64, 256), dtype=torch.float32, device=dev)
+    of = torch.empty((P, 7, 128), dtype=torch.float32, device=dev) if want_f32 else None
+    oh = H16.empty((P, 7, 128), True, dev) if want_h16 else None
+    g = L.T2IArgs()
+    g.x_hi, g.x_lo, g.x_shared = _p(x.hi), _p(x.lo), 1 if x_shared else 0
+    g.pek_hi, g.pek_lo, g.b1_hi, g.b1_lo = _p(pek.hi), _p(pek.lo), _p(b1.hi), _p(b1.lo)
+    g.P, g.xbar, g.wv_t, g.bv = P, _p(xbar), _p(wv_t), _p(bv)
+    g.out_f32 = _p(of)
+    g.out_hi, g.out_lo = (_p(oh.hi), _p(oh.lo)) if oh is not None else (None, None)
+    tok = _pb()
+    L.check(L.load().csam_dec_t2i(C.byref(g), _stream()), "csam_dec_t2i")
+    _pe("dec_t2i", tok, float(P) * 4096 * 256 * 4 * (0 if x_shared else 1))     # algorithmic bytes: the keys, once
+    return of, oh
+
+
 def upscale_shuffle_ln_gelu(y1: torch.Tensor, P: int, gamma, beta, eps: float, split: bool) -> H16:
     out = H16.empty((P * 16384, 64), split, y1.device)
     L.check(L.load().csam_upscale_shuffle_ln_gelu(_p(y1), P, _p(gamma), _p(beta), eps, _p(out.hi), _p(out.lo),

@@ -205,6 +205,28 @@ CSAM_API int csam_dec_fold_i2t(const float* kt, const float* vt, int P, const fl
 CSAM_API int csam_dec_i2t_layer(const csam_i2t_layer_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K-T2I  token->image cross attention with k_proj / v_proj folded away (transformer.py:171-176 and the final
+ * attention :104-112, Attention.forward :228-254): the 7 tokens of a prompt attend over its 4096 image tokens.
+ *   csam_dec_fold_t2i: qt fp32 [P,7,128] = q_proj(tokens + pe), wk fp32 [128,256] (k_proj.weight)
+ *                      -> b1 h16 pair [P*64, 384] (same layout as csam_dec_fold_i2t's B1);
+ *   csam_dec_t2i: x h16 pair [P*4096,256] (or [4096,256] when x_shared), pek h16 pair [4096,128] = pe Wk^T + b_k,
+ *     xbar fp32 scratch [P,64,256] (softmax-pooled keys per head and token), wv_t fp32 [256,128] = v_proj.weight^T,
+ *     bv = v_proj.bias -> out fp32 and/or h16 pair [P,7,128] = the attention output BEFORE out_proj.
+ * Reads the keys once; the k | v projection stream of the unfused path never exists.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* x_hi; const void* x_lo; int x_shared;
+  const void* pek_hi; const void* pek_lo;
+  const void* b1_hi; const void* b1_lo;
+  int P;
+  float* xbar;
+  const float* wv_t; const float* bv;
+  float* out_f32; void* out_hi; void* out_lo;
+} csam_t2i_args;
+CSAM_API int csam_dec_fold_t2i(const float* qt, int P, const float* wk, void* b1_hi, void* b1_lo, void* stream);
+CSAM_API int csam_dec_t2i(const csam_t2i_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Mask upscaling tail (mask_decoder.py:56-62,173-181).
  * shuffle_ln_gelu: ConvT1 GEMM output [P*4096, 4*64] (col = (dy*2+dx)*64 + c) -> LN2d over the
  *   64 channels + GELU -> h16 pair [P*16384, 64] with row = p*16384 + (2y+dy)*128 + (2x+dx).

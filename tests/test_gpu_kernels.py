@@ -612,3 +612,33 @@ def test_decoder_fused_i2t_layer(shared, P):
     a = att.permute(0, 2, 1, 3).reshape(P, 4096, 128)
     y = torch.nn.functional.layer_norm(xd + a @ wo.double().T + bo.double(), (256,), gam.double(), bet.double(), 1e-5)
     assert _rel(out.float().view(P, 4096, 256), y) < 2e-5
+
+
+@pytest.mark.parametrize("shared,P", [(True, 3), (False, 2), (False, 150)])
+def test_decoder_fused_t2i(shared, P):
+    """csam_dec_fold_t2i + csam_dec_t2i against the reference formulation of the token->image attention
+    (transformer.py:171-176, 228-254) in fp64: k_proj(x + pe), v_proj(x), 8 heads x 16, softmax over the 4096 image
+    tokens.  P = 150 makes some CTAs own two prompts (state reset between prompts)."""
+    o = ops()
+    g = torch.Generator().manual_seed(41 + P)
+    rows = 4096 if shared else P * 4096
+    x = torch.randn(rows, 256, generator=g)
+    pe = torch.randn(4096, 256, generator=g)
+    wk, bk = torch.randn(128, 256, generator=g) * 0.1, torch.randn(128, generator=g) * 0.1
+    wv, bv = torch.randn(128, 256, generator=g) * 0.1, torch.randn(128, generator=g) * 0.1
+    qt = torch.randn(P, 7, 128, generator=g) * 1.5          # peaked enough to exercise the lazy rescale
+    xh = _h16(x, True)
+    pek_h = _h16((pe.double() @ wk.double().T + bk.double()).float(), True)
+    b1 = o.dec_fold_t2i(qt.to(DEV), wk.to(DEV).contiguous())
+    of, oh = o.dec_t2i(xh, shared, pek_h, b1, P, wv.t().contiguous().to(DEV), bv.to(DEV), want_f32=True, want_h16=True)
+    torch.cuda.synchronize()
+    xd = xh.float().double()                                   # the exact operand values the kernel saw, on the GPU
+    xd = xd.expand(P, 4096, 256) if shared else xd.view(P, 4096, 256)
+    k = xd @ wk.double().T.to(DEV) + pek_h.float().double()[None]
+    v = xd @ wv.double().T.to(DEV) + bv.double().to(DEV)
+    kh = k.view(P, 4096, 8, 16).permute(0, 2, 1, 3)
+    vh = v.view(P, 4096, 8, 16).permute(0, 2, 1, 3)
+    qh = qt.double().to(DEV).view(P, 7, 8, 16).permute(0, 2, 1, 3)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) / 4.0, dim=-1) @ vh).permute(0, 2, 1, 3).reshape(P, 7, 128)
+    assert _rel(of, ref) < 5e-5
+    assert _rel(oh.float(), ref) < 5e-5
