@@ -14,9 +14,9 @@
 // so the [P*4096,128] q and attention-output streams and the separate out_proj GEMM of the unfused path never
 // exist: the layer reads X once (1 KB per row) and writes X' once (1 KB per row).
 //   warp 0       TMA producer  (A / B1 k-blocks through a 2-stage ring; B2 once per prompt)
-//   warp 1       MMA issuer    (MMA1 of tile i+1 is issued before MMA2 of tile i)
+//   warp 1       MMA issuer    (MMA2 of tile i, then MMA1 of tile i+1 while the epilogue normalises tile i)
 //   warp 2       TMEM allocator (S0 S1 O = 64 + 64 + 256 columns)
-//   warps 4..19  epilogue: drain O(i) -> E1(i+1) -> normalise + store (i), so MMA2(i+1) runs under the stores;
+//   warps 4..19  epilogue: residual fetch (i) | drain O(i) -> normalise + store (i) -> E1(i+1);
 //                four threads per row (64 columns each): 16 warps hide the load / TMEM / barrier latencies that
 //                8 warps could not (ncu: issue slots 22 % active, long-scoreboard + barrier stalls dominant)
 #include "common.cuh"
@@ -42,12 +42,13 @@ static_assert(I2T_SMEM_BYTES <= 227 * 1024, "i2t layer shared memory budget");
 struct I2TBars {
   uint64_t full[I2T_STAGES], empty[I2T_STAGES];
   uint64_t s_full[2], s_empty[2];
-  uint64_t p_full, o_full, o_empty, b2_full, b2_empty;
+  uint64_t p_full, o_full, o_empty, b2_full, b2_empty, tile_go;
   uint32_t tmem_slot;
 };
 
 struct I2TParams {
   int x_shared;              // 1: the same 4096 key rows for every prompt (layer 0)
+  int gate;                  // 1: MMA1 of the next tile waits for the epilogue to reach the current one
   int tiles;                 // P * 32
   const __half* x_hi; const __half* x_lo;     // residual = the keys themselves (hi + lo is fp32-accurate)
   const float* bias; const float* gamma; const float* beta; float eps;
@@ -87,6 +88,7 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
     mbar_init(&bars->o_empty, 16);
     mbar_init(&bars->b2_full, 1);
     mbar_init(&bars->b2_empty, 1);
+    mbar_init(&bars->tile_go, 16);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(&bars->tmem_slot);
@@ -103,6 +105,15 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
       for (int t = t0; t < t1; ++t) {
         const int p = t >> 5, mrow = (t & 31) * I2T_BM;
         const int arow = a.x_shared ? mrow : t * I2T_BM;
+        if (a.gate && t > t0) {
+          // tile t may enter L2 only once the epilogue has reached tile t-1 (see the MMA issuer); the k-blocks
+          // beyond the ring depth are requested from HBM right away so the ring's loads find them in L2
+          mbar_wait(&bars->tile_go, (t - t0 - 1) & 1);
+          for (int kb = I2T_STAGES; kb < 4; ++kb) {
+            tma_prefetch_l2_2d(&tx_hi, kb * 64, arow);
+            tma_prefetch_l2_2d(&tx_lo, kb * 64, arow);
+          }
+        }
         for (int kb = 0; kb < I2T_KB1; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * I2T_STAGE_BYTES;
@@ -160,7 +171,6 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
       if (t0 < t1) mma1(0);
       int li = 0;
       for (int t = t0; t < t1; ++t, ++li) {
-        if (t + 1 < t1) mma1(li + 1);
         if (t == t0 || (t & 31) == 0) { mbar_wait(&bars->b2_full, b2_cnt & 1); ++b2_cnt; }
         mbar_wait(&bars->p_full, li & 1);
         mbar_wait(&bars->o_empty, (li & 1) ^ 1);
@@ -176,6 +186,13 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
         }
         umma_commit(&bars->o_full);
         if (t + 1 == t1 || ((t + 1) & 31) == 0) umma_commit(&bars->b2_empty);   // last tile of this prompt here
+        // MMA1(li+1) pulls tile li+1 of the keys through L2; the epilogue re-reads the same rows as its residual one
+        // tile later.  Without this gate MMA1 ran up to 2.5 tiles ahead and the rows had left L2 by then (ncu: every
+        // residual byte came from HBM again); with it the reuse distance is under one tile.
+        if (t + 1 < t1) {
+          if (a.gate) mbar_wait(&bars->tile_go, li & 1);
+          mma1(li + 1);
+        }
       }
     }
   } else if (warp >= 4) {
@@ -247,6 +264,8 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
     if (t0 < t1) softmax_tile(0);
     int li = 0;
     for (int t = t0; t < t1; ++t, ++li) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tile_go);
       // residual rows (this lane's 64 columns), requested before the accumulator is waited for.  The TMA producer
       // brought the same bytes through L2 about one tile ago: evict-last on that load and evict-first on this
       // kernel's output stores keep them there (without the hints ncu showed every residual byte re-read from HBM).
@@ -289,7 +308,6 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->o_empty);
-      if (t + 1 < t1) softmax_tile(li + 1);
       ex_sum[cq * 128 + r] = sum;
       asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
       const float mean = ((ex_sum[r] + ex_sum[128 + r]) + (ex_sum[256 + r] + ex_sum[384 + r])) * (1.0f / 256.0f);
@@ -315,6 +333,9 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
         }
         store_pair16_stream(a.out_hi, a.out_lo, orow * 256 + col, y);
       }
+      // E1 of the next tile last: MMA1(li+1) had this whole iteration to finish, and MMA2(li+1) runs under the next
+      // iteration's residual fetch
+      if (t + 1 < t1) softmax_tile(li + 1);
     }
   }
   tc_fence_before();
@@ -739,6 +760,7 @@ extern "C" int csam_dec_i2t_layer(const csam_i2t_layer_args* a, void* stream) {
   }
   I2TParams p;
   p.x_shared = a->x_shared ? 1 : 0;
+  p.gate = (!a->x_shared && !(getenv("CSAM_I2T_GATE") && atoi(getenv("CSAM_I2T_GATE")) == 0)) ? 1 : 0;
   p.tiles = a->P * 32;
   p.x_hi = static_cast<const __half*>(a->x_hi); p.x_lo = static_cast<const __half*>(a->x_lo);
   p.bias = a->bias; p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps;
@@ -746,7 +768,8 @@ extern "C" int csam_dec_i2t_layer(const csam_i2t_layer_args* a, void* stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = p.tiles < sms ? p.tiles : sms;
+  int grid = p.tiles < sms ? p.tiles : sms;
+  if (const char* env = getenv("CSAM_I2T_GRID")) grid = atoi(env) > 0 && atoi(env) < grid ? atoi(env) : grid;   // experiments
   dec_i2t_layer_kernel<<<grid, I2T_THREADS, I2T_SMEM_BYTES, (cudaStream_t)stream>>>(tx_hi, tx_lo, tq_hi, tq_lo, tb1_hi,
                                                                                    tb1_lo, tb2_hi, tb2_lo, p);
   return check_launch("dec_i2t_layer_kernel");

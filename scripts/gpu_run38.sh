@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+export PYTHONPATH=$PWD
+NB="--kernel-name-base demangled"
+for g in 1 0; do echo "gate $g"; CSAM_I2T_GATE=$g timeout 300 python scripts/prof_i2t.py 256 2>&1 | tail -1; CSAM_I2T_GATE=$g timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none $NB -k 'regex:dec_i2t_layer' -s 2 -c 1 python scripts/prof_i2t.py 256 2>&1 | grep -E "dram__|gpu__time"; done
+timeout 300 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "fused_i2t" --timeout 300 -x 2>&1 | tail -2
