@@ -422,19 +422,19 @@ dec_fold_i2t_kernel(const float* __restrict__ kt, const float* __restrict__ vt, 
 //     MMA2  XBAR^T[256, 64] += X^T (MN-major A straight from the resident X tile) * P (MN-major B, h16 pair)
 // The X tile (128 KB as hi + lo) stays in shared memory from MMA1 to MMA2, so tiles are processed one
 // at a time; the next tile is prefetched into L2 meanwhile.
-constexpr int T2I_THREADS = 256;
+constexpr int T2I_THREADS = 384;                 // 4 control warps + 8 softmax warps (two threads per key row)
 constexpr int T2I_SLOT = 32768;                  // one X / PEK k-block: hi 16 KB | lo 16 KB
 constexpr int T2I_OFF_PEK = 4 * T2I_SLOT;
 constexpr int T2I_OFF_B1 = T2I_OFF_PEK + T2I_SLOT;             // 2-stage ring of B1 k-blocks (hi 8 KB | lo 8 KB)
 constexpr int T2I_OFF_P = T2I_OFF_B1 + 2 * 2 * I2T_B1_BYTES;   // P [128 keys][64] fp16, hi then lo
-constexpr int T2I_OFF_BAR = T2I_OFF_P + 2 * 16384;            // P hi | P lo
+constexpr int T2I_OFF_BAR = T2I_OFF_P + 2 * 16384;
 constexpr int T2I_OFF_ST = T2I_OFF_BAR + 256;                  // m[64] l[64] alpha[64] wmax[4][64]
 constexpr int T2I_SMEM_BYTES = T2I_OFF_ST + (3 * 64 + 4 * 64) * 4;
 static_assert(T2I_SMEM_BYTES <= 227 * 1024, "t2i shared memory budget");
 constexpr float T2I_TAU = 8.f;
 
 struct T2IBars {
-  uint64_t x_full[4], x_empty, pek_full, pek_empty, b_full[2], b_empty[2];
+  uint64_t x_full[4], x_empty[2], pek_full, pek_empty, b_full[2], b_empty[2];
   uint64_t s_full, s_empty, p_full, pv_done;
   uint32_t tmem_slot;
 };
@@ -443,6 +443,10 @@ struct T2IParams {
   int x_shared, P;
   float* xbar;               // [P, 64, 256]
 };
+
+// k-block order of MMA1: the two PEK blocks first (they do not wait for the X slots, so they run under the previous
+// tile's softmax), then the four X blocks
+__device__ __forceinline__ int t2i_kb(int i) { return i < 2 ? 4 + i : i - 2; }
 
 __global__ void __launch_bounds__(T2I_THREADS, 1)
 dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant__ CUtensorMap tx_lo,
@@ -463,11 +467,11 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(&bars->x_full[i], 1);
-    mbar_init(&bars->x_empty, 1);
+    mbar_init(&bars->x_empty[0], 1); mbar_init(&bars->x_empty[1], 1);
     mbar_init(&bars->pek_full, 1); mbar_init(&bars->pek_empty, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
-    mbar_init(&bars->s_full, 1); mbar_init(&bars->s_empty, 4);
-    mbar_init(&bars->p_full, 4); mbar_init(&bars->pv_done, 1);
+    mbar_init(&bars->s_full, 1); mbar_init(&bars->s_empty, 8);
+    mbar_init(&bars->p_full, 8); mbar_init(&bars->pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<256>(&bars->tmem_slot);
@@ -485,9 +489,11 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
         for (int ti = 0; ti < 32; ++ti, ++tl) {
           const int mrow = ti * 128;
           const int arow = a.x_shared ? mrow : p * 4096 + mrow;
-          for (int kb = 0; kb < 6; ++kb) {
-            if (kb == 0) mbar_wait(&bars->x_empty, (tl & 1) ^ 1);      // MMA2 of the previous tile has retired
+          for (int i = 0; i < 6; ++i) {
+            const int kb = t2i_kb(i);
             if (kb < 4) {
+              // slots 0,1 / 2,3 are released separately, as soon as MMA2 of the previous tile is done with them
+              if ((kb & 1) == 0) mbar_wait(&bars->x_empty[kb >> 1], (tl & 1) ^ 1);
               uint8_t* sx = smem + kb * T2I_SLOT;
               mbar_expect_tx(&bars->x_full[kb], T2I_SLOT);
               tma_load_2d(sx, &tx_hi, &bars->x_full[kb], kb * 64, arow);
@@ -507,12 +513,12 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
             tma_load_2d(sb, &tb1_hi, &bars->b_full[bs], kb * 64, p * 64);
             tma_load_2d(sb + I2T_B1_BYTES, &tb1_lo, &bars->b_full[bs], kb * 64, p * 64);
             ++bcnt;
-          }
-          // pull the next tile of X towards L2 while this one is being consumed
-          if (ti + 1 < 32) {
-            for (int kb = 0; kb < 4; ++kb) {
-              tma_prefetch_l2_2d(&tx_hi, kb * 64, arow + 128);
-              tma_prefetch_l2_2d(&tx_lo, kb * 64, arow + 128);
+            if (i == 1 && ti + 1 < 32) {
+              // the NEXT tile of X goes to L2 now, so that its loads (which must wait for this tile's MMA2) are L2 hits
+              for (int k2 = 0; k2 < 4; ++k2) {
+                tma_prefetch_l2_2d(&tx_hi, k2 * 64, arow + 128);
+                tma_prefetch_l2_2d(&tx_lo, k2 * 64, arow + 128);
+              }
             }
           }
         }
@@ -523,71 +529,84 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc1 = umma_idesc_f16(128, 64, 0, 0);
       constexpr uint32_t idesc2 = umma_idesc_f16(128, 64, 1, 1);     // A = X^T and B = P, both MN-major
-      int tl = 0, bcnt = 0, pcnt = 0;
-      for (int p = blockIdx.x; p < a.P; p += gridDim.x) {
-        for (int ti = 0; ti < 32; ++ti, ++tl) {
-          mbar_wait(&bars->s_empty, (tl & 1) ^ 1);
-          tc_fence_after();
-          for (int kb = 0; kb < 6; ++kb) {
-            uint32_t sa;
-            if (kb < 4) {
-              mbar_wait(&bars->x_full[kb], tl & 1);
-              sa = smem_u32(smem + kb * T2I_SLOT);
-            } else {
-              mbar_wait(&bars->pek_full, pcnt & 1);
-              sa = smem_u32(smem + T2I_OFF_PEK);
-            }
-            const int bs = bcnt & 1;
-            mbar_wait(&bars->b_full[bs], (bcnt >> 1) & 1);
-            tc_fence_after();
-            const uint32_t ad = umma_desc_lo(sa, 16);
-            const uint32_t bd = umma_desc_lo(smem_u32(smem + T2I_OFF_B1 + bs * 2 * I2T_B1_BYTES), 16);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_f16_w(tmem_base, ad + 2 * k, bd + 2 * k, idesc1, (kb | k) ? 1u : 0u);
-              umma_f16_w(tmem_base, ad + (16384 >> 4) + 2 * k, bd + 2 * k, idesc1, 1u);
-              umma_f16_w(tmem_base, ad + 2 * k, bd + (I2T_B1_BYTES >> 4) + 2 * k, idesc1, 1u);
-            }
-            umma_commit(&bars->b_empty[bs]);
-            ++bcnt;
-            if (kb >= 4) { umma_commit(&bars->pek_empty); ++pcnt; }
+      int bcnt = 0, pcnt = 0;
+      int n_tiles_total = 0;
+      for (int p = blockIdx.x; p < a.P; p += gridDim.x) n_tiles_total += 32;
+      // MMA1 of tile tl, k-blocks [i0, i1) in the order of t2i_kb
+      auto mma1 = [&](int tl, int i0, int i1) {
+        for (int i = i0; i < i1; ++i) {
+          const int kb = t2i_kb(i);
+          uint32_t sa;
+          if (kb < 4) {
+            mbar_wait(&bars->x_full[kb], tl & 1);
+            sa = smem_u32(smem + kb * T2I_SLOT);
+          } else {
+            mbar_wait(&bars->pek_full, pcnt & 1);
+            sa = smem_u32(smem + T2I_OFF_PEK);
           }
-          umma_commit(&bars->s_full);
-          mbar_wait(&bars->p_full, tl & 1);        // P stored, accumulator rescaled if the maxima moved
+          const int bs = bcnt & 1;
+          mbar_wait(&bars->b_full[bs], (bcnt >> 1) & 1);
           tc_fence_after();
-          const uint32_t pd = umma_desc_lo(smem_u32(smem + T2I_OFF_P), 8192);
+          const uint32_t ad = umma_desc_lo(sa, 16);
+          const uint32_t bd = umma_desc_lo(smem_u32(smem + T2I_OFF_B1 + bs * 2 * I2T_B1_BYTES), 16);
 #pragma unroll
-          for (int fb = 0; fb < 2; ++fb) {
-            const uint32_t xd = umma_desc_lo(smem_u32(smem + 2 * fb * T2I_SLOT), T2I_SLOT);   // LBO: next 64 features
-            const uint32_t d = tmem_base + 64 + fb * 64;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {           // 16 keys per step = 16 rows of 128 B
-              umma_f16_w(d, xd + 128 * k, pd + 128 * k, idesc2, (ti | k) ? 1u : 0u);
-              umma_f16_w(d, xd + (16384 >> 4) + 128 * k, pd + 128 * k, idesc2, 1u);
-              umma_f16_w(d, xd + 128 * k, pd + (16384 >> 4) + 128 * k, idesc2, 1u);
-            }
+          for (int k = 0; k < 4; ++k) {
+            umma_f16_w(tmem_base, ad + 2 * k, bd + 2 * k, idesc1, (i | k) ? 1u : 0u);
+            umma_f16_w(tmem_base, ad + (16384 >> 4) + 2 * k, bd + 2 * k, idesc1, 1u);
+            umma_f16_w(tmem_base, ad + 2 * k, bd + (I2T_B1_BYTES >> 4) + 2 * k, idesc1, 1u);
           }
-          umma_commit(&bars->x_empty);
-          umma_commit(&bars->pv_done);
+          umma_commit(&bars->b_empty[bs]);
+          ++bcnt;
+          if (kb >= 4) { umma_commit(&bars->pek_empty); ++pcnt; }
         }
+        if (i1 == 6) umma_commit(&bars->s_full);
+      };
+      if (n_tiles_total > 0) mma1(0, 0, 6);
+      for (int tl = 0; tl < n_tiles_total; ++tl) {
+        const int ti = tl & 31;
+        // the PEK part of the next tile's scores runs under this tile's softmax (S is free once it has been read)
+        if (tl + 1 < n_tiles_total) {
+          mbar_wait(&bars->s_empty, tl & 1);
+          tc_fence_after();
+          mma1(tl + 1, 0, 2);
+        }
+        mbar_wait(&bars->p_full, tl & 1);        // P stored, accumulator rescaled if the maxima moved
+        tc_fence_after();
+        const uint32_t pd = umma_desc_lo(smem_u32(smem + T2I_OFF_P), 8192);
+#pragma unroll
+        for (int fb = 0; fb < 2; ++fb) {
+          const uint32_t xd = umma_desc_lo(smem_u32(smem + 2 * fb * T2I_SLOT), T2I_SLOT);   // LBO: next 64 features
+          const uint32_t d = tmem_base + 64 + fb * 64;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {           // 16 keys per step = 16 rows of 128 B
+            umma_f16_w(d, xd + 128 * k, pd + 128 * k, idesc2, (ti | k) ? 1u : 0u);
+            umma_f16_w(d, xd + (16384 >> 4) + 128 * k, pd + 128 * k, idesc2, 1u);
+            umma_f16_w(d, xd + 128 * k, pd + (16384 >> 4) + 128 * k, idesc2, 1u);
+          }
+          umma_commit(&bars->x_empty[fb]);
+        }
+        umma_commit(&bars->pv_done);
+        if (tl + 1 < n_tiles_total) mma1(tl + 1, 2, 6);
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ softmax over keys (4 warps, one key row per thread)
-    const int wq = warp - 4;                       // TMEM lane quadrant == warp % 4
+    // ------------------------------------------------------------------ softmax over keys (8 warps, two threads per key row)
+    const int wq = (warp - 4) & 3;                 // TMEM lane quadrant == warp % 4
+    const int ch = (warp - 4) >> 2;                // which 32 of the 64 (head, token) columns
     const int r = wq * 32 + lane;
+    const int et = threadIdx.x - 128;              // 0..255
     const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const float* my_m = st_m + ch * 32;
     int tl = 0;
     for (int p = blockIdx.x; p < a.P; p += gridDim.x) {
-      float lsum[64];
+      float lsum[32];
 #pragma unroll
-      for (int c = 0; c < 64; ++c) lsum[c] = 0.f;
+      for (int c = 0; c < 32; ++c) lsum[c] = 0.f;
       for (int ti = 0; ti < 32; ++ti, ++tl) {
         mbar_wait(&bars->s_full, tl & 1);
         tc_fence_after();
-        uint32_t raw[64];
-        tmem_ld32(lane_addr, raw);
-        tmem_ld32(lane_addr + 32, raw + 32);
+        uint32_t raw[32];
+        tmem_ld32(lane_addr + ch * 32, raw);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -597,48 +616,48 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
           // cheap pass first: does any score exceed its column's (stale) maximum by more than 2^TAU ?
           int viol = 0;
 #pragma unroll
-          for (int c = 0; c < 64; c += 2) {
-            const float2 mm = *reinterpret_cast<const float2*>(st_m + c);
+          for (int c = 0; c < 32; c += 2) {
+            const float2 mm = *reinterpret_cast<const float2*>(my_m + c);
             viol |= (__uint_as_float(raw[c]) > mm.x + T2I_TAU) | (__uint_as_float(raw[c + 1]) > mm.y + T2I_TAU);
           }
           int any;
-          asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %1, 0;\n\tbar.red.or.pred q, 2, 128, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+          asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %1, 0;\n\tbar.red.or.pred q, 2, 256, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
                        : "=r"(any) : "r"(viol) : "memory");
           if (!any) break;
           // some column outgrew its (stale) maximum: exact column maxima of this tile, new m, rescale factors
 #pragma unroll
-          for (int c = 0; c < 64; ++c) {
+          for (int c = 0; c < 32; ++c) {
             const float v = warp_max(__uint_as_float(raw[c]));
-            if (lane == 0) st_wmax[wq * 64 + c] = v;
+            if (lane == 0) st_wmax[wq * 64 + ch * 32 + c] = v;
           }
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-          if (r < 64) {
-            const float mo = st_m[r];
-            const float mn = fmaxf(fmaxf(mo, fmaxf(st_wmax[r], st_wmax[64 + r])), fmaxf(st_wmax[128 + r], st_wmax[192 + r]));
-            st_alpha[r] = ex2f_approx(mo - mn);      // first tile of a prompt: exp2(-inf) = 0
-            st_m[r] = mn;
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (et < 64) {
+            const float mo = st_m[et];
+            const float mn = fmaxf(fmaxf(mo, fmaxf(st_wmax[et], st_wmax[64 + et])), fmaxf(st_wmax[128 + et], st_wmax[192 + et]));
+            st_alpha[et] = ex2f_approx(mo - mn);     // first tile of a prompt: exp2(-inf) = 0
+            st_m[et] = mn;
           }
-          asm volatile("bar.sync 2, 128;" ::: "memory");
+          asm volatile("bar.sync 2, 256;" ::: "memory");
           if (ti > 0) {
             if (!waited_pv) { mbar_wait(&bars->pv_done, (tl - 1) & 1); tc_fence_after(); waited_pv = true; }
 #pragma unroll
-            for (int hh = 0; hh < 4; ++hh) {         // this lane's feature row of both accumulator halves
+            for (int hh = 0; hh < 2; ++hh) {         // this lane's feature row of accumulator half `ch`
               uint32_t o[32];
-              tmem_ld32(lane_addr + 64 + hh * 32, o);
+              tmem_ld32(lane_addr + 64 + ch * 64 + hh * 32, o);
               tmem_ld_wait();
 #pragma unroll
-              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * st_alpha[(hh & 1) * 32 + c]);
-              tmem_st32(lane_addr + 64 + hh * 32, o);
+              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * st_alpha[hh * 32 + c]);
+              tmem_st32(lane_addr + 64 + ch * 64 + hh * 32, o);
             }
             tmem_st_wait();
 #pragma unroll
-            for (int c = 0; c < 64; ++c) lsum[c] *= st_alpha[c];
+            for (int c = 0; c < 32; ++c) lsum[c] *= st_alpha[ch * 32 + c];
           }
         }
-        uint32_t ph[32], pl[32];
+        uint32_t ph[16], pl[16];
 #pragma unroll
-        for (int c = 0; c < 64; c += 2) {
-          const float2 mm = *reinterpret_cast<const float2*>(st_m + c);
+        for (int c = 0; c < 32; c += 2) {
+          const float2 mm = *reinterpret_cast<const float2*>(my_m + c);
           const float p0 = ex2f_approx(__uint_as_float(raw[c]) - mm.x);
           const float p1 = ex2f_approx(__uint_as_float(raw[c + 1]) - mm.y);
           lsum[c] += p0;
@@ -651,8 +670,8 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
         if (tl > 0 && !waited_pv) { mbar_wait(&bars->pv_done, (tl - 1) & 1); tc_fence_after(); }   // P buffer free
         uint8_t* pb = smem + T2I_OFF_P + r * 128;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int off = (u ^ (r & 7)) << 4;
+        for (int u = 0; u < 4; ++u) {
+          const int off = ((ch * 4 + u) ^ (r & 7)) << 4;
           *reinterpret_cast<uint4*>(pb + off) = make_uint4(ph[4 * u], ph[4 * u + 1], ph[4 * u + 2], ph[4 * u + 3]);
           *reinterpret_cast<uint4*>(pb + 16384 + off) = make_uint4(pl[4 * u], pl[4 * u + 1], pl[4 * u + 2], pl[4 * u + 3]);
         }
@@ -663,29 +682,29 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
       }
       // ---- end of prompt: column sums over all keys, then XBAR = accumulator / l
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
+      for (int c = 0; c < 32; ++c) {
         const float v = warp_sum(lsum[c]);
-        if (lane == 0) atomicAdd(&st_l[c], v);
+        if (lane == 0) atomicAdd(&st_l[ch * 32 + c], v);
       }
       mbar_wait(&bars->pv_done, (tl - 1) & 1);
       tc_fence_after();
-      asm volatile("bar.sync 2, 128;" ::: "memory");
+      asm volatile("bar.sync 2, 256;" ::: "memory");
       float* xo = a.xbar + (size_t)p * 64 * 256;
 #pragma unroll
-      for (int hh = 0; hh < 4; ++hh) {
+      for (int hh = 0; hh < 2; ++hh) {
         uint32_t o[32];
-        tmem_ld32(lane_addr + 64 + hh * 32, o);
+        tmem_ld32(lane_addr + 64 + ch * 64 + hh * 32, o);
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const int col = (hh & 1) * 32 + c;
-          xo[(size_t)col * 256 + (hh >> 1) * 128 + r] = __uint_as_float(o[c]) / st_l[col];
+          const int col = hh * 32 + c;
+          xo[(size_t)col * 256 + ch * 128 + r] = __uint_as_float(o[c]) / st_l[col];
         }
       }
       tc_fence_before();
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      if (r < 64) { st_m[r] = -INFINITY; st_l[r] = 0.f; }
-      asm volatile("bar.sync 2, 128;" ::: "memory");
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (et < 64) { st_m[et] = -INFINITY; st_l[et] = 0.f; }
+      asm volatile("bar.sync 2, 256;" ::: "memory");
     }
   }
   tc_fence_before();
