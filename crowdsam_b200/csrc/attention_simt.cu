@@ -325,11 +325,65 @@ __global__ void __launch_bounds__(256) relpos_rows_kernel(const __half* __restri
   }
 }
 
+// Window blocks (S = 14): one block per (group, head), one thread per query with its q row in registers and both
+// tables in shared memory.  The row-per-block kernel above launches 5600 blocks of 392 outputs for 25 windows x 16
+// heads (78 us per layer, as long as the window attention itself); this one is a 400-block launch.
+__global__ void __launch_bounds__(224) relpos_win14_kernel(const __half* __restrict__ qhi, const __half* __restrict__ qlo,
+                                                           int ld, int heads, const float* __restrict__ rel_h,
+                                                           const float* __restrict__ rel_w, float* __restrict__ out) {
+  constexpr int S = 14, HD = 64, T = 196, LDT = HD + 4;     // rows padded to 68 floats: 16-byte aligned, bank-shifted
+  __shared__ __align__(16) float th[27 * LDT];
+  __shared__ __align__(16) float tw[27 * LDT];
+  const int h = blockIdx.x, g = blockIdx.y, t = threadIdx.x;
+  for (int i = t; i < 27 * HD; i += 224) {
+    th[(i >> 6) * LDT + (i & 63)] = rel_h[i];
+    tw[(i >> 6) * LDT + (i & 63)] = rel_w[i];
+  }
+  __syncthreads();
+  if (t >= T) return;
+  float q[HD];
+  const size_t qo = ((size_t)g * T + t) * ld + (size_t)h * HD;
+#pragma unroll
+  for (int d = 0; d < HD; d += 8) {
+    const uint4 a = *reinterpret_cast<const uint4*>(qhi + qo + d);
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(ah[k]); q[d + 2 * k] = f.x; q[d + 2 * k + 1] = f.y; }
+    if (qlo) {
+      const uint4 b = *reinterpret_cast<const uint4*>(qlo + qo + d);
+      const __half2* bl = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(bl[k]); q[d + 2 * k] += f.x; q[d + 2 * k + 1] += f.y; }
+    }
+  }
+  const int qh = t / S, qw = t % S;
+  float* o = out + (((size_t)g * heads + h) * T + t) * 2 * S;
+#pragma unroll 1
+  for (int j = 0; j < 2 * S; ++j) {
+    const float* row = (j < S) ? th + (qh - j + S - 1) * LDT : tw + (qw - (j - S) + S - 1) * LDT;
+    float acc = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD; d += 4) {
+      const float4 r4 = *reinterpret_cast<const float4*>(row + d);
+      acc = fmaf(q[d], r4.x, acc); acc = fmaf(q[d + 1], r4.y, acc);
+      acc = fmaf(q[d + 2], r4.z, acc); acc = fmaf(q[d + 3], r4.w, acc);
+    }
+    o[j] = acc;
+  }
+}
+
 // fills a->scratch with the decomposed rel-pos terms [groups*heads*tokens, 2S] (shared by both attention paths)
 int compute_relpos(const csam_attn_args* a, cudaStream_t st) {
   CSAM_REQUIRE(a->S * a->S == a->tokens, "csam_vit_attention: rel-pos needs tokens == S*S");
   const long long need = csam_vit_attention_scratch_bytes(a->groups, a->tokens, a->heads, a->hd, a->S);
   CSAM_REQUIRE(a->scratch && a->scratch_bytes >= need, "csam_vit_attention: scratch too small");
+  if (a->S == 14 && a->hd == 64 && a->tokens == 196 && (a->ld_qkv & 7) == 0 && a->heads <= 65535 &&
+      !(getenv("CSAM_RELPOS_WIN") && atoi(getenv("CSAM_RELPOS_WIN")) == 0)) {
+    relpos_win14_kernel<<<dim3(a->heads, a->groups), 224, 0, st>>>(
+        static_cast<const __half*>(a->qkv_hi), static_cast<const __half*>(a->qkv_lo), a->ld_qkv, a->heads, a->rel_h,
+        a->rel_w, a->scratch);
+    return check_launch("relpos_win14_kernel");
+  }
   const size_t smem = (size_t)(4 * a->S - 1) * (a->hd + 1) * sizeof(float);
   CSAM_REQUIRE(smem <= 100 * 1024 && a->groups <= 65535, "csam_vit_attention: rel-pos table too large");
   static bool attr = false;
