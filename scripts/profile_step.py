@@ -19,7 +19,7 @@ sam = _build_sam(D, depth, heads, 1, glob); sam.load_state_dict(weights.make_sam
 dD, dd, dh = weights.DINO_ARCHS[bench.DINO]
 dino = DinoVisionTransformer(dD, dd, dh); dino.load_state_dict(weights.make_dino_state(bench.DINO), strict=True)
 pred = SamPredictor(sam.to(dev), dino.to(dev))
-cfg = {"environ": {"device": str(dev)}, "model": {"trainfree": False}, "test": bench.test_cfg(256)}
+cfg = {"environ": {"device": str(dev)}, "model": {"trainfree": False}, "test": bench.test_cfg(int(os.environ.get("PPB", "1024")))}
 model = CrowdSAM(cfg, None, predictor=pred)
 imgs = [torch.as_tensor(weights.synthetic_image(i)).permute(2, 0, 1).contiguous().to(dev) for i in range(n_steps)]
 if "--stats" in sys.argv:
