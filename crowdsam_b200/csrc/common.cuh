@@ -188,7 +188,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Spin on the phase parity; a watchdog turns a lost arrival into a trap instead of a hang.
+// Spin on the phase parity; a watchdog turns a lost arrival into a trap instead of a hang.  The trap carries no
+// printf: a (never taken) vprintf call inside the wait loop made ptxas spill every live register around each wait
+// -- 25 STL + 25 LDL per tile in the fused decoder epilogues (ncu: local memory traffic in the hot path).
+// Build with -DCSAM_MBAR_DEBUG to get the block / thread of a lost arrival printed.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
@@ -203,7 +206,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     if (done) break;
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+#ifdef CSAM_MBAR_DEBUG
       printf("csam: mbarrier watchdog block %d thread %d\n", blockIdx.x, threadIdx.x);
+#endif
       __trap();
     }
   }

@@ -99,6 +99,7 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0; int b2_cnt = 0;
       const uint64_t keep = l2_policy_evict_last();
@@ -142,6 +143,7 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (lane == 0) {
       constexpr uint32_t idesc1 = umma_idesc_f16(I2T_BM, 64, 0, 0);
       constexpr uint32_t idesc2 = umma_idesc_f16(I2T_BM, 256, 0, 0);
@@ -195,8 +197,14 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  } else {
     // ------------------------------------------------------------------ epilogue (16 warps)
+    // 640 threads start at 96 registers (61440 for the CTA -- setmaxnreg only redistributes WITHIN that launch
+    // allocation); the 4 control warps hand 40 each back so that the 16 epilogue warps run at 104
+    // (128 x 56 + 512 x 104 = 60416)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int ew = warp - 4;
     const int q = ew & 3;                        // TMEM lane quadrant == warp % 4
     const int cq = ew >> 2;                      // column quarter (S: 16 of 64 columns, O: 64 of 256)
@@ -654,26 +662,27 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
             for (int c = 0; c < 32; ++c) lsum[c] *= st_alpha[ch * 32 + c];
           }
         }
-        uint32_t ph[16], pl[16];
-#pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          const float2 mm = *reinterpret_cast<const float2*>(my_m + c);
-          const float p0 = ex2f_approx(__uint_as_float(raw[c]) - mm.x);
-          const float p1 = ex2f_approx(__uint_as_float(raw[c + 1]) - mm.y);
-          lsum[c] += p0;
-          lsum[c + 1] += p1;
-          __half2 h2, l2;
-          split_h2(p0, p1, h2, l2);
-          ph[c >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-          pl[c >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
-        }
         if (tl > 0 && !waited_pv) { mbar_wait(&bars->pv_done, (tl - 1) & 1); tc_fence_after(); }   // P buffer free
         uint8_t* pb = smem + T2I_OFF_P + r * 128;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
+          uint32_t ph[4], pl[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = u * 8 + 2 * k;
+            const float2 mm = *reinterpret_cast<const float2*>(my_m + c);
+            const float p0 = ex2f_approx(__uint_as_float(raw[c]) - mm.x);
+            const float p1 = ex2f_approx(__uint_as_float(raw[c + 1]) - mm.y);
+            lsum[c] += p0;
+            lsum[c + 1] += p1;
+            __half2 h2, l2;
+            split_h2(p0, p1, h2, l2);
+            ph[k] = *reinterpret_cast<const uint32_t*>(&h2);
+            pl[k] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
           const int off = ((ch * 4 + u) ^ (r & 7)) << 4;
-          *reinterpret_cast<uint4*>(pb + off) = make_uint4(ph[4 * u], ph[4 * u + 1], ph[4 * u + 2], ph[4 * u + 3]);
-          *reinterpret_cast<uint4*>(pb + 16384 + off) = make_uint4(pl[4 * u], pl[4 * u + 1], pl[4 * u + 2], pl[4 * u + 3]);
+          *reinterpret_cast<uint4*>(pb + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+          *reinterpret_cast<uint4*>(pb + 16384 + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
         }
         fence_proxy_async();
         tc_fence_before();
