@@ -231,7 +231,16 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
       for (int c = 0; c < 64; ++c) relw[c] = relq[64 + c] * LOG2E;
     }
     if (BIAS == 1) {
-      for (int i = 0; i < 28; ++i) rel_r[i] = relq[i] * LOG2E;
+      // 28 floats per query = 7 float4 (rows are 112 B apart, 16-byte aligned): all loads in flight at once instead
+      // of 28 dependent scalar round trips in the prologue of a CTA that only has 4 key tiles of work
+      float4 t4[7];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) t4[i] = *reinterpret_cast<const float4*>(relq + 4 * i);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        rel_r[4 * i + 0] = t4[i].x * LOG2E; rel_r[4 * i + 1] = t4[i].y * LOG2E;
+        rel_r[4 * i + 2] = t4[i].z * LOG2E; rel_r[4 * i + 3] = t4[i].w * LOG2E;
+      }
     }
     float m = -INFINITY, l = 0.f;      // m: the (possibly stale) maximum the probabilities are taken against
     auto wait_pv = [&](int j) {        // P V(j) retired: O holds tiles 0..j, the P buffer of tile j is free
@@ -358,6 +367,320 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
   if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
+// =====================================================================================================
+// TS variant: Q and P live in TENSOR MEMORY and enter the MMAs as the A operand.
+// With both operands in shared memory a 128 x 64 x 16 MMA reads 4 KB (A) + 2 KB (B) per 32 cycles = 192 B/clk, more
+// than the 128 B/clk a CTA gets from shared memory: the SS kernel above is shared-memory-bandwidth bound (measured
+// 2540 cycles per key tile pair against 1280 cycles of tensor work).  Here the MMAs read only K / V (64 B/clk):
+//   TMEM per query tile (256 columns):  [0,64) S0 | P0   [64,128) S1 | P1   [128,192) O   [192,224) Q hi   [224,256) Q lo
+//   Q: each softmax thread copies its own row from global memory into TMEM once (tcgen05.st);
+//   P(j): fp16 pairs written over the first 32 columns of S(j) after S(j) has been read (no shared memory, no proxy
+//         fence); S(j+2) may only be issued once P V(j) has retired.
+// Shared memory holds nothing but the K/V ring (6-7 stages).
+template <int SPLIT, int BIAS, int NQ>
+struct AttnTsCfg {
+  static constexpr int NOPS = (SPLIT == 3) ? 2 : 1;
+  static constexpr int THREADS = 128 + 128 * NQ;
+  static constexpr int KV_TILE = AT_BN * AT_HD * 2;          // 8 KB
+  static constexpr int STAGE_BYTES = NOPS * 2 * KV_TILE;
+  static constexpr int REL_BYTES = (BIAS == 1) ? NQ * AT_BM * AT_REL_LD * 4 : 0;
+  static constexpr int STAGES_FIT = (227 * 1024 - REL_BYTES - 512 - 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+  static constexpr int OFF_REL = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_REL + REL_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+  static constexpr int TMEM_COLS = 256 * NQ;
+};
+
+struct AttnTsBars {
+  uint64_t kv_full[8], kv_empty[8];
+  uint64_t q_ready[2], s_full[2][2], p_full[2][2], pv_done[2][2];   // [query tile]([key tile parity])
+  uint32_t tmem_slot;
+};
+
+template <int SPLIT, int BIAS, int NQ>
+__global__ void __launch_bounds__(128 + 128 * NQ, 1)
+vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_constant__ CUtensorMap t_lo,
+                        csam_attn_args a, const float* __restrict__ rel) {
+  using Cfg = AttnTsCfg<SPLIT, BIAS, NQ>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  AttnTsBars* bars = reinterpret_cast<AttnTsBars*>(smem + Cfg::OFF_BAR);
+  float* rel_s = reinterpret_cast<float*>(smem + Cfg::OFF_REL);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * (AT_BM * NQ);
+  const int D = a.heads * AT_HD;
+  const int row_base = g * a.tokens;
+  const int n_tiles = (a.tokens + AT_BN - 1) / AT_BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&t_hi);
+    if (SPLIT == 3) tma_prefetch_desc(&t_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars->kv_full[s], 1); mbar_init(&bars->kv_empty[s], 1); }
+    for (int t = 0; t < NQ; ++t) {
+      mbar_init(&bars->q_ready[t], 4);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&bars->s_full[t][b], 1);
+        mbar_init(&bars->p_full[t][b], 4);
+        mbar_init(&bars->pv_done[t][b], 1);
+      }
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(&bars->tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (K / V only)
+    if (lane == 0) {
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % STAGES;
+        mbar_wait(&bars->kv_empty[st], ((j / STAGES) & 1) ^ 1);
+        uint8_t* sk = smem + st * Cfg::STAGE_BYTES;
+        uint8_t* sv = sk + Cfg::NOPS * Cfg::KV_TILE;
+        mbar_expect_tx(&bars->kv_full[st], Cfg::STAGE_BYTES);
+        const int row = row_base + j * AT_BN;
+        tma_load_2d(sk, &t_hi, &bars->kv_full[st], D + h * AT_HD, row);
+        tma_load_2d(sv, &t_hi, &bars->kv_full[st], 2 * D + h * AT_HD, row);
+        if (SPLIT == 3) {
+          tma_load_2d(sk + Cfg::KV_TILE, &t_lo, &bars->kv_full[st], D + h * AT_HD, row);
+          tma_load_2d(sv + Cfg::KV_TILE, &t_lo, &bars->kv_full[st], 2 * D + h * AT_HD, row);
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ MMA issuer #1: S = Q K^T, Q from TMEM
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(AT_BM, AT_BN, 0, 0);
+#pragma unroll
+      for (int t = 0; t < NQ; ++t) mbar_wait(&bars->q_ready[t], 0);
+      tc_fence_after();
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % STAGES;
+        mbar_wait(&bars->kv_full[st], (j / STAGES) & 1);
+        const uint32_t kd = umma_desc_lo(smem_u32(smem + st * Cfg::STAGE_BYTES), 16);
+#pragma unroll
+        for (int t = 0; t < NQ; ++t) {
+          // S(j) overwrites the buffer that held S(j-2) and then P(j-2): P V(j-2) must have retired
+          if (j >= 2) mbar_wait(&bars->pv_done[t][j & 1], ((j - 2) >> 1) & 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + t * 256 + (j & 1) * AT_BN;
+          const uint32_t qa = tmem_base + t * 256 + 192;
+#pragma unroll
+          for (int k = 0; k < AT_HD / 16; ++k) {
+            umma_f16_ts(d, qa + 8 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
+            if (SPLIT == 3) {
+              umma_f16_ts(d, qa + 32 + 8 * k, kd + 2 * k, idesc_s, 1u);
+              umma_f16_ts(d, qa + 8 * k, kd + (Cfg::KV_TILE >> 4) + 2 * k, idesc_s, 1u);
+            }
+          }
+          umma_commit(&bars->s_full[t][j & 1]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer #2: O += P V, P from TMEM
+    if (lane == 0) {
+      constexpr uint32_t idesc_pv = umma_idesc_f16(AT_BM, AT_HD, 0, 1);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int b = j & 1;
+        const int st = j % STAGES;
+        const uint32_t vd = umma_desc_lo(smem_u32(smem + st * Cfg::STAGE_BYTES + Cfg::NOPS * Cfg::KV_TILE), 8192);
+#pragma unroll
+        for (int t = 0; t < NQ; ++t) {
+          mbar_wait(&bars->p_full[t][b], (j >> 1) & 1);
+          tc_fence_after();
+          const uint32_t pa = tmem_base + t * 256 + b * AT_BN;      // P(j): 32 columns of fp16 pairs over S(j)
+          const uint32_t d = tmem_base + t * 256 + 128;
+#pragma unroll
+          for (int k = 0; k < AT_BN / 16; ++k) {
+            umma_f16_ts(d, pa + 8 * k, vd + 128 * k, idesc_pv, (j | k) ? 1u : 0u);
+            if (SPLIT == 3) umma_f16_ts(d, pa + 8 * k, vd + (Cfg::KV_TILE >> 4) + 128 * k, idesc_pv, 1u);
+          }
+          umma_commit(&bars->pv_done[t][b]);
+        }
+        umma_commit(&bars->kv_empty[st]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax
+    const int qt = (warp - 4) >> 2;
+    const int wq = (warp - 4) & 3;
+    const int r = wq * 32 + lane;
+    const int q = q0 + qt * AT_BM + r;
+    const int qc = min(q, a.tokens - 1);
+    const uint32_t lane_addr = tmem_base + qt * 256 + ((uint32_t)(wq * 32) << 16);
+    const uint32_t o_addr = lane_addr + 128;
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float scale2 = a.scale * LOG2E;
+    {
+      // this thread's Q row -> TMEM (A operand of every S MMA of the CTA)
+      const __half* qh = static_cast<const __half*>(a.qkv_hi) + ((size_t)row_base + qc) * a.ld_qkv + (size_t)h * AT_HD;
+      uint32_t w[32];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ldg256(qh + i * 16, w + i * 8);
+      tmem_st32(lane_addr + 192, w);
+      if (SPLIT == 3) {
+        const __half* ql = static_cast<const __half*>(a.qkv_lo) + ((size_t)row_base + qc) * a.ld_qkv + (size_t)h * AT_HD;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ldg256(ql + i * 16, w + i * 8);
+        tmem_st32(lane_addr + 224, w);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->q_ready[qt]);
+    }
+    float relw[BIAS == 2 ? 64 : 1];
+    const float* relq = nullptr;
+    float* rel_r = rel_s + (qt * AT_BM + r) * AT_REL_LD;
+    if (BIAS != 0) relq = rel + (((size_t)g * a.heads + h) * a.tokens + qc) * 2 * a.S;
+    if (BIAS == 2) {
+#pragma unroll
+      for (int c = 0; c < 64; ++c) relw[c] = relq[64 + c] * LOG2E;
+    }
+    if (BIAS == 1) {
+      float4 t4[7];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) t4[i] = *reinterpret_cast<const float4*>(relq + 4 * i);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        rel_r[4 * i + 0] = t4[i].x * LOG2E; rel_r[4 * i + 1] = t4[i].y * LOG2E;
+        rel_r[4 * i + 2] = t4[i].z * LOG2E; rel_r[4 * i + 3] = t4[i].w * LOG2E;
+      }
+    }
+    float m = -INFINITY, l = 0.f;
+    auto wait_pv = [&](int j) {
+      mbar_wait(&bars->pv_done[qt][j & 1], (j >> 1) & 1);
+      tc_fence_after();
+    };
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int b = j & 1;
+      mbar_wait(&bars->s_full[qt][b], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t raw[64];
+      tmem_ld32(lane_addr + b * AT_BN, raw);
+      tmem_ld32(lane_addr + b * AT_BN + 32, raw + 32);
+      tmem_ld_wait();
+      float s[64];
+      const int key0 = j * AT_BN;
+      if (BIAS == 2) {
+        const float bh = relq[j] * LOG2E;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) s[c] = fmaf(__uint_as_float(raw[c]), scale2, bh + relw[c]);
+      } else if (BIAS == 1) {
+        int kh = key0 / 14, kw = key0 % 14;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          const int khc = min(kh, 13);
+          s[c] = fmaf(__uint_as_float(raw[c]), scale2, rel_r[khc] + rel_r[14 + kw]);
+          if (++kw == 14) { kw = 0; ++kh; }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) s[c] = __uint_as_float(raw[c]);
+      }
+      if (key0 + AT_BN > a.tokens) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (key0 + c >= a.tokens) s[c] = -INFINITY;
+      }
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) tmax = fmaxf(tmax, s[c]);
+      if (BIAS == 0) tmax *= scale2;
+      if (j == 0) {
+        m = tmax;
+      } else if (__any_sync(0xffffffffu, tmax > m + AT_TAU)) {
+        const float m_new = fmaxf(m, tmax);
+        const float alpha = ex2_approx(m - m_new);
+        wait_pv(j - 1);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t o[32];
+          tmem_ld32(o_addr + hh * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int d = 0; d < 32; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * alpha);
+          tmem_st32(o_addr + hh * 32, o);
+        }
+        l *= alpha;
+        m = m_new;
+      }
+      float psum = 0.f;
+      uint32_t ph[32];
+#pragma unroll
+      for (int c = 0; c < 64; c += 2) {
+        float p0 = (BIAS == 0) ? fmaf(s[c], scale2, -m) : s[c] - m;
+        float p1 = (BIAS == 0) ? fmaf(s[c + 1], scale2, -m) : s[c + 1] - m;
+        p0 = ex2_approx(p0);
+        p1 = ex2_approx(p1);
+        psum += p0 + p1;
+        const __half2 h2 = __floats2half2_rn(p0, p1);
+        ph[c >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      l += psum;
+      tmem_st32(lane_addr + b * AT_BN, ph);          // P(j) over the first half of S(j)
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->p_full[qt][b]);
+    }
+    wait_pv(n_tiles - 1);
+    const float inv = 1.0f / l;
+    __half* ohi = static_cast<__half*>(a.out_hi);
+    __half* olo = static_cast<__half*>(a.out_lo);
+    const size_t oo = ((size_t)row_base + q) * a.ld_out + (size_t)h * AT_HD;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t o[32];
+      tmem_ld32(o_addr + hh * 32, o);
+      tmem_ld_wait();
+      if (q < a.tokens) {
+#pragma unroll
+        for (int d = 0; d < 32; d += 8) {
+          float v8[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v8[t] = __uint_as_float(o[d + t]) * inv;
+          store_pair8(ohi, olo, oo + hh * 32 + d, v8);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+template <int SPLIT, int BIAS, int NQ>
+static int launch_attn_ts(const csam_attn_args* a, const float* rel, cudaStream_t st) {
+  using Cfg = AttnTsCfg<SPLIT, BIAS, NQ>;
+  CUtensorMap t_hi, t_lo;
+  const uint64_t rows = (uint64_t)a->groups * a->tokens;
+  const uint64_t cols = 3ull * a->heads * a->hd;
+  if (make_tmap_2d_f16(&t_hi, a->qkv_hi, rows, cols, a->ld_qkv, 64, 64)) return 1;
+  t_lo = t_hi;
+  if (SPLIT == 3 && make_tmap_2d_f16(&t_lo, a->qkv_lo, rows, cols, a->ld_qkv, 64, 64)) return 1;
+  auto kern = vit_attention_ts_kernel<SPLIT, BIAS, NQ>;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+      return fail("%s", "cudaFuncSetAttribute(smem) failed for vit_attention_ts_kernel");
+    attr = true;
+  }
+  dim3 grid((a->tokens + AT_BM * NQ - 1) / (AT_BM * NQ), a->heads, a->groups);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(t_hi, t_lo, *a, rel);
+  return check_launch("vit_attention_ts_kernel");
+}
+
 template <int SPLIT, int BIAS, bool PLO, int NQ>
 static int launch_attn_tc(const csam_attn_args* a, const float* rel, cudaStream_t st) {
   using Cfg = AttnCfg<SPLIT, BIAS, PLO, NQ>;
@@ -404,6 +727,23 @@ int vit_attention_tc(const csam_attn_args* a, cudaStream_t st) {
     if (compute_relpos(a, st)) return 1;
     rel = a->scratch;
     bias = a->S == 14 ? 1 : 2;
+  }
+  {
+    // Q / P in tensor memory (default): needs 32-byte aligned Q rows for the row copy; p_split keeps the SS kernel
+    static const int ts_env = getenv("CSAM_ATTN_TS") ? atoi(getenv("CSAM_ATTN_TS")) : 1;
+    const bool al32 = (reinterpret_cast<uintptr_t>(a->qkv_hi) & 31) == 0 && (a->ld_qkv % 16) == 0 &&
+                      (!split || (reinterpret_cast<uintptr_t>(a->qkv_lo) & 31) == 0);
+    if (ts_env && al32 && !(split && a->p_split)) {
+      const bool nq2 = use_nq2(a, bias) && bias != 2;
+      if (split) {
+        if (bias == 0) return nq2 ? launch_attn_ts<3, 0, 2>(a, rel, st) : launch_attn_ts<3, 0, 1>(a, rel, st);
+        if (bias == 1) return nq2 ? launch_attn_ts<3, 1, 2>(a, rel, st) : launch_attn_ts<3, 1, 1>(a, rel, st);
+        return launch_attn_ts<3, 2, 1>(a, rel, st);
+      }
+      if (bias == 0) return nq2 ? launch_attn_ts<1, 0, 2>(a, rel, st) : launch_attn_ts<1, 0, 1>(a, rel, st);
+      if (bias == 1) return nq2 ? launch_attn_ts<1, 1, 2>(a, rel, st) : launch_attn_ts<1, 1, 1>(a, rel, st);
+      return launch_attn_ts<1, 2, 1>(a, rel, st);
+    }
   }
   if (split && a->p_split) {
     if (bias == 0) return launch_attn_tc<3, 0, true, 1>(a, rel, st);

@@ -335,6 +335,17 @@ __device__ __forceinline__ void umma_f16_w(uint32_t tmem_d, uint32_t a_lo32, uin
       ::"r"(tmem_d), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI_SW128)
       : "memory");
 }
+// Same, with the A operand in TENSOR MEMORY (lane = row, two consecutive K elements per 32-bit column, i.e. 8 columns
+// per K = 16 step): the MMA then reads only B from shared memory.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo32, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI_SW128)
+      : "memory");
+}
 // Instruction descriptor for kind::f16, fp16 A/B, fp32 accumulate (InstrDescriptor bit layout).
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                          // c_format = F32
