@@ -222,6 +222,7 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
       s_bias[et] = a.bias ? a.bias[et] : 0.f;
     }
     asm volatile("bar.sync 5, 512;" ::: "memory");
+    const bool has_bias = a.bias != nullptr;
 
     // E1: softmax over the 7 tokens of each of this thread's 2 heads -> P (hi/lo) in the UMMA K-major layout
     auto softmax_tile = [&](int li) {
@@ -252,7 +253,7 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
           __half2 h2, l2;
-          split_h2(pr[j], pr[j + 1], h2, l2);
+          split_h2_nc(pr[j], pr[j + 1], h2, l2);
           hi[hh * 4 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&h2);
           lo[hh * 4 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&l2);
         }
@@ -304,11 +305,14 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          const float4 bb = *reinterpret_cast<const float4*>(s_bias + cq * 64 + c + j);
-          x[c + j + 0] += __uint_as_float(raw[j + 0]) + bb.x;
-          x[c + j + 1] += __uint_as_float(raw[j + 1]) + bb.y;
-          x[c + j + 2] += __uint_as_float(raw[j + 2]) + bb.z;
-          x[c + j + 3] += __uint_as_float(raw[j + 3]) + bb.w;
+          x[c + j + 0] += __uint_as_float(raw[j + 0]);
+          x[c + j + 1] += __uint_as_float(raw[j + 1]);
+          x[c + j + 2] += __uint_as_float(raw[j + 2]);
+          x[c + j + 3] += __uint_as_float(raw[j + 3]);
+          if (has_bias) {        // only when the caller did not fold out_proj's bias into B2
+            const float4 bb = *reinterpret_cast<const float4*>(s_bias + cq * 64 + c + j);
+            x[c + j + 0] += bb.x; x[c + j + 1] += bb.y; x[c + j + 2] += bb.z; x[c + j + 3] += bb.w;
+          }
           sum += (x[c + j] + x[c + j + 1]) + (x[c + j + 2] + x[c + j + 3]);
         }
       }
@@ -326,6 +330,7 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
       asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
       const float rstd = 1.0f / sqrtf(((ex_sq[r] + ex_sq[128 + r]) + (ex_sq[256 + r] + ex_sq[384 + r])) * (1.0f / 256.0f) + a.eps);
       const size_t orow = (size_t)t * I2T_BM + r;
+      const float nmr = -mean * rstd;
 #pragma unroll
       for (int c = 0; c < 64; c += 16) {
         const int col = cq * 64 + c;
@@ -334,10 +339,10 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
         for (int j = 0; j < 16; j += 4) {
           const float4 g = *reinterpret_cast<const float4*>(s_gamma + col + j);
           const float4 bt = *reinterpret_cast<const float4*>(s_beta + col + j);
-          y[j + 0] = (x[c + j + 0] - mean) * rstd * g.x + bt.x;
-          y[j + 1] = (x[c + j + 1] - mean) * rstd * g.y + bt.y;
-          y[j + 2] = (x[c + j + 2] - mean) * rstd * g.z + bt.z;
-          y[j + 3] = (x[c + j + 3] - mean) * rstd * g.w + bt.w;
+          y[j + 0] = fmaf(fmaf(x[c + j + 0], rstd, nmr), g.x, bt.x);     // nmr = -mean * rstd
+          y[j + 1] = fmaf(fmaf(x[c + j + 1], rstd, nmr), g.y, bt.y);
+          y[j + 2] = fmaf(fmaf(x[c + j + 2], rstd, nmr), g.z, bt.z);
+          y[j + 3] = fmaf(fmaf(x[c + j + 3], rstd, nmr), g.w, bt.w);
         }
         store_pair16_stream(a.out_hi, a.out_lo, orow * 256 + col, y);
       }
@@ -357,7 +362,8 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
 // B2 [P*256, 64], row c: col n = h*8 + j = sum_d Wo[c][h*16+d] v_t[j][h*16+d] (zero for j = 7).
 __global__ void __launch_bounds__(256)
 dec_fold_i2t_kernel(const float* __restrict__ kt, const float* __restrict__ vt, const float* __restrict__ wq,
-                    const float* __restrict__ wo, __half* b1_hi, __half* b1_lo, __half* b2_hi, __half* b2_lo) {
+                    const float* __restrict__ wo, const float* __restrict__ bo, __half* b1_hi, __half* b1_lo,
+                    __half* b2_hi, __half* b2_lo) {
   __shared__ float ks[7][128];
   __shared__ float vs[7][128];
   const int p = blockIdx.x, c = threadIdx.x;
@@ -388,6 +394,9 @@ dec_fold_i2t_kernel(const float* __restrict__ kt, const float* __restrict__ vt, 
     }
   }
   if (!vt) return;                     // token -> image folding needs B1 only
+  // out_proj's bias rides along: the probabilities of every head sum to 1, so adding b_o[c] / 8 to each of the 7
+  // columns of each of the 8 heads adds exactly b_o[c] to the product (one add per element less in the epilogue)
+  const float bshare = bo ? bo[c] * 0.125f : 0.f;
   float o[64];
   const float* wrow = wo + (size_t)c * 128;
 #pragma unroll
@@ -402,6 +411,7 @@ dec_fold_i2t_kernel(const float* __restrict__ kt, const float* __restrict__ vt, 
     for (int j = 0; j < 8; ++j) {
       float acc = 0.f;
       if (j < 7) {
+        acc = bshare;
 #pragma unroll
         for (int d = 0; d < 16; ++d) acc = fmaf(w[d], vs[j][h * 16 + d], acc);
       }
@@ -676,7 +686,7 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
             lsum[c] += p0;
             lsum[c + 1] += p1;
             __half2 h2, l2;
-            split_h2(p0, p1, h2, l2);
+            split_h2_nc(p0, p1, h2, l2);
             ph[k] = *reinterpret_cast<const uint32_t*>(&h2);
             pl[k] = *reinterpret_cast<const uint32_t*>(&l2);
           }
@@ -749,13 +759,13 @@ dec_t2i_out_kernel(const float* __restrict__ xbar, const float* __restrict__ wv_
 
 using namespace csam;
 
-extern "C" int csam_dec_fold_i2t(const float* kt, const float* vt, int P, const float* wq, const float* wo,
+extern "C" int csam_dec_fold_i2t(const float* kt, const float* vt, int P, const float* wq, const float* wo, const float* bo,
                                  void* b1_hi, void* b1_lo, void* b2_hi, void* b2_lo, void* stream) {
   CSAM_REQUIRE(kt && vt && wq && wo && b1_hi && b1_lo && b2_hi && b2_lo && P > 0, "csam_dec_fold_i2t: bad args");
   CSAM_REQUIRE((reinterpret_cast<uintptr_t>(wo) & 15) == 0 && (reinterpret_cast<uintptr_t>(b2_hi) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(b2_lo) & 15) == 0,
                "csam_dec_fold_i2t: 16-byte alignment");
-  dec_fold_i2t_kernel<<<P, 256, 0, (cudaStream_t)stream>>>(kt, vt, wq, wo, static_cast<__half*>(b1_hi),
+  dec_fold_i2t_kernel<<<P, 256, 0, (cudaStream_t)stream>>>(kt, vt, wq, wo, bo, static_cast<__half*>(b1_hi),
                                                            static_cast<__half*>(b1_lo), static_cast<__half*>(b2_hi),
                                                            static_cast<__half*>(b2_lo));
   return check_launch("dec_fold_i2t_kernel");
@@ -805,7 +815,7 @@ extern "C" int csam_dec_i2t_layer(const csam_i2t_layer_args* a, void* stream) {
 
 extern "C" int csam_dec_fold_t2i(const float* qt, int P, const float* wk, void* b1_hi, void* b1_lo, void* stream) {
   CSAM_REQUIRE(qt && wk && b1_hi && b1_lo && P > 0, "csam_dec_fold_t2i: bad args");
-  dec_fold_i2t_kernel<<<P, 256, 0, (cudaStream_t)stream>>>(qt, nullptr, wk, nullptr, static_cast<__half*>(b1_hi),
+  dec_fold_i2t_kernel<<<P, 256, 0, (cudaStream_t)stream>>>(qt, nullptr, wk, nullptr, nullptr, static_cast<__half*>(b1_hi),
                                                            static_cast<__half*>(b1_lo), nullptr, nullptr);
   return check_launch("dec_fold_i2t_kernel");
 }

@@ -390,9 +390,9 @@ class MaskDecoderEngine:
             if self.fused_i2t:
                 # q_proj, the 7-key softmax, out_proj, the residual and norm4 in ONE kernel: reads the keys once,
                 # writes the new keys once (as the h16 pair that is both next operand and next residual)
-                b1, b2 = ops.dec_fold_i2t(kt.view(P, 7, 128), vt.view(P, 7, 128), Lr["i2t_wq"], Lr["i2t_wo"])
+                b1, b2 = ops.dec_fold_i2t(kt.view(P, 7, 128), vt.view(P, 7, 128), Lr["i2t_wq"], Lr["i2t_wo"], ia.o.b)
                 keys_h = ops.dec_i2t_layer(I["keys0_h"] if li == 0 else keys_h, li == 0, Lr["peq_h"], b1, b2, P,
-                                           ia.o.b, Lr["n4"][0], Lr["n4"][1], 1e-5)
+                                           None, Lr["n4"][0], Lr["n4"][1], 1e-5)     # out_proj.bias is folded into b2
                 keys_f32 = None
                 continue
             qi = I["q0"] if li == 0 else qi1

@@ -95,7 +95,7 @@ _SIGS = {
     "csam_prompt_tokens": (ci, [vp, vp, ci, vp, vp, vp, vp, vp, vp]),
     "csam_attn_few_keys": (ci, [C.POINTER(DecAttnArgs), vp]),
     "csam_attn_few_queries": (ci, [C.POINTER(DecAttnArgs), vp]),
-    "csam_dec_fold_i2t": (ci, [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp]),
+    "csam_dec_fold_i2t": (ci, [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp]),
     "csam_dec_i2t_layer": (ci, [C.POINTER(I2TArgs), vp]),
     "csam_dec_fold_t2i": (ci, [vp, ci, vp, vp, vp, vp]),
     "csam_dec_t2i": (ci, [C.POINTER(T2IArgs), vp]),
@@ -142,7 +142,7 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.csam_abi_version() != 6:
+    if lib.csam_abi_version() != 7:
         raise RuntimeError("libcsam_sm100.so ABI version mismatch")
     _lib = lib
     return lib

@@ -312,7 +312,7 @@ def attn_few_queries(q, k, v, B, nq, nk, heads, hd, want_f32=False, want_h16=Fal
     return _dec_attn("csam_attn_few_queries", q, k, v, B, nq, nk, heads, hd, want_f32, want_h16, split)
 
 
-def dec_fold_i2t(kt: torch.Tensor, vt: torch.Tensor, wq: torch.Tensor, wo: torch.Tensor):
+def dec_fold_i2t(kt: torch.Tensor, vt: torch.Tensor, wq: torch.Tensor, wo: torch.Tensor, bo: Optional[torch.Tensor] = None):
     """kt, vt fp32 [P,7,128]; wq fp32 [128,256]; wo fp32 [256,128] -> (B1 H16 [P*64,384], B2 H16 [P*256,64])
     (csam_dec_fold_i2t: the 7 prompt tokens folded into the operands of the fused image->token layer)."""
     P = kt.shape[0]
@@ -321,7 +321,7 @@ def dec_fold_i2t(kt: torch.Tensor, vt: torch.Tensor, wq: torch.Tensor, wo: torch
     b1 = H16.empty((P * 64, 384), True, kt.device)
     b2 = H16.empty((P * 256, 64), True, kt.device)
     tok = _pb()
-    L.check(L.load().csam_dec_fold_i2t(_p(kt), _p(vt), P, _p(wq), _p(wo), _p(b1.hi), _p(b1.lo), _p(b2.hi), _p(b2.lo),
+    L.check(L.load().csam_dec_fold_i2t(_p(kt), _p(vt), P, _p(wq), _p(wo), _p(bo), _p(b1.hi), _p(b1.lo), _p(b2.hi), _p(b2.lo),
                                        _stream()), "csam_dec_fold_i2t")
     _pe("dec_fold_i2t", tok, 0.0)
     return b1, b2

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSAM_ABI_VERSION 6
+#define CSAM_ABI_VERSION 7
 #if defined(__GNUC__)
 #define CSAM_API __attribute__((visibility("default")))
 #else
@@ -201,6 +201,7 @@ typedef struct {
   void* out_hi; void* out_lo;
 } csam_i2t_layer_args;
 CSAM_API int csam_dec_fold_i2t(const float* kt, const float* vt, int P, const float* wq, const float* wo,
+                      const float* bo /* out_proj.bias or NULL: folded into b2 (then pass bias = NULL to the layer) */,
                       void* b1_hi, void* b1_lo, void* b2_hi, void* b2_lo, void* stream);
 CSAM_API int csam_dec_i2t_layer(const csam_i2t_layer_args* a, void* stream);
 

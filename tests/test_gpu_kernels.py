@@ -581,8 +581,8 @@ def test_gemm_epilogue_upscaling():
     assert _rel(masks, refm) < 1e-5
 
 
-@pytest.mark.parametrize("shared,P", [(True, 3), (False, 2), (False, 40)])
-def test_decoder_fused_i2t_layer(shared, P):
+@pytest.mark.parametrize("shared,P,fold_bias", [(True, 3, False), (False, 2, True), (False, 40, True)])
+def test_decoder_fused_i2t_layer(shared, P, fold_bias):
     """csam_dec_fold_i2t + csam_dec_i2t_layer against the reference formulation of the image->token half layer
     (transformer.py:184-190, 228-254) in fp64: q_proj(x + pe), 8 heads x 16 over the 7 prompt tokens, out_proj,
     residual, LayerNorm.  P = 40 spans several CTAs' tile ranges and prompt changes inside a range."""
@@ -598,8 +598,10 @@ def test_decoder_fused_i2t_layer(shared, P):
     xh = _h16(x, True)
     peq = (pe.double() @ wq.double().T + bq.double()).float()
     peq_h = _h16(peq, True)
-    b1, b2 = o.dec_fold_i2t(kt.to(DEV), vt.to(DEV), wq.to(DEV).contiguous(), wo.to(DEV).contiguous())
-    out = o.dec_i2t_layer(xh, shared, peq_h, b1, b2, P, bo.to(DEV), gam.to(DEV), bet.to(DEV), 1e-5)
+    # out_proj.bias either folded into B2 (what the engine does) or added in the epilogue
+    b1, b2 = o.dec_fold_i2t(kt.to(DEV), vt.to(DEV), wq.to(DEV).contiguous(), wo.to(DEV).contiguous(),
+                            bo.to(DEV) if fold_bias else None)
+    out = o.dec_i2t_layer(xh, shared, peq_h, b1, b2, P, None if fold_bias else bo.to(DEV), gam.to(DEV), bet.to(DEV), 1e-5)
     torch.cuda.synchronize()
     # reference in fp64 on the exact operand values the kernel saw (hi + lo of x and of peq)
     xd = xh.float().cpu().double()
