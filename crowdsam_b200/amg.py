@@ -190,22 +190,33 @@ def _coco_string(counts: Sequence[int]) -> str:
     x = c.copy()
     if n > 3:
         x[3:] -= c[1:-2]
-    groups = []          # per pass: (emitted char codes, active mask)
-    active = np.ones(n, dtype=bool)
-    while active.any():
-        low = x & 0x1F
-        x = x >> 5       # arithmetic shift, like the C code on a signed long
-        done = np.where((low & 0x10) != 0, x == -1, x == 0)
-        ch = np.where(done, low, low | 0x20) + 48
-        groups.append((ch, active.copy()))
-        active &= ~done
-    n_chars = np.zeros(n, dtype=np.int64)
-    for _, a in groups:
-        n_chars += a
-    starts = np.concatenate([[0], np.cumsum(n_chars)[:-1]])
+    # pass k emits the k-th character of every value that still has one.  Nearly all deltas of a mask fit one
+    # character, so the first pass is plain whole-array arithmetic and the later passes run on the small remainder.
+    def one_pass(v):
+        low = v & 0x1F
+        v = v >> 5                                   # arithmetic shift, like the C code on a signed long
+        done = v == -((low >> 4) & 1)                # sign bit set: finished when the rest is -1, else when it is 0
+        return v, done, (low | ((~done).astype(np.int64) << 5)) + 48
+
+    x, done, ch0 = one_pass(x)
+    ch0 = ch0.astype(np.uint8)
+    if done.all():
+        return ch0.tobytes().decode("ascii")
+    idx = np.flatnonzero(~done)
+    x = x[idx]
+    n_chars = np.ones(n, dtype=np.int64)
+    groups = []          # later passes: (indices of the values that emit a character, the char codes)
+    while idx.size:
+        x, done, ch = one_pass(x)
+        groups.append((idx, ch.astype(np.uint8)))
+        n_chars[idx] += 1
+        keep = ~done
+        idx, x = idx[keep], x[keep]
+    starts = np.cumsum(n_chars) - n_chars
     out = np.empty(int(n_chars.sum()), dtype=np.uint8)
-    for k, (ch, a) in enumerate(groups):
-        out[starts[a] + k] = ch[a]
+    out[starts] = ch0
+    for k, (ii, ch) in enumerate(groups):
+        out[starts[ii] + k + 1] = ch
     return out.tobytes().decode("ascii")
 
 

@@ -23,9 +23,11 @@ def resize_image(image: np.ndarray, max_size: int):
     """crowdsam/utils.py:141-156: scale so the longer side is max_size (may up-scale), cv2 bilinear."""
     import cv2
 
-    h, w = image.shape[:2]
-    r = min(max_size / w, max_size / h)
-    h, w = int(r * h), int(r * w)
+    h0, w0 = image.shape[:2]
+    r = min(max_size / w0, max_size / h0)
+    h, w = int(r * h0), int(r * w0)
+    if (h, w) == (h0, w0):
+        return image, r          # cv2.resize to the same size is the identity (SURVEY §8d): skip the 3 MB copy
     return cv2.resize(image, (w, h)), r
 
 
