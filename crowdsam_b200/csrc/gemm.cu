@@ -119,7 +119,11 @@ __device__ __forceinline__ void stage_get(const float* wb, int lane, float* v) {
 constexpr int BM = 128;
 constexpr int BK = 64;           // 64 fp16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 384;   // 4 control warps + 8 epilogue warps
+// 4 control warps + 8 epilogue warps; the two upscaling epilogues (EPI_UP1 / EPI_UP2) are bound by the instruction
+// count of their erf-GELUs (3.2 G per 1024 prompts) and run 16 epilogue warps (four per TMEM lane quadrant, one
+// (dy,dx) position each) so that the schedulers have 4 warps each to hide latencies with
+__host__ __device__ constexpr int gemm_epi_warps(int epi) { return (epi == 2 || epi == 3) ? 16 : 8; }
+__host__ __device__ constexpr int gemm_threads(int epi) { return 128 + 32 * gemm_epi_warps(epi); }
 
 // WRES ("weights resident"): the skinny decoder GEMMs (millions of rows, N <= BN, K <= 256) have a weight matrix
 // of at most 128 KB.  Streaming it with every tile would spend 1/2 .. 2/3 of the L2->SM fill bandwidth on
@@ -140,7 +144,7 @@ struct GemmCfg {
 };
 
 template <int BN, int SPLIT, bool B_MN, int EPI, bool WRES>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant__ CUtensorMap ta_lo,
                const __grid_constant__ CUtensorMap tw_hi, const __grid_constant__ CUtensorMap tw_lo,
                GemmEpi e, int K, int tiles_m, int tiles_n) {
@@ -173,7 +177,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); }   // tempty: one elected lane per epilogue warp
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], gemm_epi_warps(EPI)); }   // tempty: one elected lane per epilogue warp
     mbar_init(w_bar, 1);
     fence_barrier_init();
   }
@@ -187,7 +191,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
   // two epilogue warpgroups (384 x 168 = 128 x 56 + 256 x 224)
   // (each role executes its own setmaxnreg at the top of its branch: ptxas budgets registers per region and a
   //  join after the instruction would force the smaller budget on everything that follows)
-  constexpr bool REGSPLIT = (EPI == EPI_LN);
+  constexpr bool REGSPLIT = (EPI == EPI_LN) || gemm_epi_warps(EPI) == 16;
+  constexpr int NEW = gemm_epi_warps(EPI);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -287,11 +292,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
     if constexpr (REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   } else {
     // ------------------------------------------------------------------ epilogue
-    if constexpr (REGSPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    if constexpr (EPI == EPI_LN) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");       // 128 x 56 + 256 x 224
+    if constexpr (NEW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");          // 128 x 56 + 512 x 104 <= 640 x 96
     const int ew = warp - 4;
     const int q = ew & 3;                        // TMEM lane quadrant == warp % 4
-    const int ch = ew >> 2;                      // which half of the tile's columns this warp owns
-    constexpr int HALF = BN / 2;
+    const int ch = ew >> 2;                      // which half (8 warps) or quarter (16 warps) of the tile's columns
+    constexpr int HALF = BN / (NEW / 4);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     int local = 0;
     if constexpr (EPI == EPI_LN) {
@@ -307,13 +313,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
       const int et = threadIdx.x - 128;
       float* sg = epi_smem + 1024;
       if (et < 64) { sg[et] = e.gamma[et]; sg[64 + et] = e.beta[et]; }
-      sg[128 + et] = e.bias[et];
-      asm volatile("bar.sync 5, 256;" ::: "memory");
+      if (et < 256) sg[128 + et] = e.bias[et];
+      asm volatile("bar.sync 5, 512;" ::: "memory");
     }
     if constexpr (EPI == EPI_UP2) {
       const int et = threadIdx.x - 128;
       if (et < 128) epi_smem[1024 + et] = e.bias[et];
-      asm volatile("bar.sync 5, 256;" ::: "memory");
+      asm volatile("bar.sync 5, 512;" ::: "memory");
     }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
       const int buf = local & 1;
@@ -324,7 +330,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
         // stage the 4 x 32 hypernetwork vectors of this tile's prompt (all 128 rows share it)
         const int et = threadIdx.x - 128;
         if (et < 128) epi_smem[buf * 128 + (et & 31) * 4 + (et >> 5)] = e.hyper[(size_t)(m0 >> 14) * 128 + et];   // [l][j] -> [j][l]
-        asm volatile("bar.sync 5, 256;" ::: "memory");
+        asm volatile("bar.sync 5, 512;" ::: "memory");
       }
       if constexpr (EPI != EPI_LN && EPI != EPI_STD) {   // EPI_LN / EPI_STD request their residual first, then wait
         mbar_wait(&tfull_bar[buf], bphase);
@@ -574,21 +580,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
         }
         continue;   // tempty already signalled
       } else if constexpr (EPI == EPI_UP1) {
-        // two of the four (dy,dx) positions per warp half: pos = ch*2 + g ; row-per-lane, whole sectors per lane
+        // one of the four (dy,dx) positions per warp: pos = ch ; row-per-lane, whole sectors per lane
         const float* s_gamma = epi_smem + 1024;      // [64], staged once per CTA
         const float* s_beta = s_gamma + 64;          // [64]
         const float* s_bias = s_gamma + 128;         // [256]
         const bool valid = r < e.M;
         const int p = r >> 12, pix = r & 4095, yy = pix >> 6, xx = pix & 63;
-#pragma unroll 1
-        for (int gI = 0; gI < 2; ++gI) {
-          const int pos = ch * 2 + gI;
+        {
+          const int pos = ch;
           float x[64];
           float sum = 0.f;
 #pragma unroll
           for (int c = 0; c < 64; c += 16) {
             uint32_t raw[16];
-            tmem_ld16(col_addr + gI * 64 + c, raw);
+            tmem_ld16(col_addr + c, raw);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
@@ -624,36 +629,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
           }
         }
       } else if constexpr (EPI == EPI_UP2) {
-        // row r = p*16384 + Y1*128 + X1 ; this warp half handles dy = ch, dx = 0,1 (32 channels each)
+        // row r = p*16384 + Y1*128 + X1 ; this warp handles position (dy,dx) = (ch >> 1, ch & 1), 32 channels
         const bool valid = r < e.M;
         const int p = r >> 14, pix = r & 16383, Y1 = pix >> 7, X1 = pix & 127;
         const float* hy = epi_smem + buf * 128;      // [32 channels][4 masks]
         const float* s_bias = epi_smem + 1024;       // [128], staged once per CTA
-        float mk[4][2];
+        uint32_t raw[32];
+        tmem_ld32(col_addr, raw);
+        tmem_ld_wait();
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          uint32_t raw[32];
-          tmem_ld32(col_addr + dx * 32, raw);
-          tmem_ld_wait();
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(s_bias + ch * 32 + j);
+          const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(s_bias + (ch * 2 + dx) * 32 + j);
-            const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float u = gelu_erf(__uint_as_float(raw[j + k]) + bb[k]);
-              const float4 h = *reinterpret_cast<const float4*>(hy + (j + k) * 4);
-              a0 = fmaf(u, h.x, a0); a1 = fmaf(u, h.y, a1); a2 = fmaf(u, h.z, a2); a3 = fmaf(u, h.w, a3);
-            }
+          for (int k = 0; k < 4; ++k) {
+            const float u = gelu_erf(__uint_as_float(raw[j + k]) + bb[k]);
+            const float4 h = *reinterpret_cast<const float4*>(hy + (j + k) * 4);
+            a0 = fmaf(u, h.x, a0); a1 = fmaf(u, h.y, a1); a2 = fmaf(u, h.z, a2); a3 = fmaf(u, h.w, a3);
           }
-          mk[0][dx] = a0; mk[1][dx] = a1; mk[2][dx] = a2; mk[3][dx] = a3;
         }
         if (valid) {
-          const int Y = 2 * Y1 + ch, X0 = 2 * X1;
-#pragma unroll
-          for (int l = 0; l < 4; ++l)
-            *reinterpret_cast<float2*>(e.masks + (((size_t)p * 4 + l) * 256 + Y) * 256 + X0) = make_float2(mk[l][0], mk[l][1]);
+          const int Y = 2 * Y1 + (ch >> 1), X = 2 * X1 + (ch & 1);
+          float* mo = e.masks + (((size_t)p * 4) * 256 + Y) * 256 + X;
+          mo[0] = a0; mo[65536] = a1; mo[2 * 65536] = a2; mo[3 * 65536] = a3;
         }
       }
       tc_fence_before();
@@ -776,7 +775,7 @@ static int launch_tc(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st)
   const int tiles_n = (a->N + BN - 1) / BN;
   int grid = min(tiles_m * tiles_n, num_sms());
   if (WRES) grid = (grid / tiles_n) * tiles_n;      // fixed n index per CTA (see the producer)
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, e, a->K, tiles_m, tiles_n);
+  kern<<<grid, gemm_threads(EPI), Cfg::SMEM_BYTES, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, e, a->K, tiles_m, tiles_n);
   return check_launch("gemm_tc_kernel");
 }
 
