@@ -401,7 +401,7 @@ struct AttnTsBars {
 template <int SPLIT, int BIAS, int NQ>
 __global__ void __launch_bounds__(128 + 128 * NQ, 1)
 vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_constant__ CUtensorMap t_lo,
-                        csam_attn_args a, const float* __restrict__ rel) {
+                        csam_attn_args a, const float* __restrict__ rel, int n_full, int n_single) {
   using Cfg = AttnTsCfg<SPLIT, BIAS, NQ>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -410,7 +410,19 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
   float* rel_s = reinterpret_cast<float*>(smem + Cfg::OFF_REL);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * (AT_BM * NQ);
+  // Work items in launch order: first every (query-tile pair, head, group) item, then the single-tile items.  With
+  // 336 equal pair items on 148 SMs a third of the last wave's SMs idle; sized as 2 full waves of pairs plus a
+  // wave of (shorter) single-tile CTAs the tail is one short wave instead (DINOv2: 288 + 96 CTAs).
+  const int HG = a.heads * a.groups;
+  const int lin = blockIdx.x;
+  int nqa, q0, hg;
+  if (lin < n_full * HG) {
+    nqa = NQ; q0 = (lin % n_full) * (AT_BM * NQ); hg = lin / n_full;
+  } else {
+    const int l2 = lin - n_full * HG;
+    nqa = 1; q0 = n_full * (AT_BM * NQ) + (l2 % n_single) * AT_BM; hg = l2 / n_single;
+  }
+  const int h = hg % a.heads, g = hg / a.heads;
   const int D = a.heads * AT_HD;
   const int row_base = g * a.tokens;
   const int n_tiles = (a.tokens + AT_BN - 1) / AT_BN;
@@ -460,7 +472,8 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_f16(AT_BM, AT_BN, 0, 0);
 #pragma unroll
-      for (int t = 0; t < NQ; ++t) mbar_wait(&bars->q_ready[t], 0);
+      for (int t = 0; t < NQ; ++t)
+        if (t < nqa) mbar_wait(&bars->q_ready[t], 0);
       tc_fence_after();
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % STAGES;
@@ -468,6 +481,7 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
         const uint32_t kd = umma_desc_lo(smem_u32(smem + st * Cfg::STAGE_BYTES), 16);
 #pragma unroll
         for (int t = 0; t < NQ; ++t) {
+          if (t >= nqa) break;
           // S(j) overwrites the buffer that held S(j-2) and then P(j-2): P V(j-2) must have retired
           if (j >= 2) mbar_wait(&bars->pv_done[t][j & 1], ((j - 2) >> 1) & 1);
           tc_fence_after();
@@ -495,6 +509,7 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
         const uint32_t vd = umma_desc_lo(smem_u32(smem + st * Cfg::STAGE_BYTES + Cfg::NOPS * Cfg::KV_TILE), 8192);
 #pragma unroll
         for (int t = 0; t < NQ; ++t) {
+          if (t >= nqa) break;
           mbar_wait(&bars->p_full[t][b], (j >> 1) & 1);
           tc_fence_after();
           const uint32_t pa = tmem_base + t * 256 + b * AT_BN;      // P(j): 32 columns of fp16 pairs over S(j)
@@ -520,6 +535,7 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
     const uint32_t o_addr = lane_addr + 128;
     constexpr float LOG2E = 1.4426950408889634f;
     const float scale2 = a.scale * LOG2E;
+    if (qt < nqa) {                      // the second warpgroup of a single-tile CTA has nothing to do
     {
       // this thread's Q row -> TMEM (A operand of every S MMA of the CTA)
       const __half* qh = static_cast<const __half*>(a.qkv_hi) + ((size_t)row_base + qc) * a.ld_qkv + (size_t)h * AT_HD;
@@ -654,6 +670,7 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
         }
       }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -676,8 +693,19 @@ static int launch_attn_ts(const csam_attn_args* a, const float* rel, cudaStream_
       return fail("%s", "cudaFuncSetAttribute(smem) failed for vit_attention_ts_kernel");
     attr = true;
   }
-  dim3 grid((a->tokens + AT_BM * NQ - 1) / (AT_BM * NQ), a->heads, a->groups);
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(t_hi, t_lo, *a, rel);
+  // query tiles -> n_full items of NQ tiles + n_single items of one tile (per head and group)
+  const int tiles = (a->tokens + AT_BM - 1) / AT_BM;
+  const int HG = a->heads * a->groups;
+  int n_full = (tiles + NQ - 1) / NQ, n_single = 0;
+  if (NQ == 2 && n_full * HG > 148) {
+    const int waves = (n_full * HG) / 148;               // full waves of pair items
+    const int p = (waves * 148) / HG;                    // pairs per (head, group) that fit those waves
+    const int s1 = tiles - 2 * p;
+    static const int tail_env = getenv("CSAM_ATTN_TAIL") ? atoi(getenv("CSAM_ATTN_TAIL")) : 1;
+    if (tail_env && p > 0 && s1 > 0 && s1 * HG <= 148 && (n_full * HG) % 148 != 0) { n_full = p; n_single = s1; }
+  }
+  dim3 grid((n_full + n_single) * HG);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(t_hi, t_lo, *a, rel, n_full, n_single > 0 ? n_single : 1);
   return check_launch("vit_attention_ts_kernel");
 }
 

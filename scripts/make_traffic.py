@@ -6,7 +6,7 @@ import csv, json, sys
 CLASSES = {   # bench.py roofline name -> (report file prefix, kernel-name substring)
     "gemm_tensor": ("prof_gemm_enc", "gemm_tc_kernel<128, 3, 0, 0, 0>"),
     "gemm_hbm": ("prof_gemm_up", "gemm_tc_kernel"),
-    "vit_attention": ("prof_attn_dino", "vit_attention_tc_kernel"),
+    "vit_attention": ("prof_attn_dino", "vit_attention_t"),
     "dec_i2t_layer": ("prof_dec_i2t", "dec_i2t_layer_kernel"),
     "dec_t2i": ("prof_dec_t2i", "dec_t2i_kernel"),
     "mask_post_write": ("prof_post_r", "post_write_quad_kernel"),
