@@ -110,6 +110,8 @@ _SIGS = {
     "csam_mask_overlap_scratch_bytes": (cll, [ci]),
     "csam_mask_overlap": (ci, [vp, ci, ci, ci, vp, vp, vp, cll, vp]),
     "csam_points_occupied": (ci, [vp, ci, ci, ci, vp, vp, ci, vp, vp]),
+    "csam_small_regions_scratch_bytes": (cll, [ci, ci, ci]),
+    "csam_remove_small_regions": (ci, [vp, ci, ci, ci, ci, ci, vp, vp, cll, vp]),
     "csam_rle_count": (ci, [vp, ci, ci, ci, vp, vp]),
     "csam_rle_fill": (ci, [vp, ci, ci, ci, vp, vp, vp]),
 }
@@ -142,7 +144,7 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.csam_abi_version() != 7:
+    if lib.csam_abi_version() != 8:
         raise RuntimeError("libcsam_sm100.so ABI version mismatch")
     _lib = lib
     return lib

@@ -517,3 +517,21 @@ def rle_encode(masks: torch.Tensor):
     runs_h = runs.cpu().numpy()
     o = offs.numpy()
     return [runs_h[o[i]:o[i + 1]] for i in range(n)]
+
+
+def remove_small_regions(masks: torch.Tensor, area_thresh: int, mode: str) -> torch.Tensor:
+    """In-place device version of amg.remove_small_regions for a batch of masks (uint8 [n,h,w], values 0/1):
+    mode "holes" fills background components smaller than area_thresh, mode "islands" drops foreground components
+    smaller than it (keeping the largest if all are).  Returns changed uint8 [n] (any component below the threshold)."""
+    assert masks.dtype == torch.uint8 and masks.dim() == 3 and masks.is_contiguous() and mode in ("holes", "islands")
+    n, h, w = masks.shape
+    changed = torch.zeros((n,), dtype=torch.uint8, device=masks.device)
+    if n == 0:
+        return changed
+    need = L.load().csam_small_regions_scratch_bytes(n, h, w)
+    scratch = torch.empty(need, dtype=torch.uint8, device=masks.device)
+    tok = _pb()
+    L.check(L.load().csam_remove_small_regions(_p(masks), n, h, w, int(area_thresh), 0 if mode == "holes" else 1,
+                                               _p(changed), _p(scratch), need, _stream()), "csam_remove_small_regions")
+    _pe("small_regions", tok, float(n) * h * w)
+    return changed

@@ -234,22 +234,23 @@ class CrowdSAM:
 
     @staticmethod
     def postprocess_small_regions(mask_data: MaskData, min_area: int, nms_thresh: float) -> MaskData:
-        """model.py:395-443: OpenCV connected components on the host (integer exact), NMS on the device."""
+        """model.py:395-443 with the connected-component passes on the device (csam_remove_small_regions, integer
+        exact against the cv2.connectedComponentsWithStats path of the reference): no per-mask D2H copy, no host loop."""
         if len(mask_data["masks"]) == 0:
             return mask_data
-        dev = mask_data["masks"].device
-        new_masks, scores = [], []
-        for mask in mask_data["masks"].cpu().numpy():
-            mask, c1 = amg.remove_small_regions(mask, min_area, mode="holes")
-            mask, c2 = amg.remove_small_regions(mask, min_area, mode="islands")
-            new_masks.append(torch.as_tensor(mask).unsqueeze(0))
-            scores.append(float(not c1 and not c2))
-        masks = torch.cat(new_masks, dim=0).to(dev)
-        boxes = amg.batched_mask_to_box(masks)
-        keep = ops.box_nms(boxes.float(), torch.as_tensor(scores, device=dev), nms_thresh)
-        for i in keep.tolist():
-            if scores[i] == 0.0:
-                mask_data["boxes"][i] = boxes[i]
-                mask_data["masks"][i] = masks[i]
+        old = mask_data["masks"]
+        masks = old.to(torch.uint8).contiguous().clone()
+        # the reference compares `size < area_thresh` with the config value as is (float or int)
+        thr = int(np.ceil(min_area))
+        c1 = ops.remove_small_regions(masks, thr, "holes")
+        c2 = ops.remove_small_regions(masks, thr, "islands")
+        scores = ((c1 | c2) == 0).float()                      # unchanged masks win the NMS (model.py:425-434)
+        new_masks = masks.to(old.dtype)
+        boxes = amg.batched_mask_to_box(new_masks.bool())
+        keep = ops.box_nms(boxes.float(), scores, nms_thresh)
+        upd = keep[scores[keep] == 0.0]
+        if upd.numel() > 0:
+            mask_data["boxes"][upd] = boxes[upd].to(mask_data["boxes"].dtype)
+            mask_data["masks"][upd] = new_masks[upd]
         mask_data.filter(keep)
         return mask_data

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSAM_ABI_VERSION 7
+#define CSAM_ABI_VERSION 8
 #if defined(__GNUC__)
 #define CSAM_API __attribute__((visibility("default")))
 #else
@@ -294,6 +294,19 @@ CSAM_API long long csam_mask_overlap_scratch_bytes(int n);
  * with flag[j] != 0. */
 CSAM_API int csam_points_occupied(const uint8_t* masks, int n_masks, int h, int w, const uint8_t* flag,
                          const int* pts_xy, int n_pts, uint8_t* occ, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K-CC  remove_small_regions on the device (amg.py:267-291 = cv2.connectedComponentsWithStats(working, 8) + area
+ * filter, called per mask on the host from crowdsam/model.py:395-443).  masks uint8 [n,h,w] (0/1), edited in place.
+ *   mode 0 "holes":   background components smaller than area_thresh are filled;
+ *   mode 1 "islands": foreground components smaller than area_thresh are dropped; if all are smaller the largest
+ *                     is kept (ties: the component OpenCV labels first).
+ * changed[i] = 1 when mask i had any component below the threshold (the reference's second return value).
+ * Integer-exact against OpenCV.  scratch >= csam_small_regions_scratch_bytes(n,h,w).
+ * ------------------------------------------------------------------------------------------ */
+CSAM_API long long csam_small_regions_scratch_bytes(int n, int h, int w);
+CSAM_API int csam_remove_small_regions(uint8_t* masks, int n, int h, int w, int area_thresh, int mode, uint8_t* changed,
+                              void* scratch, long long scratch_bytes, void* stream);
 
 /* Column-major run-length encoding of bool masks (amg.py:107-135), two passes:
  * count: n_runs[i] = number of runs of mask i (the first run counts zeros; 0 if the mask starts

@@ -644,3 +644,52 @@ def test_decoder_fused_t2i(shared, P):
     ref = (torch.softmax(qh @ kh.transpose(-1, -2) / 4.0, dim=-1) @ vh).permute(0, 2, 1, 3).reshape(P, 7, 128)
     assert _rel(of, ref) < 5e-5
     assert _rel(oh.float(), ref) < 5e-5
+
+
+def _region_masks(h, w, n, seed):
+    """Blobs + salt-and-pepper noise + a few hand-made corner cases for the connected-component kernel."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    masks = np.zeros((n, h, w), dtype=bool)
+    for i in range(n):
+        for _ in range(rng.integers(1, 5)):
+            cy, cx, r = rng.integers(0, h), rng.integers(0, w), rng.integers(3, max(4, min(h, w) // 3))
+            masks[i] |= (yy - cy) ** 2 + (xx - cx) ** 2 < r * r
+        noise = rng.random((h, w))
+        masks[i] ^= noise < 0.02 * (i % 4)                      # holes and islands of a few pixels
+    masks[0] = False                                            # empty mask
+    masks[1] = True                                             # full mask
+    if n > 3:
+        # all components small and of EQUAL size: A starts at (1,10) (block row 0, block col 5), B at (0,20)
+        # (block col 10): pixel-raster order says B first, OpenCV's 2x2-block scan says A first
+        masks[2] = False
+        masks[2, 1:3, 10:12] = True
+        masks[2, 0:2, 20:22] = True
+        masks[2, 9:11, 3:5] = True
+        masks[3] = False                                        # diagonal (8-connected) chain + isolated pixel
+        for k in range(12):
+            masks[3, 5 + k, 7 + k] = True
+        masks[3, 30, 40] = True
+    return masks
+
+
+@pytest.mark.parametrize("h,w,thr", [(256, 320, 30), (123, 77, 5), (200, 200, 100), (64, 64, 3)])
+def test_remove_small_regions_vs_opencv(h, w, thr):
+    """csam_remove_small_regions against the reference's own implementation (amg.py:267-291 on OpenCV),
+    bit-exact masks and changed flags, both modes, chained as model.py:411-412 does."""
+    from crowdsam_b200 import amg
+    o = ops()
+    masks = _region_masks(h, w, 40, seed=h + thr)
+    dev = torch.as_tensor(masks).to(torch.uint8).to(DEV).contiguous()
+    for mode in ("holes", "islands"):
+        want, flags = [], []
+        for m in dev.cpu().numpy().astype(bool):
+            r, c = amg.remove_small_regions(m, thr, mode)
+            want.append(r)
+            flags.append(c)
+        changed = o.remove_small_regions(dev, thr, mode)
+        torch.cuda.synchronize()
+        got = dev.cpu().numpy().astype(bool)
+        assert np.array_equal(changed.cpu().numpy().astype(bool), np.array(flags)), mode
+        for i in range(len(want)):
+            assert np.array_equal(got[i], want[i]), (mode, i, int((got[i] != want[i]).sum()))
