@@ -141,9 +141,21 @@ def stage_case():
     print("wrote stage", {k: v.shape for k, v in out.items()})
 
 
+def config0_case():
+    """BASELINE.json configs[0] at FULL depth: SAM ViT-B (12 blocks) + DINOv2 ViT-L/14 (24 blocks) through the real
+    reference on CPU, 1024x1024 synthetic image, 8x8 prompt grid -> model_vit_b.npz, pipeline_vit_b_grid8.npz."""
+    sam, dino = model_case("vit_b", "vit_b", "dinov2_vitl14")
+    pipeline_case("vit_b_grid8", sam, dino,
+                  dict(grid_size=8, pos_sim_thresh=-1, max_prompts=64, points_per_batch=32,
+                       filter_thresh=2.0, min_mask_region_area=0))
+
+
 if __name__ == "__main__":
     assert ref_import.available(), "needs /root/reference"
     torch.manual_seed(0)
+    if "--config0" in sys.argv:          # only the (slow, ~3 min) full-depth case; the other files stay as they are
+        config0_case()
+        sys.exit(0)
     stage_case()
     sam, dino = model_case("tiny", "tiny", "tiny")
     pipeline_case("tiny_grid8", sam, dino,
@@ -154,3 +166,4 @@ if __name__ == "__main__":
                        filter_thresh=0.3, min_mask_region_area=100, pred_iou_thresh=0.05,
                        stability_score_thresh=0.5), image_index=2, hw=(768, 1024))
     model_case("tiny_l", "tiny_l", "tiny")
+    config0_case()

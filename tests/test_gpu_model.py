@@ -57,7 +57,11 @@ def test_set_image_vs_oracle_and_golden(arch, golden_dir):
     assert pred.features.shape == (1, 256, 64, 64) and pred.dino_feats.shape == (1, 73, 73, 1024)
     assert _rel(pred.features, feats) < TOL, _rel(pred.features, feats)
     assert _rel(pred.dino_feats, dino) < TOL, _rel(pred.dino_feats, dino)
-    g = np.load(os.path.join(golden_dir, f"model_{arch}.npz"))
+    _check_model_golden(pred, np.load(os.path.join(golden_dir, f"model_{arch}.npz")))
+
+
+def _check_model_golden(pred, g):
+    """pred has the square golden image set: compare with the real reference's outputs stored by make_golden.py."""
     assert _rel(pred.features[:, ::8, ::2, ::2], g["features"]) < TOL
     assert _rel(pred.dino_feats[:, ::6, ::6, ::8], g["dino_feats"]) < TOL
     assert _rel(pred.predict_fg_map()[:, :, ::4, ::4], g["fg_map"]) < TOL
@@ -133,6 +137,12 @@ def test_crowdsam_generate_vs_golden_and_oracle(name, golden_dir):
     test_cfg = dict(restate.DEFAULT_TEST_CFG)
     test_cfg.update(over)
     test_cfg.update(apply_box_offsets=False, fuse_simmap=False, output_rles=True)
+    _check_pipeline_golden(pred, g, test_cfg)
+
+
+def _check_pipeline_golden(pred, g, test_cfg):
+    from crowdsam_b200.pipeline import CrowdSAM
+
     cfg = {"environ": {"device": DEV}, "model": {"trainfree": False}, "test": test_cfg}
     model = CrowdSAM(cfg, None, predictor=pred)
     hw = tuple(int(x) for x in g["hw"])
@@ -148,6 +158,21 @@ def test_crowdsam_generate_vs_golden_and_oracle(name, golden_dir):
     for r, ref in zip(res["rles"], g["rle_counts"]):
         a, b = _decode_coco(r["counts"], r["size"]), _decode_coco(str(ref), r["size"])
         assert (a != b).mean() < 1e-4
+
+
+def test_config0_vit_b_full_depth_vs_reference(golden_dir):
+    """BASELINE.json configs[0]: SAM ViT-B at full depth (12 blocks) + DINOv2 ViT-L/14 (24 blocks), 1024x1024 synthetic
+    image, 8x8 prompt grid, against the outputs of the REAL reference run on CPU (tests/golden/make_golden.py
+    --config0): encoder features, DINOv2 tokens, fg map, decoder logits / IoU / class scores, and CrowdSAM.generate."""
+    pred, *_ = make_predictor("vit_b", "dinov2_vitl14")
+    pred.set_image(weights.synthetic_image(0))
+    _check_model_golden(pred, np.load(os.path.join(golden_dir, "model_vit_b.npz")))
+    g = np.load(os.path.join(golden_dir, "pipeline_vit_b_grid8.npz"))
+    test_cfg = dict(restate.DEFAULT_TEST_CFG)
+    for k, v in zip(g["cfg_keys"], g["cfg_vals"]):
+        test_cfg[str(k)] = int(str(v)) if str(v).lstrip("-").isdigit() else float(str(v))
+    test_cfg.update(apply_box_offsets=False, fuse_simmap=False, output_rles=True)
+    _check_pipeline_golden(pred, g, test_cfg)
 
 
 def test_errors_and_state():

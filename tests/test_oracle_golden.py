@@ -55,6 +55,16 @@ def test_encoder_dino_decoder_square(model_case):
     _close(full[:, :, ::32, ::32], g["masks"], what="masks")
 
 
+def test_config0_vit_b_full_depth(golden_dir):
+    """BASELINE.json configs[0] at full depth (SAM ViT-B 12 blocks + DINOv2 ViT-L/14 24 blocks): the oracle against
+    the real reference's outputs (about a minute of CPU)."""
+    g = np.load(os.path.join(golden_dir, "model_vit_b.npz"))
+    sam_sd, dino_sd = weights.make_sam_state("vit_b"), weights.make_dino_state("dinov2_vitl14")
+    _, depth, heads, glob = weights.SAM_ARCHS["vit_b"]
+    _, ddepth, dheads = weights.DINO_ARCHS["dinov2_vitl14"]
+    test_encoder_dino_decoder_square((g, sam_sd, dino_sd, (depth, heads, glob), (ddepth, dheads)))
+
+
 def test_non_square_image(model_case):
     g, sam_sd, dino_sd, scfg, dcfg = model_case
     from PIL import Image
