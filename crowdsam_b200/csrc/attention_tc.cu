@@ -377,11 +377,13 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
 //   P(j): fp16 pairs written over the first 32 columns of S(j) after S(j) has been read (no shared memory, no proxy
 //         fence); S(j+2) may only be issued once P V(j) has retired.
 // Shared memory holds nothing but the K/V ring (6-7 stages).
-template <int SPLIT, int BIAS, int NQ>
+template <int SPLIT, int BIAS, int NQ, int HD = 64>
 struct AttnTsCfg {
   static constexpr int NOPS = (SPLIT == 3) ? 2 : 1;
   static constexpr int THREADS = 128 + 128 * NQ;
-  static constexpr int KV_TILE = AT_BN * AT_HD * 2;          // 8 KB
+  static_assert(HD == 64 || (HD == 80 && NQ == 1), "head dim 64, or 80 with one query tile per CTA");
+  static constexpr int NA = (HD + 63) / 64;                  // 64-wide swizzle atoms per K / V tile (80 -> 2, the second 1/4 used)
+  static constexpr int KV_TILE = NA * AT_BN * 64 * 2;        // 8 KB per atom
   static constexpr int STAGE_BYTES = NOPS * 2 * KV_TILE;
   static constexpr int REL_BYTES = (BIAS == 1) ? NQ * AT_BM * AT_REL_LD * 4 : 0;
   static constexpr int STAGES_FIT = (227 * 1024 - REL_BYTES - 512 - 1024) / STAGE_BYTES;
@@ -389,7 +391,10 @@ struct AttnTsCfg {
   static constexpr int OFF_REL = STAGES * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_REL + REL_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
-  static constexpr int TMEM_COLS = 256 * NQ;
+  // TMEM columns per query tile: S0 | P0 [0,64)  S1 | P1 [64,128)  O [128,128+HD)  Q hi  Q lo (HD/2 columns each)
+  static constexpr int COL_O = 128, COL_QH = 128 + HD, COL_QL = COL_QH + HD / 2;
+  static constexpr int TSTRIDE = (HD == 64) ? 256 : 512;
+  static constexpr int TMEM_COLS = TSTRIDE * NQ;
 };
 
 struct AttnTsBars {
@@ -398,12 +403,13 @@ struct AttnTsBars {
   uint32_t tmem_slot;
 };
 
-template <int SPLIT, int BIAS, int NQ>
+template <int SPLIT, int BIAS, int NQ, int HD>
 __global__ void __launch_bounds__(128 + 128 * NQ, 1)
 vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_constant__ CUtensorMap t_lo,
                         csam_attn_args a, const float* __restrict__ rel, int n_full, int n_single) {
-  using Cfg = AttnTsCfg<SPLIT, BIAS, NQ>;
+  using Cfg = AttnTsCfg<SPLIT, BIAS, NQ, HD>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int TS = Cfg::TSTRIDE;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   AttnTsBars* bars = reinterpret_cast<AttnTsBars*>(smem + Cfg::OFF_BAR);
@@ -423,7 +429,7 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
     nqa = 1; q0 = n_full * (AT_BM * NQ) + (l2 % n_single) * AT_BM; hg = l2 / n_single;
   }
   const int h = hg % a.heads, g = hg / a.heads;
-  const int D = a.heads * AT_HD;
+  const int D = a.heads * HD;
   const int row_base = g * a.tokens;
   const int n_tiles = (a.tokens + AT_BN - 1) / AT_BN;
 
@@ -459,11 +465,14 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
         uint8_t* sv = sk + Cfg::NOPS * Cfg::KV_TILE;
         mbar_expect_tx(&bars->kv_full[st], Cfg::STAGE_BYTES);
         const int row = row_base + j * AT_BN;
-        tma_load_2d(sk, &t_hi, &bars->kv_full[st], D + h * AT_HD, row);
-        tma_load_2d(sv, &t_hi, &bars->kv_full[st], 2 * D + h * AT_HD, row);
-        if (SPLIT == 3) {
-          tma_load_2d(sk + Cfg::KV_TILE, &t_lo, &bars->kv_full[st], D + h * AT_HD, row);
-          tma_load_2d(sv + Cfg::KV_TILE, &t_lo, &bars->kv_full[st], 2 * D + h * AT_HD, row);
+#pragma unroll
+        for (int at = 0; at < Cfg::NA; ++at) {      // head dim 80: a second 64-wide box of which 16 columns are used
+          tma_load_2d(sk + at * 8192, &t_hi, &bars->kv_full[st], D + h * HD + at * 64, row);
+          tma_load_2d(sv + at * 8192, &t_hi, &bars->kv_full[st], 2 * D + h * HD + at * 64, row);
+          if (SPLIT == 3) {
+            tma_load_2d(sk + Cfg::KV_TILE + at * 8192, &t_lo, &bars->kv_full[st], D + h * HD + at * 64, row);
+            tma_load_2d(sv + Cfg::KV_TILE + at * 8192, &t_lo, &bars->kv_full[st], 2 * D + h * HD + at * 64, row);
+          }
         }
       }
     }
@@ -485,14 +494,15 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
           // S(j) overwrites the buffer that held S(j-2) and then P(j-2): P V(j-2) must have retired
           if (j >= 2) mbar_wait(&bars->pv_done[t][j & 1], ((j - 2) >> 1) & 1);
           tc_fence_after();
-          const uint32_t d = tmem_base + t * 256 + (j & 1) * AT_BN;
-          const uint32_t qa = tmem_base + t * 256 + 192;
+          const uint32_t d = tmem_base + t * TS + (j & 1) * AT_BN;
+          const uint32_t qa = tmem_base + t * TS + Cfg::COL_QH;
 #pragma unroll
-          for (int k = 0; k < AT_HD / 16; ++k) {
-            umma_f16_ts(d, qa + 8 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
+          for (int k = 0; k < HD / 16; ++k) {
+            const uint32_t kk = kd + (k >> 2) * (8192 >> 4) + 2 * (k & 3);      // swizzle atom k/4, 32-byte step k%4
+            umma_f16_ts(d, qa + 8 * k, kk, idesc_s, k ? 1u : 0u);
             if (SPLIT == 3) {
-              umma_f16_ts(d, qa + 32 + 8 * k, kd + 2 * k, idesc_s, 1u);
-              umma_f16_ts(d, qa + 8 * k, kd + (Cfg::KV_TILE >> 4) + 2 * k, idesc_s, 1u);
+              umma_f16_ts(d, qa + HD / 2 + 8 * k, kk, idesc_s, 1u);
+              umma_f16_ts(d, qa + 8 * k, kk + (Cfg::KV_TILE >> 4), idesc_s, 1u);
             }
           }
           umma_commit(&bars->s_full[t][j & 1]);
@@ -502,7 +512,7 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer #2: O += P V, P from TMEM
     if (lane == 0) {
-      constexpr uint32_t idesc_pv = umma_idesc_f16(AT_BM, AT_HD, 0, 1);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(AT_BM, HD, 0, 1);
       for (int j = 0; j < n_tiles; ++j) {
         const int b = j & 1;
         const int st = j % STAGES;
@@ -512,8 +522,8 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
           if (t >= nqa) break;
           mbar_wait(&bars->p_full[t][b], (j >> 1) & 1);
           tc_fence_after();
-          const uint32_t pa = tmem_base + t * 256 + b * AT_BN;      // P(j): 32 columns of fp16 pairs over S(j)
-          const uint32_t d = tmem_base + t * 256 + 128;
+          const uint32_t pa = tmem_base + t * TS + b * AT_BN;      // P(j): 32 columns of fp16 pairs over S(j)
+          const uint32_t d = tmem_base + t * TS + Cfg::COL_O;
 #pragma unroll
           for (int k = 0; k < AT_BN / 16; ++k) {
             umma_f16_ts(d, pa + 8 * k, vd + 128 * k, idesc_pv, (j | k) ? 1u : 0u);
@@ -531,23 +541,28 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
     const int r = wq * 32 + lane;
     const int q = q0 + qt * AT_BM + r;
     const int qc = min(q, a.tokens - 1);
-    const uint32_t lane_addr = tmem_base + qt * 256 + ((uint32_t)(wq * 32) << 16);
-    const uint32_t o_addr = lane_addr + 128;
+    const uint32_t lane_addr = tmem_base + qt * TS + ((uint32_t)(wq * 32) << 16);
+    const uint32_t o_addr = lane_addr + Cfg::COL_O;
     constexpr float LOG2E = 1.4426950408889634f;
     const float scale2 = a.scale * LOG2E;
     if (qt < nqa) {                      // the second warpgroup of a single-tile CTA has nothing to do
     {
       // this thread's Q row -> TMEM (A operand of every S MMA of the CTA)
-      const __half* qh = static_cast<const __half*>(a.qkv_hi) + ((size_t)row_base + qc) * a.ld_qkv + (size_t)h * AT_HD;
-      uint32_t w[32];
+      const __half* qh = static_cast<const __half*>(a.qkv_hi) + ((size_t)row_base + qc) * a.ld_qkv + (size_t)h * HD;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) ldg256(qh + i * 16, w + i * 8);
-      tmem_st32(lane_addr + 192, w);
+      for (int i = 0; i < HD / 16; ++i) {          // 16 elements = 32 bytes = 8 TMEM columns at a time
+        uint32_t w[8];
+        ldg256(qh + i * 16, w);
+        tmem_st8(lane_addr + Cfg::COL_QH + i * 8, w);
+      }
       if (SPLIT == 3) {
-        const __half* ql = static_cast<const __half*>(a.qkv_lo) + ((size_t)row_base + qc) * a.ld_qkv + (size_t)h * AT_HD;
+        const __half* ql = static_cast<const __half*>(a.qkv_lo) + ((size_t)row_base + qc) * a.ld_qkv + (size_t)h * HD;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ldg256(ql + i * 16, w + i * 8);
-        tmem_st32(lane_addr + 224, w);
+        for (int i = 0; i < HD / 16; ++i) {
+          uint32_t w[8];
+          ldg256(ql + i * 16, w);
+          tmem_st8(lane_addr + Cfg::COL_QL + i * 8, w);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
@@ -620,13 +635,13 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
         const float alpha = ex2_approx(m - m_new);
         wait_pv(j - 1);
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t o[32];
-          tmem_ld32(o_addr + hh * 32, o);
+        for (int hh = 0; hh < HD / 16; ++hh) {
+          uint32_t o[16];
+          tmem_ld16(o_addr + hh * 16, o);
           tmem_ld_wait();
 #pragma unroll
-          for (int d = 0; d < 32; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * alpha);
-          tmem_st32(o_addr + hh * 32, o);
+          for (int d = 0; d < 16; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * alpha);
+          tmem_st16(o_addr + hh * 16, o);
         }
         l *= alpha;
         m = m_new;
@@ -654,19 +669,19 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
     const float inv = 1.0f / l;
     __half* ohi = static_cast<__half*>(a.out_hi);
     __half* olo = static_cast<__half*>(a.out_lo);
-    const size_t oo = ((size_t)row_base + q) * a.ld_out + (size_t)h * AT_HD;
+    const size_t oo = ((size_t)row_base + q) * a.ld_out + (size_t)h * HD;
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      uint32_t o[32];
-      tmem_ld32(o_addr + hh * 32, o);
+    for (int hh = 0; hh < HD / 16; ++hh) {
+      uint32_t o[16];
+      tmem_ld16(o_addr + hh * 16, o);
       tmem_ld_wait();
       if (q < a.tokens) {
 #pragma unroll
-        for (int d = 0; d < 32; d += 8) {
+        for (int d = 0; d < 16; d += 8) {
           float v8[8];
 #pragma unroll
           for (int t = 0; t < 8; ++t) v8[t] = __uint_as_float(o[d + t]) * inv;
-          store_pair8(ohi, olo, oo + hh * 32 + d, v8);
+          store_pair8(ohi, olo, oo + hh * 16 + d, v8);
         }
       }
     }
@@ -677,16 +692,16 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
   if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
-template <int SPLIT, int BIAS, int NQ>
+template <int SPLIT, int BIAS, int NQ, int HD = 64>
 static int launch_attn_ts(const csam_attn_args* a, const float* rel, cudaStream_t st) {
-  using Cfg = AttnTsCfg<SPLIT, BIAS, NQ>;
+  using Cfg = AttnTsCfg<SPLIT, BIAS, NQ, HD>;
   CUtensorMap t_hi, t_lo;
   const uint64_t rows = (uint64_t)a->groups * a->tokens;
   const uint64_t cols = 3ull * a->heads * a->hd;
   if (make_tmap_2d_f16(&t_hi, a->qkv_hi, rows, cols, a->ld_qkv, 64, 64)) return 1;
   t_lo = t_hi;
   if (SPLIT == 3 && make_tmap_2d_f16(&t_lo, a->qkv_lo, rows, cols, a->ld_qkv, 64, 64)) return 1;
-  auto kern = vit_attention_ts_kernel<SPLIT, BIAS, NQ>;
+  auto kern = vit_attention_ts_kernel<SPLIT, BIAS, NQ, HD>;
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
@@ -742,7 +757,7 @@ static bool use_nq2(const csam_attn_args* a, int bias) {
 }
 
 int vit_attention_tc(const csam_attn_args* a, cudaStream_t st) {
-  CSAM_REQUIRE(a->hd == 64, "csam_vit_attention(tcgen05): head dim 64 only (use impl=1 for others)");
+  CSAM_REQUIRE(a->hd == 64 || a->hd == 80, "csam_vit_attention(tcgen05): head dim 64 or 80 (use impl=1 for others)");
   CSAM_REQUIRE((a->ld_qkv % 8) == 0 && (a->ld_out % 8) == 0, "csam_vit_attention: strides must be multiples of 8");
   CSAM_REQUIRE((reinterpret_cast<uintptr_t>(a->qkv_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->out_hi) & 15) == 0,
                "csam_vit_attention: 16-byte alignment");
@@ -761,6 +776,18 @@ int vit_attention_tc(const csam_attn_args* a, cudaStream_t st) {
     static const int ts_env = getenv("CSAM_ATTN_TS") ? atoi(getenv("CSAM_ATTN_TS")) : 1;
     const bool al32 = (reinterpret_cast<uintptr_t>(a->qkv_hi) & 31) == 0 && (a->ld_qkv % 16) == 0 &&
                       (!split || (reinterpret_cast<uintptr_t>(a->qkv_lo) & 31) == 0);
+    if (a->hd == 80) {
+      // ViT-H: one query tile per CTA (TMEM: 128 + 80 + 80 columns), K / V tiles of two swizzle atoms
+      CSAM_REQUIRE(al32 && !(split && a->p_split), "csam_vit_attention(tcgen05): head dim 80 needs 32-byte aligned rows, no p_split");
+      if (split) {
+        if (bias == 0) return launch_attn_ts<3, 0, 1, 80>(a, rel, st);
+        if (bias == 1) return launch_attn_ts<3, 1, 1, 80>(a, rel, st);
+        return launch_attn_ts<3, 2, 1, 80>(a, rel, st);
+      }
+      if (bias == 0) return launch_attn_ts<1, 0, 1, 80>(a, rel, st);
+      if (bias == 1) return launch_attn_ts<1, 1, 1, 80>(a, rel, st);
+      return launch_attn_ts<1, 2, 1, 80>(a, rel, st);
+    }
     if (ts_env && al32 && !(split && a->p_split)) {
       const bool nq2 = use_nq2(a, bias) && bias != 2;
       if (split) {

@@ -293,11 +293,12 @@ def _attn_ref(qkv, groups, tokens, heads, hd, rel_h=None, rel_w=None, S=0):
 
 @pytest.mark.parametrize("impl", ATTN_IMPLS)
 @pytest.mark.parametrize("split", [True, False])
-@pytest.mark.parametrize("groups,S,heads,hd", [(3, 14, 2, 64), (1, 32, 2, 64), (2, 14, 2, 80), (1, 64, 2, 64), (25, 14, 1, 64)])
+@pytest.mark.parametrize("groups,S,heads,hd", [(3, 14, 2, 64), (1, 32, 2, 64), (2, 14, 2, 80), (1, 64, 2, 64), (25, 14, 1, 64),
+                                               (1, 64, 3, 80)])
 def test_vit_attention_relpos(groups, S, heads, hd, split, impl):
     o = ops()
-    if impl == 0 and (hd != 64 or S not in (14, 64)):
-        pytest.skip("tcgen05 attention: head dim 64, S in {14, 64}")
+    if impl == 0 and S not in (14, 64):
+        pytest.skip("tcgen05 attention: S in {14, 64}")
     g = torch.Generator().manual_seed(S)
     tokens = S * S
     qkv = torch.randn(groups * tokens, 3 * heads * hd, generator=g)
@@ -305,6 +306,8 @@ def test_vit_attention_relpos(groups, S, heads, hd, split, impl):
     qh = _h16(qkv, split)
     ref = _attn_ref(qh.float().cpu(), groups, tokens, heads, hd, rel_h, rel_w, S)
     for p_split in (1, 0):
+        if impl == 0 and hd == 80 and p_split == 1:
+            continue        # head dim 80 (ViT-H) runs on the tensor-memory kernel, which keeps P as one fp16
         out = o.vit_attention(qh, groups, tokens, heads, hd, hd ** -0.5, rel_h.to(DEV), rel_w.to(DEV), S, impl=impl,
                               p_split=p_split)
         # tensor cores: P as one fp16 costs 2^-12 relative per probability; with P split (or on the SIMT kernel,
@@ -326,6 +329,19 @@ def test_vit_attention_plain_ragged(tokens, impl):
     out = o.vit_attention(qh, 1, tokens, heads, hd, hd ** -0.5, impl=impl, p_split=1)
     assert _rel(out.float(), ref) < 1e-5, _rel(out.float(), ref)
     out = o.vit_attention(qh, 1, tokens, heads, hd, hd ** -0.5, impl=impl, p_split=0)
+    assert _rel(out.float(), ref) < 5e-4, _rel(out.float(), ref)
+
+
+@pytest.mark.parametrize("tokens", [200, 5330])
+def test_vit_attention_head_dim_80_plain(tokens):
+    """ViT-H head dim on the tcgen05 kernel without a bias (K / V tiles of two swizzle atoms, Q / P in TMEM)."""
+    o = ops()
+    g = torch.Generator().manual_seed(80)
+    heads, hd = 2, 80
+    qkv = torch.randn(tokens, 3 * heads * hd, generator=g) * 1.5
+    qh = _h16(qkv, True)
+    ref = _attn_ref(qh.float().cpu(), 1, tokens, heads, hd)
+    out = o.vit_attention(qh, 1, tokens, heads, hd, hd ** -0.5, impl=0, p_split=0)
     assert _rel(out.float(), ref) < 5e-4, _rel(out.float(), ref)
 
 
