@@ -101,11 +101,11 @@ def test_cfg(points_per_batch: int):
 # ------------------------------------------------------------------------------------------------
 # CPU oracle timing (cpu_baseline leg and --impl reference)
 # ------------------------------------------------------------------------------------------------
-def cpu_sample_seconds(sam_sd, dino_sd, image_index: int, frac_blocks: int = 4, n_prompts: int = 8):
-    """Bounded sample of the workload on the host cores with the oracle port: 1/frac of the SAM ViT-L blocks
-    (6 of 24, one of them global = the model's 1:5 mix), 1/frac of the DINOv2 blocks, patch embed + neck,
-    `n_prompts` of the 1024 prompts through decoder + post-processing.  Returns (extrapolated seconds per
-    image, description).  Extrapolation: blocks x frac, prompts x 1024/n_prompts, fixed parts x 1."""
+def cpu_sample_seconds(sam_sd, dino_sd, image_index: int, frac_blocks: int = 1, n_prompts: int = 64):
+    """Bounded sample of the workload on the host cores with the oracle port (10-20 s of CPU work): both encoders
+    in full by default (frac_blocks = 1; otherwise 1/frac of the SAM ViT-L and of the DINOv2 blocks), patch embed +
+    neck, and `n_prompts` of the 1024 prompts through decoder + post-processing + NMS.  Returns (extrapolated
+    seconds per image, description).  Extrapolation: blocks x frac, prompts x 1024/n_prompts, fixed parts x 1."""
     import torch
     from oracle import restate, weights
 
