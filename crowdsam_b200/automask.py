@@ -20,7 +20,8 @@ class SamAutomaticMaskGenerator:
     def __init__(self, model, dino_model=None, points_per_side: Optional[int] = 32, points_per_batch: int = 64,
                  pred_iou_thresh: float = 0.88, stability_score_thresh: float = 0.95,
                  stability_score_offset: float = 1.0, box_nms_thresh: float = 0.7, crop_n_layers: int = 0,
-                 min_mask_region_area: int = 0, output_mode: str = "binary_mask", **unused) -> None:
+                 min_mask_region_area: int = 0, output_mode: str = "binary_mask", crop_nms_thresh: float = 0.7,
+                 **unused) -> None:
         assert output_mode in ("binary_mask", "uncompressed_rle", "coco_rle")
         if crop_n_layers != 0:
             raise NotImplementedError("multi-crop AMG is outside the B200 hot path")
@@ -33,6 +34,8 @@ class SamAutomaticMaskGenerator:
         self.stability_score_thresh = stability_score_thresh
         self.stability_score_offset = stability_score_offset
         self.box_nms_thresh = box_nms_thresh
+        self.crop_nms_thresh = crop_nms_thresh
+        self.min_mask_region_area = min_mask_region_area
         self.output_mode = output_mode
 
     @torch.no_grad()
@@ -61,6 +64,20 @@ class SamAutomaticMaskGenerator:
         boxes = torch.cat(all_boxes); ptsk = torch.cat(all_pts)
         keep = ops.box_nms(boxes.float(), iou, self.box_nms_thresh)
         masks, iou, stab, boxes, ptsk = masks[keep], iou[keep], stab[keep], boxes[keep], ptsk[keep.cpu()]
+        if self.min_mask_region_area > 0 and len(masks) > 0:
+            # upstream postprocess_small_regions (automatic_mask_generator.py:326-372) on the device: fill holes /
+            # drop islands below the area, recompute boxes, NMS that prefers the masks that needed no change
+            m8 = masks.to(torch.uint8).contiguous().clone()
+            c1 = ops.remove_small_regions(m8, int(np.ceil(self.min_mask_region_area)), "holes")
+            c2 = ops.remove_small_regions(m8, int(np.ceil(self.min_mask_region_area)), "islands")
+            unchanged = ((c1 | c2) == 0).float()
+            nb = amg.batched_mask_to_box(m8.bool())
+            keep2 = ops.box_nms(nb.float(), unchanged, max(self.box_nms_thresh, self.crop_nms_thresh))
+            upd = keep2[unchanged[keep2] == 0.0]
+            if upd.numel() > 0:
+                masks[upd] = m8[upd].to(masks.dtype)
+                boxes[upd] = nb[upd].to(boxes.dtype)
+            masks, iou, stab, boxes, ptsk = masks[keep2], iou[keep2], stab[keep2], boxes[keep2], ptsk[keep2.cpu()]
         if self.output_mode == "binary_mask":
             segs = [m for m in masks.cpu().numpy()]
         else:

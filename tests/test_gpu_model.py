@@ -175,6 +175,48 @@ def test_config0_vit_b_full_depth_vs_reference(golden_dir):
     _check_pipeline_golden(pred, g, test_cfg)
 
 
+def test_automatic_mask_generator_vs_oracle():
+    """SamAutomaticMaskGenerator (upstream-SAM grid semantics: every grid point, all 4 masks per point, IoU / stability
+    filters, box NMS by predicted IoU) against the same steps composed from the CPU oracle."""
+    from crowdsam_b200 import amg
+    from crowdsam_b200.automask import SamAutomaticMaskGenerator
+
+    pred, sam_sd, dino_sd, scfg, dcfg = make_predictor("tiny")
+    img = weights.synthetic_image(5)
+    gen = SamAutomaticMaskGenerator(pred.model, pred.dino_model, points_per_side=4, points_per_batch=8,
+                                    pred_iou_thresh=0.0, stability_score_thresh=0.0, box_nms_thresh=0.7,
+                                    output_mode="binary_mask")
+    res = gen.generate(img)
+    # oracle: same grid, same filters
+    t = torch.as_tensor(img).permute(2, 0, 1)[None]
+    feats, dino = restate.set_image(sam_sd, dino_sd, t, scfg, dcfg)
+    pts = amg.build_point_grid(4) * np.array([[1024, 1024]])
+    coords = torch.as_tensor(restate.apply_coords(pts, (1024, 1024)))[:, None, :]
+    labels = torch.ones(len(pts), dtype=torch.int)[:, None]
+    low, iou, _ = restate.mask_decoder(sam_sd, feats, restate.dense_pe(sam_sd), restate.embed_points(sam_sd, coords, labels), dino)
+    full = restate.postprocess_masks(low, (1024, 1024), (1024, 1024)).reshape(-1, 1024, 1024)
+    iou_f = iou.reshape(-1)
+    stab = restate.stability_score(full, 0.0, 1.0)
+    ok = (iou_f > 0.0) & (stab >= 0.0)
+    boxes = restate.mask_to_box(full[ok] > 0.0)
+    keep = restate.nms_reference(boxes.float().numpy(), iou_f[ok].numpy(), 0.7)
+    assert len(res) == len(keep) > 0
+    ref_iou = iou_f[ok][keep]
+    ref_boxes = boxes[keep]
+    for i, r in enumerate(res):
+        assert set(r.keys()) == {"segmentation", "area", "bbox", "predicted_iou", "point_coords", "stability_score", "crop_box"}
+        assert abs(r["predicted_iou"] - float(ref_iou[i])) <= TOL * max(1.0, float(ref_iou.abs().max()))
+        b = ref_boxes[i].tolist()
+        assert r["bbox"] == [b[0], b[1], b[2] - b[0], b[3] - b[1]]
+        assert r["segmentation"].shape == (1024, 1024) and r["segmentation"].dtype == bool
+    # small-region cleanup path runs on the device and keeps the output well formed
+    gen2 = SamAutomaticMaskGenerator(pred.model, pred.dino_model, points_per_side=4, points_per_batch=16,
+                                     pred_iou_thresh=0.0, stability_score_thresh=0.0, min_mask_region_area=50,
+                                     output_mode="coco_rle")
+    res2 = gen2.generate(img)
+    assert len(res2) > 0 and all(isinstance(r["segmentation"]["counts"], str) for r in res2)
+
+
 def test_errors_and_state():
     pred, *_ = make_predictor("tiny")
     pred.reset_image()
