@@ -1,5 +1,5 @@
 #!/bin/bash
-# Re-entry validation of HEAD: GPU tests, smoke, bench (both arms).
+# Validation of HEAD on a B200 box: GPU tests, smoke, bench (both arms).  usage: gpurun -- bash scripts/gpu_validate.sh
 mkdir -p gpurun_out
 export PYTHONPATH=$PWD
 run() { name=$1; shift; echo "=== $name"; timeout 1500 "$@" > gpurun_out/$name.log 2>&1; echo "exit $? $name"; tail -n 14 gpurun_out/$name.log | cut -c1-600; }

@@ -1,0 +1,45 @@
+"""CPU checks of host-side logic that the GPU tests rely on but that needs no device."""
+import numpy as np
+
+from crowdsam_b200 import amg
+
+
+def _coco_string_scalar(counts):
+    """Straight restatement of maskApi.c rleToString (published COCO API algorithm), one value at a time."""
+    out = []
+    for i, c in enumerate(counts):
+        x = int(c)
+        if i > 2:
+            x -= int(counts[i - 2])
+        more = True
+        while more:
+            ch = x & 0x1F
+            x >>= 5
+            more = (x != -1) if (ch & 0x10) else (x != 0)
+            if more:
+                ch |= 0x20
+            out.append(chr(ch + 48))
+    return "".join(out)
+
+
+def test_coco_string_vectorised_matches_scalar():
+    rng = np.random.default_rng(7)
+    for n in (0, 1, 2, 3, 4, 7, 1000, 5000):
+        for hi in (15, 70000, 1 << 20):
+            counts = rng.integers(0, hi, size=n)
+            assert amg._coco_string(counts) == _coco_string_scalar(counts), (n, hi)
+
+
+def test_rle_round_trip():
+    rng = np.random.default_rng(3)
+    m = rng.random((37, 53)) < 0.4
+    # column-major runs, first run counts zeros (amg.py:107-135)
+    flat = m.T.reshape(-1)
+    change = np.flatnonzero(np.diff(flat.astype(np.int8))) + 1
+    bounds = np.concatenate([[0], change, [flat.size]])
+    counts = list(np.diff(bounds))
+    if flat[0]:
+        counts = [0] + counts
+    rle = {"size": [37, 53], "counts": counts}
+    assert np.array_equal(amg.rle_to_mask(rle), m)
+    assert amg.area_from_rle(rle) == int(m.sum())
