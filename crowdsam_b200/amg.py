@@ -183,7 +183,9 @@ def _coco_string(counts: Sequence[int]) -> str:
     """COCO API run-length string (maskApi.c rleToString): counts beyond the second are delta coded
     against counts[i-2]; each value is emitted as 5-bit groups (little endian), bit 5 = continuation, + 48.
     Vectorised over all counts: one numpy pass per 5-bit group (at most 7 for int32 values)."""
-    c = np.asarray(counts, dtype=np.int64)
+    c = np.asarray(counts)
+    # run lengths of a mask fit 32 bits (h * w < 2^31), and so do their pairwise differences: half the bytes to move
+    c = c.astype(np.int32 if (c.size == 0 or int(c.max(initial=0)) < (1 << 30)) else np.int64, copy=False)
     n = c.shape[0]
     if n == 0:
         return ""
@@ -196,7 +198,7 @@ def _coco_string(counts: Sequence[int]) -> str:
         low = v & 0x1F
         v = v >> 5                                   # arithmetic shift, like the C code on a signed long
         done = v == -((low >> 4) & 1)                # sign bit set: finished when the rest is -1, else when it is 0
-        return v, done, (low | ((~done).astype(np.int64) << 5)) + 48
+        return v, done, (low | ((~done).astype(v.dtype) << 5)) + 48
 
     x, done, ch0 = one_pass(x)
     ch0 = ch0.astype(np.uint8)
