@@ -275,28 +275,50 @@ __global__ void __launch_bounds__(256) hyper_masks_kernel(const float* __restric
 }
 
 // ---- PWD softmax weights --------------------------------------------------------------------
+// RV = float4 slots per thread kept in registers (n == 4096 * RV: the row is read from memory ONCE); RV = 0 is the
+// generic two-pass version.  exp via ex2.approx (relative error 2^-22), 8-byte packed hi / lo stores.
+template <int RV>
 __global__ void __launch_bounds__(1024) softmax_weights_kernel(const float* __restrict__ x, int n, __half* __restrict__ ehi,
                                                                __half* __restrict__ elo, float* __restrict__ inv_sum) {
   __shared__ float red[32];
   const float* row = x + (size_t)blockIdx.x * n;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr float LOG2E = 1.4426950408889634f;
+  float4 keep[RV > 0 ? RV : 1];
   float m = -INFINITY;
-  for (int i = threadIdx.x * 4; i < n; i += 4096) {
-    const float4 v = *reinterpret_cast<const float4*>(row + i);
-    m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  if (RV > 0) {
+#pragma unroll
+    for (int k = 0; k < RV; ++k) {
+      keep[k] = *reinterpret_cast<const float4*>(row + threadIdx.x * 4 + k * 4096);
+      m = fmaxf(m, fmaxf(fmaxf(keep[k].x, keep[k].y), fmaxf(keep[k].z, keep[k].w)));
+    }
+  } else {
+    for (int i = threadIdx.x * 4; i < n; i += 4096) {
+      const float4 v = *reinterpret_cast<const float4*>(row + i);
+      m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    }
   }
   m = warp_max(m);
   if (lane == 0) red[wid] = m;
   __syncthreads();
   m = warp_max(red[lane]);
   __syncthreads();
+  const float ml = m * LOG2E;
   float s = 0.f;
-  for (int i = threadIdx.x * 4; i < n; i += 4096) {
-    const float4 v = *reinterpret_cast<const float4*>(row + i);
-    const float e[4] = {expf(v.x - m), expf(v.y - m), expf(v.z - m), expf(v.w - m)};
+  auto emit = [&](const float4& v, size_t at) {
+    float e[4];
+    e[0] = exp2f(fmaf(v.x, LOG2E, -ml)); e[1] = exp2f(fmaf(v.y, LOG2E, -ml));
+    e[2] = exp2f(fmaf(v.z, LOG2E, -ml)); e[3] = exp2f(fmaf(v.w, LOG2E, -ml));
     s += (e[0] + e[1]) + (e[2] + e[3]);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) store_pair(ehi, elo, (size_t)blockIdx.x * n + i + t, e[t] * 16384.f);
+    for (int t = 0; t < 4; ++t) e[t] *= 16384.f;
+    store_pair4(ehi, elo, at, e);
+  };
+  if (RV > 0) {
+#pragma unroll
+    for (int k = 0; k < RV; ++k) emit(keep[k], (size_t)blockIdx.x * n + threadIdx.x * 4 + k * 4096);
+  } else {
+    for (int i = threadIdx.x * 4; i < n; i += 4096) emit(*reinterpret_cast<const float4*>(row + i), (size_t)blockIdx.x * n + i);
   }
   s = warp_sum(s);
   if (lane == 0) red[wid] = s;
@@ -405,7 +427,15 @@ extern "C" int csam_upscale_hyper_masks(const float* y2, int P, const float* hyp
 
 extern "C" int csam_softmax_weights(const float* x, int R, int n, void* e_hi, void* e_lo, float* inv_sum, void* stream) {
   CSAM_REQUIRE(x && e_hi && inv_sum && R > 0 && n > 0 && (n % 4) == 0, "csam_softmax_weights: bad args");
-  softmax_weights_kernel<<<R, 1024, 0, (cudaStream_t)stream>>>(x, n, (__half*)e_hi, (__half*)e_lo, inv_sum);
+  CSAM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(e_hi) & 7) == 0 &&
+                   (!e_lo || (reinterpret_cast<uintptr_t>(e_lo) & 7) == 0),
+               "csam_softmax_weights: alignment");
+  // (keeping a 65,536-value row in registers would need the whole register file: the second pass re-reads the row,
+  //  which is 256 KB and still in L2)
+  if (n == 8192)
+    softmax_weights_kernel<2><<<R, 1024, 0, (cudaStream_t)stream>>>(x, n, (__half*)e_hi, (__half*)e_lo, inv_sum);
+  else
+    softmax_weights_kernel<0><<<R, 1024, 0, (cudaStream_t)stream>>>(x, n, (__half*)e_hi, (__half*)e_lo, inv_sum);
   return check_launch("softmax_weights_kernel");
 }
 

@@ -412,6 +412,10 @@ def test_prompt_tokens_and_small_kernels():
     e, inv = o.softmax_weights(x.to(DEV), True)
     w = e.float().cpu().double() * inv.cpu().double()[:, None]
     assert (w - x.double().softmax(-1)).abs().max() / x.double().softmax(-1).max() < 1e-5
+    x2 = torch.randn(5, 8192, generator=g) * 5          # the register-resident variant
+    e2, inv2 = o.softmax_weights(x2.to(DEV), True)
+    w2 = e2.float().cpu().double() * inv2.cpu().double()[:, None]
+    assert (w2 - x2.double().softmax(-1)).abs().max() / x2.double().softmax(-1).max() < 1e-5
     # select
     iou, cls = torch.randn(50, 4, generator=g), torch.randn(50, 4, 1, generator=g)
     iou[3] = 0.5
