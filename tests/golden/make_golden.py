@@ -150,9 +150,22 @@ def config0_case():
                        filter_thresh=2.0, min_mask_region_area=0))
 
 
+def config1_case():
+    """BASELINE.json configs[1] (the headline workload) at full depth: SAM ViT-L + DINOv2 ViT-L/14 through the real
+    reference on CPU, 1024x1024 synthetic image, 32x32 prompt grid = 1024 prompts, PWD-Net scoring + filters + NMS
+    -> model_vit_l.npz, pipeline_vit_l_grid32.npz (about 5 minutes on 8 cores)."""
+    sam, dino = model_case("vit_l", "vit_l", "dinov2_vitl14")
+    pipeline_case("vit_l_grid32", sam, dino,
+                  dict(grid_size=32, pos_sim_thresh=-1, max_prompts=1024, points_per_batch=64,
+                       filter_thresh=2.0, min_mask_region_area=0))
+
+
 if __name__ == "__main__":
     assert ref_import.available(), "needs /root/reference"
     torch.manual_seed(0)
+    if "--config1" in sys.argv:
+        config1_case()
+        sys.exit(0)
     if "--config0" in sys.argv:          # only the (slow, ~3 min) full-depth case; the other files stay as they are
         config0_case()
         sys.exit(0)
@@ -167,3 +180,4 @@ if __name__ == "__main__":
                        stability_score_thresh=0.5), image_index=2, hw=(768, 1024))
     model_case("tiny_l", "tiny_l", "tiny")
     config0_case()
+    config1_case()

@@ -175,6 +175,23 @@ def test_config0_vit_b_full_depth_vs_reference(golden_dir):
     _check_pipeline_golden(pred, g, test_cfg)
 
 
+def test_config1_vit_l_headline_vs_reference(golden_dir):
+    """BASELINE.json configs[1], the bench workload: SAM ViT-L (24 blocks) + DINOv2 ViT-L/14, 1024x1024 synthetic image,
+    32x32 grid = 1024 prompts, against the outputs of the REAL reference run on CPU (make_golden.py --config1)."""
+    pred, *_ = make_predictor("vit_l", "dinov2_vitl14")
+    pred.set_image(weights.synthetic_image(0))
+    _check_model_golden(pred, np.load(os.path.join(golden_dir, "model_vit_l.npz")))
+    g = np.load(os.path.join(golden_dir, "pipeline_vit_l_grid32.npz"))
+    test_cfg = dict(restate.DEFAULT_TEST_CFG)
+    for k, v in zip(g["cfg_keys"], g["cfg_vals"]):
+        test_cfg[str(k)] = int(str(v)) if str(v).lstrip("-").isdigit() else float(str(v))
+    test_cfg.update(apply_box_offsets=False, fuse_simmap=False, output_rles=True)
+    _check_pipeline_golden(pred, g, test_cfg)
+    # the same image with all 1024 prompts in ONE decoder batch (what bench.py runs) gives the same detections
+    test_cfg["points_per_batch"] = 1024
+    _check_pipeline_golden(pred, g, test_cfg)
+
+
 def test_automatic_mask_generator_vs_oracle():
     """SamAutomaticMaskGenerator (upstream-SAM grid semantics: every grid point, all 4 masks per point, IoU / stability
     filters, box NMS by predicted IoU) against the same steps composed from the CPU oracle."""

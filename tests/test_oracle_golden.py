@@ -65,6 +65,15 @@ def test_config0_vit_b_full_depth(golden_dir):
     test_encoder_dino_decoder_square((g, sam_sd, dino_sd, (depth, heads, glob), (ddepth, dheads)))
 
 
+def test_config1_vit_l_full_depth(golden_dir):
+    """BASELINE.json configs[1] at full depth (SAM ViT-L + DINOv2 ViT-L/14): the oracle against the real reference."""
+    g = np.load(os.path.join(golden_dir, "model_vit_l.npz"))
+    sam_sd, dino_sd = weights.make_sam_state("vit_l"), weights.make_dino_state("dinov2_vitl14")
+    _, depth, heads, glob = weights.SAM_ARCHS["vit_l"]
+    _, ddepth, dheads = weights.DINO_ARCHS["dinov2_vitl14"]
+    test_encoder_dino_decoder_square((g, sam_sd, dino_sd, (depth, heads, glob), (ddepth, dheads)))
+
+
 def test_non_square_image(model_case):
     g, sam_sd, dino_sd, scfg, dcfg = model_case
     from PIL import Image
