@@ -160,9 +160,22 @@ def config1_case():
                        filter_thresh=2.0, min_mask_region_area=0))
 
 
+def config3_case():
+    """BASELINE.json configs[3] (encoder-bound): SAM ViT-H (32 blocks, head dim 80) + DINOv2 ViT-L/14 through the real
+    reference on CPU, 32x32 grid -> model_vit_h.npz, pipeline_vit_h_grid32.npz."""
+    sam, dino = model_case("vit_h", "vit_h", "dinov2_vitl14")
+    cfg = dict(grid_size=32, pos_sim_thresh=-1, max_prompts=1024, points_per_batch=64,
+               filter_thresh=2.0, min_mask_region_area=0)
+    pipeline_case("vit_h_grid32", sam, dino, cfg)                           # image 0: the reference finds nothing
+    pipeline_case("vit_h_grid32_img3", sam, dino, cfg, image_index=3)       # image 3: one detection
+
+
 if __name__ == "__main__":
     assert ref_import.available(), "needs /root/reference"
     torch.manual_seed(0)
+    if "--config3" in sys.argv:
+        config3_case()
+        sys.exit(0)
     if "--config1" in sys.argv:
         config1_case()
         sys.exit(0)
@@ -181,3 +194,4 @@ if __name__ == "__main__":
     model_case("tiny_l", "tiny_l", "tiny")
     config0_case()
     config1_case()
+    config3_case()

@@ -74,6 +74,16 @@ def test_config1_vit_l_full_depth(golden_dir):
     test_encoder_dino_decoder_square((g, sam_sd, dino_sd, (depth, heads, glob), (ddepth, dheads)))
 
 
+@pytest.mark.skipif(os.environ.get("CSAM_SLOW_TESTS", "0") != "1", reason="~1.5 min of CPU: set CSAM_SLOW_TESTS=1")
+def test_config3_vit_h_full_depth(golden_dir):
+    """BASELINE.json configs[3] at full depth (SAM ViT-H + DINOv2 ViT-L/14): the oracle against the real reference."""
+    g = np.load(os.path.join(golden_dir, "model_vit_h.npz"))
+    sam_sd, dino_sd = weights.make_sam_state("vit_h"), weights.make_dino_state("dinov2_vitl14")
+    _, depth, heads, glob = weights.SAM_ARCHS["vit_h"]
+    _, ddepth, dheads = weights.DINO_ARCHS["dinov2_vitl14"]
+    test_encoder_dino_decoder_square((g, sam_sd, dino_sd, (depth, heads, glob), (ddepth, dheads)))
+
+
 def test_non_square_image(model_case):
     g, sam_sd, dino_sd, scfg, dcfg = model_case
     from PIL import Image
