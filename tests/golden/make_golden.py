@@ -158,6 +158,10 @@ def config1_case():
     pipeline_case("vit_l_grid32", sam, dino,
                   dict(grid_size=32, pos_sim_thresh=-1, max_prompts=1024, points_per_batch=64,
                        filter_thresh=2.0, min_mask_region_area=0))
+    # configs[2]: 64x64 dense grid = 4096 prompts per image (about 5 more minutes)
+    pipeline_case("vit_l_grid64", sam, dino,
+                  dict(grid_size=64, pos_sim_thresh=-1, max_prompts=4096, points_per_batch=64,
+                       filter_thresh=2.0, min_mask_region_area=0), image_index=1)
 
 
 def config3_case():

@@ -197,6 +197,18 @@ def test_config1_vit_l_headline_vs_reference(golden_dir):
     _check_pipeline_golden(pred, g, test_cfg)
 
 
+def test_config2_vit_l_grid64_vs_reference(golden_dir):
+    """BASELINE.json configs[2]: SAM ViT-L, 64x64 dense grid = 4096 prompts decoded in ONE batch, against the real
+    reference's CrowdSAM.generate (which took them 64 at a time)."""
+    pred, *_ = make_predictor("vit_l", "dinov2_vitl14")
+    g = np.load(os.path.join(golden_dir, "pipeline_vit_l_grid64.npz"))
+    test_cfg = dict(restate.DEFAULT_TEST_CFG)
+    for k, v in zip(g["cfg_keys"], g["cfg_vals"]):
+        test_cfg[str(k)] = int(str(v)) if str(v).lstrip("-").isdigit() else float(str(v))
+    test_cfg.update(apply_box_offsets=False, fuse_simmap=False, output_rles=True, points_per_batch=4096)
+    _check_pipeline_golden(pred, g, test_cfg)
+
+
 def test_config3_vit_h_vs_reference(golden_dir):
     """BASELINE.json configs[3]: SAM ViT-H (32 blocks, head dim 80 on the tcgen05 attention) + DINOv2 ViT-L/14, 32x32 grid,
     against the outputs of the REAL reference run on CPU (make_golden.py --config3)."""
