@@ -433,8 +433,8 @@ dec_fold_i2t_kernel(const float* __restrict__ kt, const float* __restrict__ vt, 
 //     out[i, h*16+d]   = Wv[h*16+d, :] . xbar[(h,i), :] + b_v                   (csam_dec_t2i_out, tiny)
 // so the kernel reads the keys once (1 KB per row) and the [P*4096, 256] k | v stream of the unfused path
 // (4 KB per row written + read) never exists.  One CTA owns a prompt; per 128-key tile:
-//     MMA1  S[128 keys, 64] = [X | PEK] (K = 384) * B1^T
-//     softmax over KEYS: one thread per key row; the column maxima live in shared memory and may lag by
+//     MMA1  S[128 keys, 64] = [PEK | X] (K = 384, the two positional k-blocks first) * B1^T
+//     softmax over KEYS: two threads per key row (32 columns each); the column maxima live in shared memory and may lag by
 //           2^8, so the common path is exp2(s - m[c]) and a block-wide vote; a violated bound triggers
 //           an exact column maximum (warp shuffles) and a rescale of the accumulator in TMEM
 //     MMA2  XBAR^T[256, 64] += X^T (MN-major A straight from the resident X tile) * P (MN-major B, h16 pair)
