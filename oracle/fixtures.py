@@ -66,3 +66,44 @@ def grid_points(G: int, size: int = 1024) -> np.ndarray:
     (j*size/G, i*size/G) for every grid cell, row-major (model.py:200-223)."""
     ii, jj = np.meshgrid(np.arange(G), np.arange(G), indexing="ij")
     return np.stack([jj.reshape(-1) * (size / G), ii.reshape(-1) * (size / G)], axis=1).astype(int)
+
+
+# ------------------------------------------------------------------------------------------------
+# Decoder-output injection keyed by the prompt point (multi-detection end-to-end parity)
+# ------------------------------------------------------------------------------------------------
+def injected_decoder_outputs(coords_xy: np.ndarray, seed: int = 0, sigma_lo: float = 3.0, sigma_hi: float = 14.0,
+                             lowres: int = 256):
+    """Deterministic stand-in for the mask decoder's three outputs, a pure function of each prompt's
+    input-frame coordinates (the `apply_coords` output both the reference's `predict_torch` and this
+    repo's `decode_low_res` receive): low-res logits [P,4,256,256] = +6 Gaussian blob near the prompt
+    over a -6 floor plus N(0,0.5) pixel noise, the four candidates sharing a centre with growing sigma;
+    iou [P,4] in U(0,1) (about 10 % of the prompts quantised to quarters: exact score ties across prompts)
+    and cls logits [P,4,1].  Injected on both sides at the low-res-logit boundary so that the whole
+    selection chain (PWD score, select_mask, filters, boxes, EPS pruning, NMS, small-region cleanup, RLE,
+    crop merge) of the REAL reference runs on many distinct instances (tests/golden/make_golden.py) and is
+    compared with the CUDA path on identical inputs."""
+    pts = np.asarray(coords_xy, dtype=np.float64).reshape(-1, 2)
+    P = pts.shape[0]
+    yy, xx = np.meshgrid(np.arange(lowres, dtype=np.float32), np.arange(lowres, dtype=np.float32), indexing="ij")
+    low = np.empty((P, 4, lowres, lowres), dtype=np.float32)
+    iou = np.empty((P, 4), dtype=np.float32)
+    cls = np.empty((P, 4, 1), dtype=np.float32)
+    for p in range(P):
+        kx, ky = int(round(pts[p, 0] * 4)), int(round(pts[p, 1] * 4))
+        rng = np.random.default_rng([int(seed), kx & 0xFFFFFFFF, ky & 0xFFFFFFFF])
+        cx = np.float32(pts[p, 0] / 4.0 + rng.normal(0.0, 1.5))
+        cy = np.float32(pts[p, 1] / 4.0 + rng.normal(0.0, 1.5))
+        sig = np.float32(rng.uniform(sigma_lo, sigma_hi))
+        aspect = np.float32(rng.uniform(0.6, 1.8))              # people are taller than wide
+        d2x = (xx - cx) ** 2
+        d2y = ((yy - cy) / aspect) ** 2
+        for c in range(4):
+            s = sig * np.float32(0.6 + 0.3 * c)
+            low[p, c] = np.float32(-6.0) + np.float32(12.0) * np.exp(-(d2x + d2y) / (np.float32(2.0) * s * s))
+        low[p] += np.float32(0.5) * rng.standard_normal(low[p].shape, dtype=np.float32)
+        q = rng.uniform(0.0, 1.0, 4).astype(np.float32)
+        if rng.uniform() < 0.1:
+            q = np.round(q * 4) / 4
+        iou[p] = q
+        cls[p, :, 0] = (3.0 * rng.standard_normal(4)).astype(np.float32)
+    return torch.from_numpy(low), torch.from_numpy(iou), torch.from_numpy(cls)

@@ -174,9 +174,89 @@ def config3_case():
     pipeline_case("vit_h_grid32_img3", sam, dino, cfg, image_index=3)       # image 3: one detection
 
 
+# --------------------------------------------------------------------------------------------------
+# Multi-detection end-to-end goldens: the REAL CrowdSAM pipeline on injected decoder outputs
+# --------------------------------------------------------------------------------------------------
+def _inject(pred, seed, log):
+    """Replace the real predictor's predict_torch by the injected decoder (fixtures.injected_decoder_outputs)
+    followed by the reference's own Sam.postprocess_masks, i.e. predictor.py:285-292 with the decoder swapped."""
+
+    def predict_torch(point_coords, point_labels, boxes=None, mask_input=None, multimask_output=True,
+                      return_logits=False, **kw):
+        assert pred.is_image_set
+        xy = point_coords[:, 0, :].cpu().numpy()
+        log.append(xy.copy())
+        low, iou, cls = fixtures.injected_decoder_outputs(xy, seed)
+        masks = pred.model.postprocess_masks(low, pred.input_size, pred.original_size)
+        if not return_logits:
+            masks = masks > pred.model.mask_threshold
+        return masks, iou, cls, low
+
+    pred.predict_torch = predict_torch
+
+
+def injected_pipeline_case(name, sam, dino, overrides, image_index=0, hw=(1024, 1024), seed=0, coordinate_trick=False):
+    """CrowdSAM.generate of the real crowdsam/model.py (EPS iterator, select_mask, filters, boxes, crop-edge filter,
+    per-crop NMS, postprocess_small_regions + second NMS, RLE, uncrop, cross-crop NMS) with the decoder outputs
+    injected per prompt point -> many distinct instances instead of the single full-image box random weights give.
+    coordinate_trick: route batched_nms through torchvision's coordinate-trick branch, the one the reference takes
+    on CUDA for N <= 25000 boxes (on CPU it would switch to the vanilla branch above 1000 boxes, whose final
+    non-stable sort orders tied scores differently)."""
+    cfg = dict(DEFAULT_TEST_CFG)
+    cfg.update(overrides)
+    m = ref_import.build_crowdsam(sam, dino, cfg)
+    log = []
+    _inject(m.predictor, seed, log)
+    _, cmodel, _ = ref_import.load()
+    saved = cmodel.batched_nms
+    if coordinate_trick:
+        from torchvision.ops.boxes import _batched_nms_coordinate_trick
+
+        cmodel.batched_nms = lambda b, s, i, iou_threshold: _batched_nms_coordinate_trick(b, s, i, iou_threshold)
+    try:
+        img = weights.synthetic_image(image_index, *hw)
+        np.random.seed(42)
+        res = m.generate(img)
+    finally:
+        cmodel.batched_nms = saved
+    out = {"cfg_keys": np.array(sorted(overrides.keys())),
+           "cfg_vals": np.array([str(overrides[k]) for k in sorted(overrides.keys())]),
+           "image_index": np.array(image_index), "hw": np.array(hw), "inject_seed": np.array(seed),
+           "call_sizes": np.array([len(x) for x in log]), "call_points": np.concatenate(log, 0)}
+    for k, v in res.items():
+        if k == "rles":
+            out["rle_counts"] = np.array([r["counts"] for r in v])
+            out["rle_sizes"] = np.array([r["size"] for r in v]).reshape(-1, 2)
+        elif k == "rles_info":
+            out["rles_info"] = np.array([list(v[0]), list(v[1]) + [0, 0]])
+        else:
+            out[k] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, f"pipeline_inj_{name}.npz"), **out)
+    print("wrote injected pipeline", name, "calls", len(log), "prompts", int(sum(len(x) for x in log)),
+          "detections", len(res["boxes"]))
+
+
+def injected_cases():
+    sam_sd, dino_sd = weights.make_sam_state("tiny"), weights.make_dino_state("tiny")
+    sam, dino = ref_import.build_sam(sam_sd, "tiny"), ref_import.build_dino(dino_sd, "tiny")
+    eps = dict(pos_sim_thresh=-1, points_per_batch=32, filter_thresh=0.3, min_mask_region_area=100)
+    injected_pipeline_case("p64", sam, dino, dict(grid_size=8, max_prompts=64, **eps), seed=1)
+    injected_pipeline_case("p1024", sam, dino, dict(grid_size=32, max_prompts=1024, **eps), seed=2)
+    injected_pipeline_case("p4096", sam, dino, dict(grid_size=64, max_prompts=4096, pos_sim_thresh=-1, points_per_batch=64,
+                                                    filter_thresh=2.0, min_mask_region_area=0), seed=3,
+                           coordinate_trick=True)
+    injected_pipeline_case("crops", sam, dino, dict(grid_size=16, max_prompts=256, crop_n_layers=1, **eps),
+                           image_index=4, hw=(600, 900), seed=4)
+    for sel in ("max_area", "min_area"):
+        injected_pipeline_case(sel, sam, dino, dict(grid_size=16, max_prompts=256, mask_selection=sel, **eps), seed=5)
+
+
 if __name__ == "__main__":
     assert ref_import.available(), "needs /root/reference"
     torch.manual_seed(0)
+    if "--injected" in sys.argv:
+        injected_cases()
+        sys.exit(0)
     if "--config3" in sys.argv:
         config3_case()
         sys.exit(0)
@@ -196,6 +276,7 @@ if __name__ == "__main__":
                        filter_thresh=0.3, min_mask_region_area=100, pred_iou_thresh=0.05,
                        stability_score_thresh=0.5), image_index=2, hw=(768, 1024))
     model_case("tiny_l", "tiny_l", "tiny")
+    injected_cases()
     config0_case()
     config1_case()
     config3_case()
