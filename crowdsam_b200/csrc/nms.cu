@@ -6,20 +6,31 @@
 
 namespace csam {
 
-// stable descending order by rank counting: rank_i = #{j : s_j > s_i or (s_j == s_i and j < i)}
+// Total order on scores that matches torch.sort(descending=True, stable=True), which torchvision's nms uses:
+// NaN sorts as the greatest value (first), -0.0 == +0.0, everything else by value.  Mapping the float bits to
+// an unsigned key makes the rank below a permutation for ANY input (with NaN scores the plain `>` / `==`
+// comparisons are all false, several boxes would share a rank and slots of order[] would stay unwritten).
+__device__ __forceinline__ uint32_t score_key(float s) {
+  if (s != s) return 0xFFFFFFFFu;
+  if (s == 0.f) s = 0.f;                      // -0.0 -> +0.0
+  const uint32_t b = __float_as_uint(s);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// stable descending order by rank counting: rank_i = #{j : key_j > key_i or (key_j == key_i and j < i)}
 __global__ void nms_rank_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, int n,
                                 int* __restrict__ order, float4* __restrict__ sorted) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  __shared__ float sh[256];
-  const float si = i < n ? scores[i] : 0.f;
+  __shared__ uint32_t sh[256];
+  const uint32_t si = i < n ? score_key(scores[i]) : 0u;
   int rank = 0;
   for (int j0 = 0; j0 < n; j0 += 256) {
     __syncthreads();
-    if (j0 + threadIdx.x < n) sh[threadIdx.x] = scores[j0 + threadIdx.x];
+    if (j0 + threadIdx.x < n) sh[threadIdx.x] = score_key(scores[j0 + threadIdx.x]);
     __syncthreads();
     const int lim = min(256, n - j0);
     for (int t = 0; t < lim; ++t) {
-      const float sj = sh[t];
+      const uint32_t sj = sh[t];
       rank += (sj > si) || (sj == si && (j0 + t) < i);
     }
   }

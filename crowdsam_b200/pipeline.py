@@ -108,6 +108,12 @@ class CrowdSAM:
         for crop_box in crop_boxes:
             crop_data = self._process_crop(image, crop_box)
             if crop_data is not None:
+                if len(crop_boxes) > 1 and "rles_info" in crop_data._stats:
+                    # The reference appends every crop's 2-element [crop_box, [H, W]] list (model.py:293) and then
+                    # indexes the concatenation with the cross-crop NMS keep indices (amg.py:55): IndexError as soon
+                    # as a kept index exceeds 2 x n_crops.  Here multi-crop runs keep one [crop_box, [H, W]] entry
+                    # per detection, which filters like every other column; single-crop output is unchanged.
+                    crop_data["rles_info"] = [list(crop_data["rles_info"]) for _ in range(len(crop_data["boxes"]))]
                 data.cat(crop_data)
         if len(crop_boxes) > 1 and "crop_boxes" in data._stats and len(data["crop_boxes"]) > 0:
             cb = data["crop_boxes"].float()

@@ -71,14 +71,17 @@ def grid_points(G: int, size: int = 1024) -> np.ndarray:
 # ------------------------------------------------------------------------------------------------
 # Decoder-output injection keyed by the prompt point (multi-detection end-to-end parity)
 # ------------------------------------------------------------------------------------------------
-def injected_decoder_outputs(coords_xy: np.ndarray, seed: int = 0, sigma_lo: float = 3.0, sigma_hi: float = 14.0,
+def injected_decoder_outputs(coords_xy: np.ndarray, seed: int = 0, r_lo: float = 4.0, r_hi: float = 22.0,
                              lowres: int = 256):
     """Deterministic stand-in for the mask decoder's three outputs, a pure function of each prompt's
     input-frame coordinates (the `apply_coords` output both the reference's `predict_torch` and this
-    repo's `decode_low_res` receive): low-res logits [P,4,256,256] = +6 Gaussian blob near the prompt
-    over a -6 floor plus N(0,0.5) pixel noise, the four candidates sharing a centre with growing sigma;
-    iou [P,4] in U(0,1) (about 10 % of the prompts quantised to quarters: exact score ties across prompts)
-    and cls logits [P,4,1].  Injected on both sides at the low-res-logit boundary so that the whole
+    repo's `decode_low_res` receive): low-res logits [P,4,256,256] = 6*tanh((r - d)/tau) for an elliptical
+    distance d from a centre near the prompt (plateau +6 inside, -6 outside, edge width tau in U[0.4,3] low-res
+    px so that the stability score spreads over ~[0.55, 0.97]), about half of the prompts with a small hole
+    and / or a small satellite island (areas around the 100 px cleanup threshold at full resolution), plus
+    N(0,0.5) pixel noise (ragged edges); the four candidates share the centre with growing radius.
+    iou [P,4] in U(0,1) and cls logits [P,4,1]; about 10 % of the prompts have both quantised (exact score
+    ties across prompts).  Injected on both sides at the low-res-logit boundary so that the whole
     selection chain (PWD score, select_mask, filters, boxes, EPS pruning, NMS, small-region cleanup, RLE,
     crop merge) of the REAL reference runs on many distinct instances (tests/golden/make_golden.py) and is
     compared with the CUDA path on identical inputs."""
@@ -88,22 +91,36 @@ def injected_decoder_outputs(coords_xy: np.ndarray, seed: int = 0, sigma_lo: flo
     low = np.empty((P, 4, lowres, lowres), dtype=np.float32)
     iou = np.empty((P, 4), dtype=np.float32)
     cls = np.empty((P, 4, 1), dtype=np.float32)
+    six = np.float32(6.0)
     for p in range(P):
         kx, ky = int(round(pts[p, 0] * 4)), int(round(pts[p, 1] * 4))
         rng = np.random.default_rng([int(seed), kx & 0xFFFFFFFF, ky & 0xFFFFFFFF])
         cx = np.float32(pts[p, 0] / 4.0 + rng.normal(0.0, 1.5))
         cy = np.float32(pts[p, 1] / 4.0 + rng.normal(0.0, 1.5))
-        sig = np.float32(rng.uniform(sigma_lo, sigma_hi))
+        r = np.float32(rng.uniform(r_lo, r_hi))
+        tau = np.float32(rng.uniform(0.4, 3.0))
         aspect = np.float32(rng.uniform(0.6, 1.8))              # people are taller than wide
-        d2x = (xx - cx) ** 2
-        d2y = ((yy - cy) / aspect) ** 2
+        d = np.sqrt((xx - cx) ** 2 + ((yy - cy) / aspect) ** 2)
+        extras = []
+        for sign in (-1.0, 1.0):                                # a hole inside / an island outside
+            if rng.uniform() < 0.5:
+                rr = np.float32(rng.uniform(1.0, 2.6))
+                ang, rad = rng.uniform(0, 2 * np.pi), (rng.uniform(0.0, 0.5) if sign < 0 else rng.uniform(1.5, 2.0))
+                ex = cx + np.float32(rad * np.cos(ang)) * r
+                ey = cy + np.float32(rad * np.sin(ang)) * r * aspect
+                de = np.sqrt((xx - ex) ** 2 + (yy - ey) ** 2)
+                extras.append((np.float32(sign), np.tanh((rr - de) / np.float32(0.5))))
         for c in range(4):
-            s = sig * np.float32(0.6 + 0.3 * c)
-            low[p, c] = np.float32(-6.0) + np.float32(12.0) * np.exp(-(d2x + d2y) / (np.float32(2.0) * s * s))
+            rc = r * np.float32(0.6 + 0.3 * c)
+            m = six * np.tanh((rc - d) / tau)
+            for sign, e in extras:                               # e = +1 inside the feature, -1 outside
+                m = np.where(e > 0, sign * six * e, m) if c == 0 or sign < 0 else m
+            low[p, c] = m
         low[p] += np.float32(0.5) * rng.standard_normal(low[p].shape, dtype=np.float32)
         q = rng.uniform(0.0, 1.0, 4).astype(np.float32)
+        k = (3.0 * rng.standard_normal(4)).astype(np.float32)
         if rng.uniform() < 0.1:
-            q = np.round(q * 4) / 4
+            q, k = np.round(q * 4) / 4, np.round(k)
         iou[p] = q
-        cls[p, :, 0] = (3.0 * rng.standard_normal(4)).astype(np.float32)
+        cls[p, :, 0] = k
     return torch.from_numpy(low), torch.from_numpy(iou), torch.from_numpy(cls)

@@ -130,3 +130,11 @@ def build_crowdsam(sam, dino, test_cfg):
     m.fuse_simmap = False
     m.output_rles = True
     return m
+
+
+def coco_string(rle) -> str:
+    """COCO compressed string of an uncompressed RLE dict of the reference (through the pycocotools stand-in)."""
+    load()
+    from segment_anything_cs.utils.amg import coco_encode_rle
+
+    return coco_encode_rle(dict(rle))["counts"]

@@ -359,7 +359,8 @@ def nms_reference(boxes: np.ndarray, scores: np.ndarray, thr: float) -> np.ndarr
     """Greedy box NMS with torchvision's arithmetic, restated from the published torchvision
     CPU kernel (torchvision 0.26.0 csrc/ops/cpu/nms_kernel.cpp; dependency absent from the
     reference tree; call sites model.py:171,257,429):
-      order = stable argsort(-score); area = (x2-x1)*(y2-y1) (no +1);
+      order = stable descending sort of the scores (torch.sort semantics: NaN first, -0.0 == 0.0);
+      area = (x2-x1)*(y2-y1) (no +1);
       suppress j when inter/(area_i+area_j-inter) > thr  (fp32; 0/0 = NaN never suppresses).
     Returns kept ORIGINAL indices in stable descending-score order."""
     boxes = np.asarray(boxes, dtype=np.float32)
@@ -367,7 +368,7 @@ def nms_reference(boxes: np.ndarray, scores: np.ndarray, thr: float) -> np.ndarr
     n = boxes.shape[0]
     if n == 0:
         return np.zeros((0,), dtype=np.int64)
-    order = np.argsort(-scores, kind="stable")
+    order = torch.sort(torch.as_tensor(scores), descending=True, stable=True)[1].numpy()
     x1, y1, x2, y2 = (boxes[:, i] for i in range(4))
     areas = (x2 - x1) * (y2 - y1)
     dead = np.zeros(n, dtype=bool)

@@ -236,6 +236,55 @@ def injected_pipeline_case(name, sam, dino, overrides, image_index=0, hw=(1024, 
           "detections", len(res["boxes"]))
 
 
+def injected_crops_case(sam, dino, overrides, image_index, hw, seed):
+    """crop_n_layers = 1 (5 crops).  The reference's own generate() cannot finish this case: MaskData.cat appends
+    the 2-element `rles_info` list of every crop (model.py:293) and MaskData.filter then indexes that list with the
+    NMS keep indices (amg.py:55) -> IndexError as soon as a kept index exceeds 2 x n_crops [observed here].  So the
+    golden pins what does run: the real `_process_crop` of every crop box of the real `generate_crop_boxes`
+    (crop + resize to max_size, EPS, filters incl. the crop-edge filter, per-crop NMS, small regions, uncrop), and
+    the reference's cross-crop NMS statement (model.py:167-176) applied to the concatenated crop outputs."""
+    from torchvision.ops.boxes import batched_nms, box_area
+
+    cfg = dict(DEFAULT_TEST_CFG)
+    cfg.update(overrides)
+    m = ref_import.build_crowdsam(sam, dino, cfg)
+    log = []
+    _inject(m.predictor, seed, log)
+    sacs, _, _ = ref_import.load()
+    from segment_anything_cs.utils.amg import generate_crop_boxes
+
+    img = weights.synthetic_image(image_index, *hw)
+    crop_boxes, _ = generate_crop_boxes(img.shape[:2], cfg["crop_n_layers"], cfg["crop_overlap_ratio"])
+    np.random.seed(42)
+    out = {"cfg_keys": np.array(sorted(overrides.keys())),
+           "cfg_vals": np.array([str(overrides[k]) for k in sorted(overrides.keys())]),
+           "image_index": np.array(image_index), "hw": np.array(hw), "inject_seed": np.array(seed),
+           "crop_boxes_all": np.array(crop_boxes)}
+    boxes, cbs, scores = [], [], []
+    for ci, cb in enumerate(crop_boxes):
+        with torch.no_grad():
+            d = m._process_crop(img, cb)
+        n = 0 if d is None else len(d["boxes"])
+        out[f"crop{ci}_n"] = np.array(n)
+        if d is None:
+            continue
+        for k in ("boxes", "points", "scores", "stability_score", "categories", "crop_boxes"):
+            out[f"crop{ci}_{k}"] = d[k].cpu().numpy()
+        out[f"crop{ci}_rle_counts"] = np.array([ref_import.coco_string(r) for r in d["rles"]])
+        out[f"crop{ci}_rle_size"] = np.array(d["rles"][0]["size"]) if n else np.zeros(2, int)
+        boxes.append(d["boxes"]); cbs.append(d["crop_boxes"]); scores.append(d["scores"])
+    allb, allc = torch.cat(boxes), torch.cat(cbs)
+    sc = 1 / box_area(allc)                                                       # model.py:169
+    keep = batched_nms(allb.float(), sc, torch.zeros_like(allb[:, 0]), iou_threshold=cfg["crop_nms_thresh"])
+    out["cross_keep"] = keep.numpy()
+    out["cross_boxes"] = allb[keep].numpy()
+    out["cross_scores"] = torch.cat(scores)[keep].numpy()
+    out["call_sizes"] = np.array([len(x) for x in log])
+    np.savez_compressed(os.path.join(HERE, "pipeline_inj_crops.npz"), **out)
+    print("wrote injected crops: per-crop detections", [int(out[f"crop{i}_n"]) for i in range(len(crop_boxes))],
+          "kept after cross-crop NMS", len(keep), "of", len(allb))
+
+
 def injected_cases():
     sam_sd, dino_sd = weights.make_sam_state("tiny"), weights.make_dino_state("tiny")
     sam, dino = ref_import.build_sam(sam_sd, "tiny"), ref_import.build_dino(dino_sd, "tiny")
@@ -245,8 +294,8 @@ def injected_cases():
     injected_pipeline_case("p4096", sam, dino, dict(grid_size=64, max_prompts=4096, pos_sim_thresh=-1, points_per_batch=64,
                                                     filter_thresh=2.0, min_mask_region_area=0), seed=3,
                            coordinate_trick=True)
-    injected_pipeline_case("crops", sam, dino, dict(grid_size=16, max_prompts=256, crop_n_layers=1, **eps),
-                           image_index=4, hw=(600, 900), seed=4)
+    injected_crops_case(sam, dino, dict(grid_size=16, max_prompts=256, crop_n_layers=1, **eps), image_index=4,
+                        hw=(600, 900), seed=4)
     for sel in ("max_area", "min_area"):
         injected_pipeline_case(sel, sam, dino, dict(grid_size=16, max_prompts=256, mask_selection=sel, **eps), seed=5)
 
