@@ -90,7 +90,7 @@ class ClockSampler:
 def test_cfg(points_per_batch: int):
     """Reference config overrides of SURVEY.md §8d: every grid cell becomes a prompt, EPS never prunes,
     the OpenCV small-region pass (not on the north_star path) is off; filters keep their YAML defaults."""
-    from oracle.restate import DEFAULT_TEST_CFG
+    from crowdsam_b200.synthetic import DEFAULT_TEST_CFG
 
     c = dict(DEFAULT_TEST_CFG)
     c.update(grid_size=GRID, pos_sim_thresh=-1, max_prompts=GRID * GRID, points_per_batch=points_per_batch,
@@ -204,7 +204,7 @@ def main():
     from crowdsam_b200.modules import DinoVisionTransformer
     from crowdsam_b200.pipeline import CrowdSAM
     from crowdsam_b200.predictor import SamPredictor
-    from oracle import weights     # synthetic weight recipe + images only (test infrastructure, not timed)
+    from crowdsam_b200 import synthetic as weights     # synthetic weight recipe + images (pure data; no oracle import)
 
     if args.warmup < 3:
         print(f"[bench] --warmup {args.warmup} raised to 3 (timing rules: at least 3 warm-up steps)", file=sys.stderr)

@@ -393,11 +393,7 @@ int compute_relpos(const csam_attn_args* a, cudaStream_t st) {
   }
   const size_t smem = (size_t)(4 * a->S - 1) * (a->hd + 1) * sizeof(float);
   CSAM_REQUIRE(smem <= 100 * 1024 && a->groups <= 65535, "csam_vit_attention: rel-pos table too large");
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(relpos_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr = true;
-  }
+  CSAM_DYN_SMEM(relpos_rows_kernel, 100 * 1024, "relpos_rows_kernel");
   relpos_rows_kernel<<<dim3(a->S, a->heads, a->groups), 256, smem, st>>>(
       static_cast<const __half*>(a->qkv_hi), static_cast<const __half*>(a->qkv_lo), a->ld_qkv, a->tokens, a->heads,
       a->hd, a->rel_h, a->rel_w, a->S, a->scratch);
@@ -587,21 +583,13 @@ extern "C" int csam_attn_few_queries(const csam_dec_attn_args* a, void* stream) 
                "csam_attn_few_queries: row strides must be multiples of 4 floats");
   if (a->heads == 8 && a->hd == 16 && a->nq == 7) {   // token -> image cross attention
     const size_t sm = (size_t)16 * 7 * (8 + 8 + 128) * sizeof(float);
-    static bool attr2 = false;
-    if (!attr2) {
-      cudaFuncSetAttribute(attn_t2i_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-      attr2 = true;
-    }
+    CSAM_DYN_SMEM(attn_t2i_kernel<7>, (int)sm, "attn_t2i_kernel<7>");
     attn_t2i_kernel<7><<<a->B, 512, sm, (cudaStream_t)stream>>>(*a);
     return check_launch("attn_t2i_kernel");
   }
   const size_t smem = ((size_t)a->nq * a->nk + a->nq * a->hd + 16 * 8 * 16) * sizeof(float);
   CSAM_REQUIRE(smem <= 200 * 1024, "csam_attn_few_queries: nk too large for shared memory");
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(attn_few_queries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
-  }
+  CSAM_DYN_SMEM(attn_few_queries_kernel, 200 * 1024, "attn_few_queries_kernel");
   dim3 grid(a->heads, a->B);
   attn_few_queries_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(*a);
   return check_launch("attn_few_queries_kernel");

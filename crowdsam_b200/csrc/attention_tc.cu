@@ -702,12 +702,7 @@ static int launch_attn_ts(const csam_attn_args* a, const float* rel, cudaStream_
   t_lo = t_hi;
   if (SPLIT == 3 && make_tmap_2d_f16(&t_lo, a->qkv_lo, rows, cols, a->ld_qkv, 64, 64)) return 1;
   auto kern = vit_attention_ts_kernel<SPLIT, BIAS, NQ, HD>;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
-      return fail("%s", "cudaFuncSetAttribute(smem) failed for vit_attention_ts_kernel");
-    attr = true;
-  }
+  CSAM_DYN_SMEM(kern, Cfg::SMEM_BYTES, "vit_attention_ts_kernel");
   // query tiles -> n_full items of NQ tiles + n_single items of one tile (per head and group)
   const int tiles = (a->tokens + AT_BM - 1) / AT_BM;
   const int HG = a->heads * a->groups;
@@ -734,12 +729,7 @@ static int launch_attn_tc(const csam_attn_args* a, const float* rel, cudaStream_
   t_lo = t_hi;
   if (SPLIT == 3 && make_tmap_2d_f16(&t_lo, a->qkv_lo, rows, cols, a->ld_qkv, 64, 64)) return 1;
   auto kern = vit_attention_tc_kernel<SPLIT, BIAS, PLO, NQ>;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
-      return fail("%s", "cudaFuncSetAttribute(smem) failed for vit_attention_tc_kernel");
-    attr = true;
-  }
+  CSAM_DYN_SMEM(kern, Cfg::SMEM_BYTES, "vit_attention_tc_kernel");
   dim3 grid((a->tokens + AT_BM * NQ - 1) / (AT_BM * NQ), a->heads, a->groups);
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(t_hi, t_lo, *a, rel);
   return check_launch("vit_attention_tc_kernel");

@@ -28,6 +28,34 @@ inline int check_launch(const char* what) {
   }
   return 0;
 }
+// ---- per-device state ---------------------------------------------------------------------------------
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are per DEVICE: a process that calls the
+// library on a second GPU must opt in again there.  One bit per device ordinal in a per-call-site atomic.
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+template <typename Kern>
+inline int ensure_dyn_smem(Kern kern, int bytes, std::atomic<unsigned long long>& done, const char* what) {
+  const int dev = current_device();
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute(max dynamic smem = %d) failed for %s on device %d", bytes, what, dev);
+    return 1;
+  }
+  done.fetch_or(bit, std::memory_order_release);
+  return 0;
+}
+#define CSAM_DYN_SMEM(kern, bytes, what)                                    \
+  do {                                                                      \
+    static std::atomic<unsigned long long> csam_done_{0};                   \
+    if (::csam::ensure_dyn_smem(kern, bytes, csam_done_, what)) return 1;   \
+  } while (0)
+int num_sms();   // SM count of the current device (gemm.cu)
+
 #define CSAM_REQUIRE(cond, msg)                                   \
   do {                                                            \
     if (!(cond)) return ::csam::fail("%s (%lld)", msg, __LINE__); \
@@ -195,6 +223,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Watchdog budget in SM clocks.  A lost arrival is a protocol bug of this library, never a data-dependent event;
+// the budget only has to be far above any legitimate wait.  ~60 s at 2 GHz leaves room for compute-sanitizer /
+// debugger single-stepping and time-sliced (MPS) sharing, where a 2 s budget could kill a healthy process
+// (round-1 ADVICE); build with -DCSAM_MBAR_BUDGET=... to change it, -DCSAM_MBAR_DEBUG to print the waiter.
+#ifndef CSAM_MBAR_BUDGET
+#define CSAM_MBAR_BUDGET 120000000000LL
+#endif
 // Spin on the phase parity; a watchdog turns a lost arrival into a trap instead of a hang.  The trap carries no
 // printf: a (never taken) vprintf call inside the wait loop made ptxas spill every live register around each wait
 // -- 25 STL + 25 LDL per tile in the fused decoder epilogues (ncu: local memory traffic in the hot path).
@@ -212,7 +247,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) break;
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+    if (clock64() - t0 > CSAM_MBAR_BUDGET) {
 #ifdef CSAM_MBAR_DEBUG
       printf("csam: mbarrier watchdog block %d thread %d\n", blockIdx.x, threadIdx.x);
 #endif

@@ -790,12 +790,7 @@ extern "C" int csam_dec_i2t_layer(const csam_i2t_layer_args* a, void* stream) {
   if (make_tmap_2d_f16(&tb1_lo, a->b1_lo, (uint64_t)a->P * 64, 384, 384, 64, 64)) return 1;
   if (make_tmap_2d_f16(&tb2_hi, a->b2_hi, (uint64_t)a->P * 256, 64, 64, 256, 64)) return 1;
   if (make_tmap_2d_f16(&tb2_lo, a->b2_lo, (uint64_t)a->P * 256, 64, 64, 256, 64)) return 1;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(dec_i2t_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I2T_SMEM_BYTES) != cudaSuccess)
-      return fail("%s", "cudaFuncSetAttribute(smem) failed for dec_i2t_layer_kernel");
-    attr = true;
-  }
+  CSAM_DYN_SMEM(dec_i2t_layer_kernel, I2T_SMEM_BYTES, "dec_i2t_layer_kernel");
   I2TParams p;
   p.x_shared = a->x_shared ? 1 : 0;
   p.gate = (!a->x_shared && !(getenv("CSAM_I2T_GATE") && atoi(getenv("CSAM_I2T_GATE")) == 0)) ? 1 : 0;
@@ -836,12 +831,7 @@ extern "C" int csam_dec_t2i(const csam_t2i_args* a, void* stream) {
   if (make_tmap_2d_f16(&tk_lo, a->pek_lo, 4096, 128, 128, 128, 64)) return 1;
   if (make_tmap_2d_f16(&tb1_hi, a->b1_hi, (uint64_t)a->P * 64, 384, 384, 64, 64)) return 1;
   if (make_tmap_2d_f16(&tb1_lo, a->b1_lo, (uint64_t)a->P * 64, 384, 384, 64, 64)) return 1;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(dec_t2i_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2I_SMEM_BYTES) != cudaSuccess)
-      return fail("%s", "cudaFuncSetAttribute(smem) failed for dec_t2i_kernel");
-    attr = true;
-  }
+  CSAM_DYN_SMEM(dec_t2i_kernel, T2I_SMEM_BYTES, "dec_t2i_kernel");
   T2IParams p;
   p.x_shared = a->x_shared ? 1 : 0;
   p.P = a->P;

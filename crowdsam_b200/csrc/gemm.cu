@@ -21,6 +21,7 @@
 //
 // Replaces the nn.Linear / conv call sites listed in include/csam.h (K-GEMM).
 #include "common.cuh"
+#include <mutex>
 
 namespace csam {
 
@@ -722,8 +723,37 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
+// Descriptor cache (the library's only mutable global state besides the launch counter).  A step of the
+// hot path re-uses a few hundred (pointer, shape, box) combinations -- weights always, activations whenever the caching
+// allocator hands the same block back -- and cuTensorMapEncodeTiled costs about a microsecond of host time per call,
+// four times per GEMM launch.  Direct-mapped, 2048 entries, guarded by a mutex (callable from any thread).  The
+// descriptor is a pure function of the key, so a stale entry can never be wrong, only evicted.
+struct TmapKey {
+  const void* ptr; uint64_t rows, cols, ld; uint32_t box_rows, box_cols; int dev;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+           box_cols == o.box_cols && dev == o.dev;
+  }
+};
+struct TmapSlot { TmapKey key; CUtensorMap map; bool valid; };
+static TmapSlot g_tmap_cache[2048];
+static std::mutex g_tmap_mutex;
+static std::atomic<long long> g_tmap_hits{0}, g_tmap_misses{0};
+
 int make_tmap_2d_f16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
                      uint32_t box_rows, uint32_t box_cols) {
+  const TmapKey key{ptr, rows, cols, ld, box_rows, box_cols, current_device()};
+  uint64_t h = reinterpret_cast<uint64_t>(ptr) * 0x9E3779B97F4A7C15ull;
+  h ^= (rows * 0xC2B2AE3D27D4EB4Full) ^ (cols << 21) ^ (ld << 7) ^ ((uint64_t)box_rows << 40) ^ ((uint64_t)box_cols << 52);
+  TmapSlot& slot = g_tmap_cache[(h >> 17) & 2047];
+  {
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
+    if (slot.valid && slot.key == key) {
+      *map = slot.map;
+      g_tmap_hits.fetch_add(1, std::memory_order_relaxed);
+      return 0;
+    }
+  }
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return fail("%s", "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[2] = {cols, rows};
@@ -734,18 +764,27 @@ int make_tmap_2d_f16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t 
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed %s(%lld)", "", (long long)r);
+  g_tmap_misses.fetch_add(1, std::memory_order_relaxed);
+  std::lock_guard<std::mutex> lock(g_tmap_mutex);
+  slot.key = key;
+  slot.map = *map;
+  slot.valid = true;
   return 0;
 }
+long long tmap_cache_hits() { return g_tmap_hits.load(); }
+long long tmap_cache_misses() { return g_tmap_misses.load(); }
 
-static int g_num_sms = 0;
-static int num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+// SM count per device ordinal (a process may drive several GPUs)
+int num_sms() {
+  static std::atomic<int> cache[64];
+  const int dev = current_device() & 63;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n <= 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, current_device());
+    if (n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
-  return g_num_sms;
+  return n;
 }
 
 template <int BN, int SPLIT, bool B_MN, int EPI = EPI_STD, bool WRES = false>
@@ -765,12 +804,7 @@ static int launch_tc(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st)
     if (SPLIT == 3 && make_tmap_2d_f16(&tw_lo, a->w_lo, a->K, a->N, a->ldw, BK, 64)) return 1;
   }
   auto kern = gemm_tc_kernel<BN, SPLIT, B_MN, EPI, WRES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
-      return fail("%s", "cudaFuncSetAttribute(smem) failed for gemm_tc_kernel");
-    attr_set = true;
-  }
+  CSAM_DYN_SMEM(kern, Cfg::SMEM_BYTES, "gemm_tc_kernel");
   const int tiles_m = (a->M + BM - 1) / BM;
   const int tiles_n = (a->N + BN - 1) / BN;
   int grid = min(tiles_m * tiles_n, num_sms());

@@ -99,24 +99,47 @@ __global__ void post_finalize_kernel(int* boxes, int P) {
 struct Quad {
   float ha[16], hb[16];   // horizontal interpolation of low-res rows g-1 (clamped) and g (clamped)
 };
-__device__ __forceinline__ void quad_rows(const float* __restrict__ L, int gI, int X0, Quad& q) {
+struct Taps {
+  float ra[6], rb[6];     // the 12 low-res values the 64 output pixels of a quad depend on
+};
+// Loads the taps and classifies the quad.  Every output pixel is a convex combination of the 12 taps (weights
+// hx + lx = 1, hy + ly = 1, all in [0, 1]) evaluated with 7 rounded fp32 operations, so it lies within
+// [mn, mx] widened by a few ulps.  Returns +1 when all 64 pixels are certainly > hi, -1 when they are certainly
+// <= lo, 0 when the quad has to be evaluated.  The margin (1e-6 relative = 16 ulps, plus a denormal floor) makes
+// the decision safe against the rounding of the full evaluation; non-finite taps (0 * inf = NaN at the clamped
+// borders, NaN compares false) always take the full evaluation.  On instance masks almost every quad is far
+// from the object boundary: the stats pass is otherwise bound by its ~500 ALU operations per quad, not by HBM.
+__device__ __forceinline__ int quad_load(const float* __restrict__ L, int gI, int X0, Taps& t, float hi, float lo) {
   const int ya = max(gI - 1, 0), yb = min(gI, 255);
   const int k0 = X0 >> 2;
-  float ra[6], rb[6];
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
     const int cc = min(max(k0 - 1 + c, 0), 255);
-    ra[c] = L[ya * 256 + cc];
-    rb[c] = L[yb * 256 + cc];
+    t.ra[c] = L[ya * 256 + cc];
+    t.rb[c] = L[yb * 256 + cc];
   }
+  float mn = t.ra[0], mx = t.ra[0], sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    mn = fminf(mn, fminf(t.ra[c], t.rb[c]));
+    mx = fmaxf(mx, fmaxf(t.ra[c], t.rb[c]));
+    sum += t.ra[c] + t.rb[c];
+  }
+  if (!(fabsf(sum) < 3.0e38f)) return 0;                   // NaN / inf among the taps
+  const float margin = 1e-6f * fmaxf(fabsf(mn), fabsf(mx)) + 1e-30f;
+  if (mn - margin > hi) return 1;
+  if (mx + margin < lo) return -1;
+  return 0;
+}
+__device__ __forceinline__ void quad_h(const Taps& t, int X0, Quad& q) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const int i0 = (j + 2) >> 2;
     float lx = ((j & 3) == 0) ? 0.625f : ((j & 3) == 1) ? 0.875f : ((j & 3) == 2) ? 0.125f : 0.375f;
     if (X0 == 0 && j < 2) lx = 0.f;
     const float hx = 1.f - lx;
-    q.ha[j] = hx * ra[i0] + lx * ra[i0 + 1];
-    q.hb[j] = hx * rb[i0] + lx * rb[i0 + 1];
+    q.ha[j] = hx * t.ra[i0] + lx * t.ra[i0 + 1];
+    q.hb[j] = hx * t.rb[i0] + lx * t.rb[i0 + 1];
   }
 }
 // vertical weight of output row Y = 4g - 2 + jr
@@ -138,8 +161,19 @@ __global__ void __launch_bounds__(256) post_stats_quad_kernel(csam_post_args a, 
   for (int s = blockIdx.x * 256 + threadIdx.x; s < total; s += gridDim.x * 256) {
     const int gI = s / segs_per_row, X0 = (s % segs_per_row) * 16;
     const int nx = min(16, g.out_w - X0);
+    Taps tp;
+    const int cls = quad_load(L, gI, X0, tp, fmaxf(t_hi, fmaxf(t_lo, a.thr)), fminf(t_hi, fminf(t_lo, a.thr)));
+    if (cls < 0) continue;                                  // all three comparisons false for all 64 pixels
+    if (cls > 0) {                                          // all three true: counts and box from the geometry
+      const int ya0 = max(4 * gI - 2, 0), yb0 = min(4 * gI + 1, g.out_h - 1);
+      const int n = (yb0 - ya0 + 1) * nx;
+      c_hi += n; c_lo += n; c_mid += n;
+      xmin = min(xmin, X0); xmax = max(xmax, X0 + nx - 1);
+      ymin = min(ymin, ya0); ymax = max(ymax, yb0);
+      continue;
+    }
     Quad q;
-    quad_rows(L, gI, X0, q);
+    quad_h(tp, X0, q);
 #pragma unroll
     for (int jr = 0; jr < 4; ++jr) {
       const int Y = 4 * gI - 2 + jr;
@@ -206,8 +240,20 @@ __global__ void __launch_bounds__(256) post_write_quad_kernel(csam_post_args a, 
   float* lo = a.logits ? a.logits + (size_t)i * g.out_h * g.out_w : nullptr;
   for (int s = blockIdx.x * 256 + threadIdx.x; s < total; s += gridDim.x * 256) {
     const int gI = s / segs_per_row, X0 = (s % segs_per_row) * 16;
+    Taps tp;
+    const int cls = quad_load(L, gI, X0, tp, a.thr, a.thr);
+    if (cls != 0 && !lo) {                                  // uniform quad: four constant 16-byte stores
+      const uint32_t w = cls > 0 ? 0x01010101u : 0u;
+#pragma unroll
+      for (int jr = 0; jr < 4; ++jr) {
+        const int Y = 4 * gI - 2 + jr;
+        if (Y < 0 || Y >= g.out_h) continue;
+        *reinterpret_cast<uint4*>(mo + (size_t)Y * g.out_w + X0) = make_uint4(w, w, w, w);
+      }
+      continue;
+    }
     Quad q;
-    quad_rows(L, gI, X0, q);
+    quad_h(tp, X0, q);
 #pragma unroll
     for (int jr = 0; jr < 4; ++jr) {
       const int Y = 4 * gI - 2 + jr;

@@ -312,15 +312,19 @@ class MaskDecoderEngine:
         if not self.fused_i2t:
             q0, _ = ops.gemm(keys0_h, L0["i2t"].q.w, residual=self.pe_qi[0], want_f32=True)
             q0 = q0.view(1, 4096, 128)
-        dproj, dproj_h = self.dino_proj(dino_tok_h, want_f32=True, want_h16=True)      # [5329,256]
-        planes = ops.transpose_f32(dproj).view(256, 73, 73)
-        dmap = ops.bilinear(planes, 256, 256, chlast=False)                            # [256,256,256]
-        _, dmap_h, _ = ops.layernorm(dmap.view(256 * 32, 2048), normalize=False, want_h16=True, split=split)
-        self.img = dict(keys0=keys0, keys0_h=keys0_h, k0=k0, v0=v0, q0=q0,
-                        dproj_h=dproj_h, dmap_h=dmap_h.view(256, 65536))
+        dproj_h = dmap_h = None
+        if dino_tok_h is not None:
+            dproj, dproj_h = self.dino_proj(dino_tok_h, want_f32=True, want_h16=True)  # [5329,256]
+            planes = ops.transpose_f32(dproj).view(256, 73, 73)
+            dmap = ops.bilinear(planes, 256, 256, chlast=False)                        # [256,256,256]
+            _, dmap_h, _ = ops.layernorm(dmap.view(256 * 32, 2048), normalize=False, want_h16=True, split=split)
+            dmap_h = dmap_h.view(256, 65536)
+        self.img = dict(keys0=keys0, keys0_h=keys0_h, k0=k0, v0=v0, q0=q0, dproj_h=dproj_h, dmap_h=dmap_h)
 
     def fg_logits(self) -> torch.Tensor:
         """predict_fg_map (predictor.py:113-121) -> fp32 [1,n_class,256,256]."""
+        if self.img["dproj_h"] is None:
+            raise RuntimeError("predict_fg_map needs DINOv2 features (the predictor was built without dino_model)")
         logits = self.point_cls(self.img["dproj_h"])                                   # [5329,n_class]
         planes = ops.transpose_f32(logits).view(self.n_class, 73, 73)
         return ops.bilinear(planes, 256, 256, chlast=False).view(1, self.n_class, 256, 256)
@@ -450,10 +454,13 @@ class MaskDecoderEngine:
         # IoU head (mask_decoder.py:184)
         iou = self.iou_head(cols(hs2, 0, 256))                                         # [P,4]
         # PWD-Net (mask_decoder.py:187-198): softmax-weighted pooling of the DINO map as one GEMM
-        e, inv = ops.softmax_weights(masks.view(4 * P, 65536), split)
-        _, pooled = ops.gemm(e, I["dmap_h"], row_scale=inv, want_h16=True)
-        del e
-        cls = self.point_cls(pooled).view(P, 4, self.n_class)
+        if I["dmap_h"] is None:
+            cls = torch.zeros((P, 4, self.n_class), dtype=torch.float32, device=self.dev)   # no DINOv2 features bound
+        else:
+            e, inv = ops.softmax_weights(masks.view(4 * P, 65536), split)
+            _, pooled = ops.gemm(e, I["dmap_h"], row_scale=inv, want_h16=True)
+            del e
+            cls = self.point_cls(pooled).view(P, 4, self.n_class)
         # parallel IoU head on cat(iou_token, mask_token) (mask_decoder.py:194-198); the residual add
         # iou_pred + res_iou_pred is the epilogue of its last GEMM
         m_iou, m_tok = self._gather_maps(P)

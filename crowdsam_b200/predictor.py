@@ -49,10 +49,15 @@ class SamPredictor:
         self.reset_image()
         self.original_size, self.input_size = tuple(original_size), tuple(input_size)
         feats, feat_tok = self.model.image_encoder.forward_u8(img_u8)
-        dino_f32, dino_h = self.dino_model.forward_features_u8(img_u8)
         self.features = feats
-        self.dino_feats = dino_f32.view(1, 73, 73, -1)
-        self._bind(feats, self.dino_feats, feat_tok, dino_h)
+        if self.dino_model is None:
+            # mask / IoU prediction only (SamAutomaticMaskGenerator without PWD-Net features): no DINOv2 pass
+            self.dino_feats = None
+            self._bind(feats, None, feat_tok, None)
+        else:
+            dino_f32, dino_h = self.dino_model.forward_features_u8(img_u8)
+            self.dino_feats = dino_f32.view(1, 73, 73, -1)
+            self._bind(feats, self.dino_feats, feat_tok, dino_h)
         self.is_image_set = True
 
     @torch.no_grad()
@@ -80,7 +85,7 @@ class SamPredictor:
         eng = self.model.mask_decoder.engine()
         if feat_tok is None:
             feat_tok = ops.transpose_f32(feats.reshape(256, 4096).float().contiguous())
-        if dino_h is None:
+        if dino_h is None and dino_feats is not None:
             d = dino_feats.reshape(-1, dino_feats.shape[-1]).float().contiguous()
             _, dino_h, _ = ops.layernorm(d, normalize=False, want_h16=True, split=eng.split)
         eng.set_image(feat_tok, dino_h)
@@ -140,17 +145,19 @@ class SamPredictor:
 
     def predict(self, point_coords=None, point_labels=None, box=None, mask_input=None, multimask_output=True,
                 return_logits=False, attn_sim=None, target_embedding=None):
-        """numpy front end of predict_torch (predictor.py:133-212) for a single prompt."""
+        """numpy front end of predict_torch (predictor.py:133-212) for a single prompt.  Returns the reference's four
+        values: masks [C,H,W], iou [C], class scores [C,n_class] (numpy) and the low-res logits [C,256,256] (tensor, as
+        predictor.py:208-212 leaves it)."""
         if not self.is_image_set:
             raise RuntimeError("An image must be set with .set_image(...) before mask prediction.")
+        if box is not None or mask_input is not None:
+            raise NotImplementedError("only point prompts are on the B200 hot path (boxes / mask inputs are not)")
         assert point_coords is not None and point_labels is not None, "point_labels must be supplied with point_coords."
         pc = self.transform.apply_coords(point_coords, self.original_size)
         ct = torch.as_tensor(pc, dtype=torch.float)[None]
         lt = torch.as_tensor(point_labels, dtype=torch.int)[None]
-        if box is not None or mask_input is not None:
-            raise NotImplementedError("only point prompts are on the B200 hot path")
-        masks, iou, _, low = self.predict_torch(ct, lt, None, None, multimask_output, return_logits=return_logits)
-        return masks[0].cpu().numpy(), iou[0].cpu().numpy(), low[0].cpu().numpy()
+        masks, iou, cls, low = self.predict_torch(ct, lt, None, None, multimask_output, return_logits=return_logits)
+        return masks[0].cpu().numpy(), iou[0].cpu().numpy(), cls[0].cpu().numpy(), low[0]
 
     # ------------------------------------------------------------------ state
     def get_image_embedding(self) -> torch.Tensor:

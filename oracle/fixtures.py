@@ -68,6 +68,14 @@ def grid_points(G: int, size: int = 1024) -> np.ndarray:
     return np.stack([jj.reshape(-1) * (size / G), ii.reshape(-1) * (size / G)], axis=1).astype(int)
 
 
+def cluster_points(n: int, seed: int = 0, n_clusters: int = 12, spread: float = 30.0, size: int = 1024) -> np.ndarray:
+    """n integer prompt points (x, y) around a few cluster centres, so that the injected instances overlap heavily."""
+    rng = np.random.default_rng(3000 + seed)
+    centres = rng.uniform(100, size - 100, (n_clusters, 2))
+    pts = centres[rng.integers(0, n_clusters, n)] + rng.normal(0, spread, (n, 2))
+    return np.clip(np.round(pts), 0, size - 1).astype(np.float64)
+
+
 # ------------------------------------------------------------------------------------------------
 # Decoder-output injection keyed by the prompt point (multi-detection end-to-end parity)
 # ------------------------------------------------------------------------------------------------

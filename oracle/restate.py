@@ -509,11 +509,7 @@ def remove_small_regions(mask: np.ndarray, area_thresh: float, mode: str):
 # --------------------------------------------------------------------------------------
 # L4 pipeline: CrowdSAM.generate                                        model.py:134-449
 # --------------------------------------------------------------------------------------
-DEFAULT_TEST_CFG = dict(   # configs/crowdhuman.yaml:34-60
-    crop_n_layers=0, crop_nms_thresh=0.7, crop_overlap_ratio=0.341, pos_sim_thresh=0.5,
-    grid_size=192, max_prompts=500, filter_thresh=0.7, points_per_batch=32,
-    mask_selection="max_iou", max_size=1024, min_mask_region_area=100, box_nms_thresh=0.65,
-    stability_score_thresh=0.8, stability_score_offset=1, pred_iou_thresh=0.1)
+from crowdsam_b200.synthetic import DEFAULT_TEST_CFG  # noqa: E402  configs/crowdhuman.yaml:34-60 (shared input data)
 
 
 def resize_image(image: np.ndarray, max_size: int):

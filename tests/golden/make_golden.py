@@ -285,6 +285,104 @@ def injected_crops_case(sam, dino, overrides, image_index, hw, seed):
           "kept after cross-crop NMS", len(keep), "of", len(allb))
 
 
+def extra_stage_case():
+    """stage_extra.npz: (1) `mask_iou_nms` of the reference (crowdsam/utils.py:422-459, dead code there but callable)
+    on overlapping instance masks; (2) torchvision nms with NaN / signed-zero scores; (3) the K-POST stage functions of
+    the reference (postprocess_masks, calculate_stability_score, batched_mask_to_box) on injected logits at P = 64."""
+    _, _, cutils = ref_import.load()
+    from segment_anything_cs.utils import amg
+    from segment_anything_cs.modeling.sam import Sam
+    from torchvision.ops import nms as tv_nms
+
+    out = {}
+    # (1) 48 masks at 256x256 from the injected decoder around 12 cluster centres -> heavy overlap
+    pts = fixtures.cluster_points(48, seed=7)
+    low, iou, _ = fixtures.injected_decoder_outputs(pts, seed=7)
+    masks = low[:, 2] > 0                                      # third candidate: the larger ones
+    scores = iou[:, 2].numpy().copy()
+    out["miou_points"] = pts
+    for thr in (0.3, 0.5, 0.8):
+        keep = cutils.mask_iou_nms(np.zeros((len(pts), 4)), scores, masks, thr)
+        out[f"miou_keep_{thr}"] = np.asarray(keep)
+    out["miou_empty"] = np.asarray(cutils.mask_iou_nms(np.zeros((0, 4)), np.zeros(0), masks[:0], 0.5))
+    # (2) NaN / -0.0 scores (torch.sort: NaN first, -0.0 == +0.0, stable)
+    b, sc = fixtures.random_boxes(300, 9)
+    sc = sc.copy()
+    sc[::17] = np.nan
+    sc[5::23] = -0.0
+    sc[6::23] = 0.0
+    out["nan_scores"] = sc
+    out["nan_keep"] = tv_nms(torch.as_tensor(b), torch.as_tensor(sc), 0.65).numpy()
+    # (3) K-POST stage on injected logits, all four planes, P = 64, square and non-square geometry
+    P = 64
+    pts = fixtures.grid_points(8).astype(np.float64)
+    low, iou, cls = fixtures.injected_decoder_outputs(pts, seed=11)
+
+    class _Enc:
+        img_size = 1024
+
+    class _S:
+        image_encoder = _Enc()
+
+    for tag, (inp, orig) in {"sq": ((1024, 1024), (1024, 1024)), "ns": ((683, 1024), (600, 900))}.items():
+        full = Sam.postprocess_masks(_S(), low, inp, orig).flatten(0, 1)
+        out[f"p64_{tag}_stability"] = amg.calculate_stability_score(full, 0.0, 1.0).numpy()
+        binm = full > 0.0
+        out[f"p64_{tag}_boxes"] = amg.batched_mask_to_box(binm).numpy()
+        out[f"p64_{tag}_area"] = binm.flatten(1).sum(1).numpy()
+    np.savez_compressed(os.path.join(HERE, "stage_extra.npz"), **out)
+    print("wrote stage_extra", {k: v.shape for k, v in out.items()})
+
+
+def amg_case():
+    """amg_inj.npz: the reference's SamAutomaticMaskGenerator, which cannot be constructed as shipped
+    (`SamPredictor(model)` lacks dino_model, automatic_mask_generator.py:123) nor unpack predict_torch's 4 returns
+    (:279).  Patched at RUN TIME only (no source copy): the module's `SamPredictor` name is bound to a subclass that
+    supplies dino_model and returns the first three values; the decoder outputs are injected as for the CrowdSAM cases."""
+    sacs, _, _ = ref_import.load()
+    import segment_anything_cs.automatic_mask_generator as ramg
+
+    sam_sd, dino_sd = weights.make_sam_state("tiny"), weights.make_dino_state("tiny")
+    sam, dino = ref_import.build_sam(sam_sd, "tiny"), ref_import.build_dino(dino_sd, "tiny")
+    seed = 21
+
+    class _Pred(sacs.SamPredictor):
+        def __init__(self, model):
+            super().__init__(model, dino)
+
+        def predict_torch(self, point_coords, point_labels, boxes=None, mask_input=None, multimask_output=True,
+                          return_logits=False, **kw):
+            low, iou, cls = fixtures.injected_decoder_outputs(point_coords[:, 0, :].cpu().numpy(), seed)
+            masks = self.model.postprocess_masks(low, self.input_size, self.original_size)
+            if not return_logits:
+                masks = masks > self.model.mask_threshold
+            return masks, iou, cls
+
+    saved = ramg.SamPredictor
+    ramg.SamPredictor = _Pred
+    out = {"inject_seed": np.array(seed)}
+    try:
+        for tag, hw, kw in (("sq", (1024, 1024), dict(min_mask_region_area=0)),
+                            ("ns", (600, 900), dict(min_mask_region_area=100))):
+            gen = ramg.SamAutomaticMaskGenerator(sam, points_per_side=12, points_per_batch=32, pred_iou_thresh=0.5,
+                                                 stability_score_thresh=0.85, box_nms_thresh=0.7,
+                                                 output_mode="coco_rle", **kw)
+            img = weights.synthetic_image(6, *hw)
+            recs = gen.generate(img)
+            out[f"{tag}_hw"] = np.array(hw)
+            out[f"{tag}_bbox"] = np.array([r["bbox"] for r in recs])
+            out[f"{tag}_area"] = np.array([r["area"] for r in recs])
+            out[f"{tag}_iou"] = np.array([r["predicted_iou"] for r in recs], dtype=np.float32)
+            out[f"{tag}_stab"] = np.array([r["stability_score"] for r in recs], dtype=np.float32)
+            out[f"{tag}_point"] = np.array([r["point_coords"][0] for r in recs])
+            out[f"{tag}_crop_box"] = np.array([r["crop_box"] for r in recs])
+            out[f"{tag}_rle"] = np.array([r["segmentation"]["counts"] for r in recs])
+            print("amg", tag, len(recs), "records")
+    finally:
+        ramg.SamPredictor = saved
+    np.savez_compressed(os.path.join(HERE, "amg_inj.npz"), **out)
+
+
 def injected_cases():
     sam_sd, dino_sd = weights.make_sam_state("tiny"), weights.make_dino_state("tiny")
     sam, dino = ref_import.build_sam(sam_sd, "tiny"), ref_import.build_dino(dino_sd, "tiny")
@@ -303,6 +401,10 @@ def injected_cases():
 if __name__ == "__main__":
     assert ref_import.available(), "needs /root/reference"
     torch.manual_seed(0)
+    if "--extra" in sys.argv:
+        extra_stage_case()
+        amg_case()
+        sys.exit(0)
     if "--injected" in sys.argv:
         injected_cases()
         sys.exit(0)
@@ -326,6 +428,8 @@ if __name__ == "__main__":
                        stability_score_thresh=0.5), image_index=2, hw=(768, 1024))
     model_case("tiny_l", "tiny_l", "tiny")
     injected_cases()
+    extra_stage_case()
+    amg_case()
     config0_case()
     config1_case()
     config3_case()

@@ -247,7 +247,7 @@ def test_automatic_mask_generator_vs_oracle():
     full = restate.postprocess_masks(low, (1024, 1024), (1024, 1024)).reshape(-1, 1024, 1024)
     iou_f = iou.reshape(-1)
     stab = restate.stability_score(full, 0.0, 1.0)
-    ok = (iou_f > 0.0) & (stab >= 0.0)
+    ok = torch.ones_like(iou_f, dtype=torch.bool)          # thresholds of 0 disable both filters (reference :294,302)
     boxes = restate.mask_to_box(full[ok] > 0.0)
     keep = restate.nms_reference(boxes.float().numpy(), iou_f[ok].numpy(), 0.7)
     assert len(res) == len(keep) > 0
@@ -265,6 +265,14 @@ def test_automatic_mask_generator_vs_oracle():
                                      output_mode="coco_rle")
     res2 = gen2.generate(img)
     assert len(res2) > 0 and all(isinstance(r["segmentation"]["counts"], str) for r in res2)
+    # dino_model is optional: masks / IoU do not depend on the PWD-Net features
+    gen3 = SamAutomaticMaskGenerator(pred.model, None, points_per_side=4, points_per_batch=8, pred_iou_thresh=0.0,
+                                     stability_score_thresh=0.0, box_nms_thresh=0.7, output_mode="binary_mask")
+    res3 = gen3.generate(img)
+    assert [r["bbox"] for r in res3] == [r["bbox"] for r in res] and [r["predicted_iou"] for r in res3] == [r["predicted_iou"] for r in res]
+    with pytest.raises(RuntimeError):
+        gen3.predictor.set_image(img)
+        gen3.predictor.predict_fg_map()
 
 
 def test_errors_and_state():

@@ -100,3 +100,77 @@ def test_injected_single_batch_equals_batched(golden_dir):
     for k in ("boxes", "points", "scores", "stability_score", "categories"):
         np.testing.assert_array_equal(np.asarray(a[k]), np.asarray(b[k]))
     assert [r["counts"] for r in a["rles"]] == [r["counts"] for r in b["rles"]]
+
+
+# ---- stage-level goldens of the reference's own functions (tests/golden/stage_extra.npz) -----------------------------
+def test_mask_iou_nms_vs_reference_function(golden_dir):
+    """The drop-in `crowdsam.utils.mask_iou_nms` (greedy wrapper over K-MIOU) against the reference function
+    crowdsam/utils.py:422-459 run on the same overlapping instance masks."""
+    from crowdsam_b200.dropin.crowdsam import utils as dutils
+    from oracle import fixtures
+
+    g = np.load(os.path.join(golden_dir, "stage_extra.npz"))
+    low, iou, _ = fixtures.injected_decoder_outputs(g["miou_points"], seed=7)
+    masks, scores = (low[:, 2] > 0).to(DEV), iou[:, 2].numpy()
+    for thr in (0.3, 0.5, 0.8):
+        keep = dutils.mask_iou_nms(np.zeros((48, 4)), scores, masks, thr)
+        np.testing.assert_array_equal(np.asarray(keep), g[f"miou_keep_{thr}"])
+    assert len(dutils.mask_iou_nms(np.zeros((0, 4)), np.zeros(0), masks[:0], 0.5)) == 0
+
+
+def test_box_nms_nan_and_signed_zero_scores(golden_dir):
+    """torchvision.ops.nms sorts NaN scores first and treats -0.0 == +0.0 (stable); K-NMS ranks by a total order key."""
+    from crowdsam_b200 import ops
+    from oracle import fixtures
+
+    g = np.load(os.path.join(golden_dir, "stage_extra.npz"))
+    b, _ = fixtures.random_boxes(300, 9)
+    keep = ops.box_nms(torch.as_tensor(b, device=DEV), torch.as_tensor(g["nan_scores"], device=DEV), 0.65)
+    np.testing.assert_array_equal(keep.cpu().numpy(), g["nan_keep"])
+
+
+@pytest.mark.parametrize("tag,inp,orig", [("sq", (1024, 1024), (1024, 1024)), ("ns", (683, 1024), (600, 900))])
+def test_kpost_all_planes_p64_vs_reference(tag, inp, orig, golden_dir):
+    """K-POST stats on 256 planes (64 prompts x 4 candidates) of injected logits against the reference's
+    postprocess_masks + calculate_stability_score + batched_mask_to_box: counts ratio and boxes bit-exact."""
+    from crowdsam_b200 import ops
+    from oracle import fixtures
+
+    g = np.load(os.path.join(golden_dir, "stage_extra.npz"))
+    low, _, _ = fixtures.injected_decoder_outputs(fixtures.grid_points(8).astype(np.float64), seed=11)
+    flat = low.reshape(-1, 256, 256).to(DEV)
+    counts, boxes = ops.mask_post_stats(flat, None, inp, orig, 0.0, 1.0)
+    stab = (counts[:, 0] / counts[:, 1]).cpu().numpy()
+    n_box = int((boxes.cpu().numpy() == g[f"p64_{tag}_boxes"]).all(1).sum())
+    n_stab = int((stab == g[f"p64_{tag}_stability"]).sum())
+    n_area = int((counts[:, 2].cpu().numpy() == g[f"p64_{tag}_area"]).sum())
+    print(f"[kpost p64 {tag}] exact boxes {n_box}/256, stability {n_stab}/256, area {n_area}/256")
+    assert n_box == 256 and n_stab == 256 and n_area == 256
+    masks, _ = ops.mask_post_write(flat, None, None, inp, orig, 0.0)
+    assert np.array_equal(masks.flatten(1).sum(1).cpu().numpy(), g[f"p64_{tag}_area"])
+
+
+@pytest.mark.parametrize("tag,extra", [("sq", dict(min_mask_region_area=0)), ("ns", dict(min_mask_region_area=100))])
+def test_automatic_mask_generator_vs_patched_reference(tag, extra, golden_dir):
+    """SamAutomaticMaskGenerator against the reference class patched at run time (make_golden.py amg_case): ~200
+    records, every field exact (bbox, area, predicted_iou, point_coords, stability_score, crop_box, COCO RLE)."""
+    from crowdsam_b200.automask import SamAutomaticMaskGenerator
+    from oracle import weights
+    from test_gpu_model import make_predictor
+
+    g = np.load(os.path.join(golden_dir, "amg_inj.npz"))
+    base, *_ = make_predictor("tiny")
+    gen = SamAutomaticMaskGenerator(base.model, base.dino_model, points_per_side=12, points_per_batch=32,
+                                    pred_iou_thresh=0.5, stability_score_thresh=0.85, box_nms_thresh=0.7,
+                                    output_mode="coco_rle", **extra)
+    iu.inject_predictor(gen.predictor, int(g["inject_seed"]))
+    recs = gen.generate(weights.synthetic_image(6, *(int(x) for x in g[f"{tag}_hw"])))
+    assert len(recs) == len(g[f"{tag}_bbox"]) > 100
+    np.testing.assert_array_equal(np.array([r["bbox"] for r in recs]), g[f"{tag}_bbox"])
+    np.testing.assert_array_equal(np.array([r["area"] for r in recs]), g[f"{tag}_area"])
+    np.testing.assert_array_equal(np.array([r["predicted_iou"] for r in recs], dtype=np.float32), g[f"{tag}_iou"])
+    np.testing.assert_array_equal(np.array([r["stability_score"] for r in recs], dtype=np.float32), g[f"{tag}_stab"])
+    np.testing.assert_array_equal(np.array([r["point_coords"][0] for r in recs]), g[f"{tag}_point"])
+    np.testing.assert_array_equal(np.array([r["crop_box"] for r in recs]), g[f"{tag}_crop_box"])
+    assert [r["segmentation"]["counts"] for r in recs] == [str(x) for x in g[f"{tag}_rle"]]
+    assert all(r["segmentation"]["size"] == [int(x) for x in g[f"{tag}_hw"]] for r in recs)

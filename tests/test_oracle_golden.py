@@ -231,3 +231,21 @@ def test_injected_crops(golden_dir):
     keep = restate.nms_reference(allb.astype(np.float32), sc.astype(np.float32), m.cfg["crop_nms_thresh"])
     np.testing.assert_array_equal(keep, g["cross_keep"])
     assert len(keep) < len(allb)                                         # the cross-crop NMS really suppresses
+
+
+def test_stage_extra(golden_dir):
+    """mask_iou_nms of the reference (crowdsam/utils.py:422-459), torchvision nms with NaN / signed-zero scores, and the
+    post-processing stage functions on injected logits at P = 64 (all four planes), vs the oracle."""
+    g = np.load(os.path.join(golden_dir, "stage_extra.npz"))
+    low, iou, _ = fixtures.injected_decoder_outputs(g["miou_points"], seed=7)
+    masks, scores = low[:, 2] > 0, iou[:, 2].numpy()
+    for thr in (0.3, 0.5, 0.8):
+        np.testing.assert_array_equal(restate.mask_iou_nms(scores, masks, thr), g[f"miou_keep_{thr}"])
+    assert len(g["miou_keep_0.3"]) < len(g["miou_keep_0.8"]) < 48
+    b, _ = fixtures.random_boxes(300, 9)
+    np.testing.assert_array_equal(restate.nms_reference(b, g["nan_scores"], 0.65), g["nan_keep"])
+    low, _, _ = fixtures.injected_decoder_outputs(fixtures.grid_points(8).astype(np.float64), seed=11)
+    for tag, (inp, orig) in {"sq": ((1024, 1024), (1024, 1024)), "ns": ((683, 1024), (600, 900))}.items():
+        full = restate.postprocess_masks(low, inp, orig).flatten(0, 1)
+        np.testing.assert_array_equal(restate.stability_score(full, 0.0, 1.0).numpy(), g[f"p64_{tag}_stability"])
+        np.testing.assert_array_equal(restate.mask_to_box(full > 0).numpy(), g[f"p64_{tag}_boxes"])
