@@ -293,6 +293,10 @@ class MaskDecoderEngine:
         self.point_cls = _MLP(sd, f"{m}.point_classifier", 2, dev, split)
         self._maps: Dict[int, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
         self.img = None
+        self.img_gen = 0                  # bumped whenever the bound image changes (set_image or a graph replay)
+        from .graphs import GraphCache
+
+        self.graphs = GraphCache(2)       # captured set_image regions (per image shape), each owning its decode graphs
 
     # ---- per-image, prompt-independent work -------------------------------------------------
     def set_image(self, feat_tok: torch.Tensor, dino_tok_h: H16):
@@ -320,6 +324,7 @@ class MaskDecoderEngine:
             _, dmap_h, _ = ops.layernorm(dmap.view(256 * 32, 2048), normalize=False, want_h16=True, split=split)
             dmap_h = dmap_h.view(256, 65536)
         self.img = dict(keys0=keys0, keys0_h=keys0_h, k0=k0, v0=v0, q0=q0, dproj_h=dproj_h, dmap_h=dmap_h)
+        self.img_gen += 1
 
     def fg_logits(self) -> torch.Tensor:
         """predict_fg_map (predictor.py:113-121) -> fp32 [1,n_class,256,256]."""

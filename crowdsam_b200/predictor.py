@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import numpy as np
 import torch
 
-from . import ops
+from . import graphs, ops
 from .ops import H16
 from .transforms import ResizeLongestSide
 
@@ -43,21 +43,46 @@ class SamPredictor:
             h, w = mask_t.shape[-2:]
             return torch.nn.functional.pad(mask_t, (0, size - w, 0, size - h))
 
+    @staticmethod
+    def _encode_bind(enc, dino_eng, eng, img_u8: torch.Tensor):
+        """Both encoders + the prompt-independent decoder work for one image: the region that is replayed as ONE
+        CUDA graph (static shapes, ~380 launches, no host sync).  Returns (features, dino_feats, engine image state)."""
+        feats, feat_tok = enc.forward(img_u8)
+        dino_feats, dino_h = None, None
+        if dino_eng is not None:
+            dino_f32, dino_h = dino_eng.forward(img_u8)
+            dino_feats = dino_f32.view(1, 73, 73, -1)
+        eng.set_image(feat_tok, dino_h)
+        return feats, dino_feats, eng.img
+
     @torch.no_grad()
     def _set_u8(self, img_u8: torch.Tensor, original_size, input_size):
         """img_u8: uint8 [h,w,3] or [3,h,w] on the device at the model resolution."""
         self.reset_image()
         self.original_size, self.input_size = tuple(original_size), tuple(input_size)
-        feats, feat_tok = self.model.image_encoder.forward_u8(img_u8)
-        self.features = feats
-        if self.dino_model is None:
-            # mask / IoU prediction only (SamAutomaticMaskGenerator without PWD-Net features): no DINOv2 pass
-            self.dino_feats = None
-            self._bind(feats, None, feat_tok, None)
-        else:
-            dino_f32, dino_h = self.dino_model.forward_features_u8(img_u8)
-            self.dino_feats = dino_f32.view(1, 73, 73, -1)
-            self._bind(feats, self.dino_feats, feat_tok, dino_h)
+        enc = self.model.image_encoder.engine()
+        # without a DINOv2 model: mask / IoU prediction only (SamAutomaticMaskGenerator needs no PWD-Net features)
+        dino_eng = self.dino_model.engine() if self.dino_model is not None else None
+        eng = self.model.mask_decoder.engine()
+        out = None
+        if graphs.usable():
+            key = ("set_image", tuple(img_u8.shape), id(enc), id(dino_eng))
+            g = eng.graphs.get(key)
+            if g is None and eng.graphs.second_sight(key):
+                g = eng.graphs.put(key, graphs.Graphed(lambda im: SamPredictor._encode_bind(enc, dino_eng, eng, im), [img_u8]))
+                g.out[2]["_decode_graphs"] = graphs.GraphCache(3)
+            if g is not None:
+                feats, dino_feats, state = g(img_u8)
+                eng.img = state          # the engine state this replay just refreshed (decode graphs hang off it)
+                eng.img_gen += 1
+                # the graph's output buffers are rewritten by the next set_image: hand out copies (4 MB + 22 MB),
+                # callers may keep `predictor.features` of earlier images (tools/train.py caches them)
+                out = (feats.clone(), None if dino_feats is None else dino_feats.clone())
+        if out is None:
+            feats, dino_feats, _ = self._encode_bind(enc, dino_eng, eng, img_u8)
+            out = (feats, dino_feats)
+        self.features, self.dino_feats = out
+        self._bound = (self.features, self.dino_feats, eng, eng.img_gen)
         self.is_image_set = True
 
     @torch.no_grad()
@@ -89,14 +114,17 @@ class SamPredictor:
             d = dino_feats.reshape(-1, dino_feats.shape[-1]).float().contiguous()
             _, dino_h, _ = ops.layernorm(d, normalize=False, want_h16=True, split=eng.split)
         eng.set_image(feat_tok, dino_h)
-        self._bound = (feats, dino_feats, eng)
+        self._bound = (feats, dino_feats, eng, eng.img_gen)
 
     def _engine(self):
         if not self.is_image_set:
             raise RuntimeError("An image must be set with .set_image(...) before mask prediction.")
         eng = self.model.mask_decoder.engine()
         b = self._bound
-        if b is None or b[0] is not self.features or b[1] is not self.dino_feats or b[2] is not eng:
+        # the decoder engine holds ONE image state; rebind when the caller assigned other embeddings, the engine was
+        # rebuilt (weights changed) or another predictor sharing the model set a different image in between
+        if (b is None or b[0] is not self.features or b[1] is not self.dino_feats or b[2] is not eng
+                or b[3] != eng.img_gen):
             self._bind(self.features, self.dino_feats)
         return self._bound[2]
 
@@ -122,7 +150,21 @@ class SamPredictor:
         """low-res logits [P,4,256,256], iou [P,4], cls [P,4,n_class] without the full-size upsample."""
         eng = self._engine()
         c01, lab = self._coords01(point_coords, point_labels, boxes, mask_input)
-        return eng.decode(c01, lab)
+        return self._decode(eng, c01, lab)[0]
+
+    def _decode(self, eng, c01, lab):
+        """-> ((low, iou, cls), from_graph).  The decoder's ~110 launches for a prompt batch are replayed as one CUDA
+        graph when the image state came from a set_image graph (static pointers) and this batch size was seen before;
+        graph outputs are static buffers, valid until the next decode of the same size."""
+        dg = eng.img.get("_decode_graphs") if (eng.img is not None and graphs.usable()) else None
+        if dg is not None:
+            P = int(c01.shape[0])
+            g = dg.get(P)
+            if g is None and dg.second_sight(P):
+                g = dg.put(P, graphs.Graphed(eng.decode, [c01, lab]))
+            if g is not None:
+                return g(c01, lab), True
+        return eng.decode(c01, lab), False
 
     @torch.no_grad()
     def predict_torch(self, point_coords: Optional[torch.Tensor], point_labels: Optional[torch.Tensor],
@@ -131,7 +173,10 @@ class SamPredictor:
                       target_embedding=None):
         if not self.is_image_set:
             raise RuntimeError("An image must be set with .set_image(...) before mask prediction.")
-        low, iou, cls = self.decode_low_res(point_coords, point_labels, boxes, mask_input)
+        c01, lab = self._coords01(point_coords, point_labels, boxes, mask_input)
+        (low, iou, cls), static = self._decode(self._engine(), c01, lab)
+        if static:                                       # public API: results must outlive the next call
+            low, iou, cls = low.clone(), iou.clone(), cls.clone()
         if not multimask_output:                         # mask_decoder.py:128-134
             low, iou, cls = low[:, :1].contiguous(), iou[:, :1], cls[:, :1]
         P, Cn = low.shape[:2]

@@ -286,6 +286,13 @@ def test_errors_and_state():
         pred.set_image(np.zeros((10, 10, 3), np.uint8), image_format="XYZ")
     with pytest.raises(AssertionError):
         pred.set_torch_image(torch.zeros(1, 3, 100, 100, dtype=torch.uint8), (100, 100))
+    # predict(): the reference's four return values (predictor.py:196-212), box / mask prompts refused up front
+    pred.set_image(weights.synthetic_image(0))
+    m, iou, cls, low = pred.predict(np.array([[500.0, 400.0]]), np.array([1]))
+    assert m.shape == (4, 1024, 1024) and m.dtype == bool and iou.shape == (4,) and cls.shape == (4, 1)
+    assert isinstance(low, torch.Tensor) and low.shape == (4, 256, 256)
+    with pytest.raises(NotImplementedError):
+        pred.predict(np.array([[5.0, 4.0]]), np.array([1]), box=np.array([0, 0, 10, 10]))
 
 
 def test_full_scale_vit_l_grid32_against_oracle_run():
