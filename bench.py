@@ -9,8 +9,10 @@ A step = one image.  Reported on one JSON line:
   e2e     the same metric through the public API `CrowdSAM.generate(np.ndarray)`: pinned-host image ->
           H2D every step, full result dict (boxes, scores, COCO RLEs) read back to the host
   roofline      dominant kernel class, CUDA-event timed inside the timed region
-  cpu_baseline  the CPU oracle port (oracle/restate.py) on a bounded sample of the same workload
-`--impl reference` times the reference's CPU path (oracle port) instead.
+  cpu_baseline  ONE full, un-extrapolated image of the same workload through the reference's CPU path
+`--impl reference` times the reference's own CPU path on full images: the real /root/reference code when that tree
+(or baseline/_ref) is present, else the oracle port (oracle/restate.py); as many whole images as fit the time budget,
+never an extrapolated sample.
 """
 from __future__ import annotations
 
@@ -99,81 +101,111 @@ def test_cfg(points_per_batch: int):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU oracle timing (cpu_baseline leg and --impl reference)
+# The reference's CPU path on whole images (cpu_baseline leg and --impl reference)
 # ------------------------------------------------------------------------------------------------
-def cpu_sample_seconds(sam_sd, dino_sd, image_index: int, frac_blocks: int = 1, n_prompts: int = 64):
-    """Bounded sample of the workload on the host cores with the oracle port (10-20 s of CPU work): both encoders
-    in full by default (frac_blocks = 1; otherwise 1/frac of the SAM ViT-L and of the DINOv2 blocks), patch embed +
-    neck, and `n_prompts` of the 1024 prompts through decoder + post-processing + NMS.  Returns (extrapolated
-    seconds per image, description).  Extrapolation: blocks x frac, prompts x 1024/n_prompts, fixed parts x 1."""
+CPU_POINTS_PER_BATCH = 64      # 1024 prompts at once would materialise 2 x 17 GB of fp32 masks on the host
+
+
+def make_cpu_model():
+    """-> (generate(image) -> result, kind, description).  Probes baseline/_ref, then $CROWDSAM_REFERENCE or
+    /root/reference, for the real reference (crowdsam/model.py on CPU with the three import shims of SURVEY §8c);
+    falls back to the oracle port, which is pinned to the real reference by tests/golden."""
     import torch
-    from oracle import restate, weights
+    from crowdsam_b200 import synthetic as weights
 
-    D, depth, heads, glob = weights.SAM_ARCHS[ARCH]
-    dD, ddepth, dheads = weights.DINO_ARCHS[DINO]
-    img = torch.as_tensor(weights.synthetic_image(image_index)).permute(2, 0, 1)[None]
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = test_cfg(CPU_POINTS_PER_BATCH)
+    sam_sd, dino_sd = weights.make_sam_state(ARCH), weights.make_dino_state(DINO)
+    for cand in (os.path.join(ROOT, "baseline", "_ref"), os.environ.get("CROWDSAM_REFERENCE", "/root/reference")):
+        if os.path.isdir(os.path.join(cand, "segment_anything_cs")) and os.path.isdir(os.path.join(cand, "crowdsam")):
+            os.environ["CROWDSAM_REFERENCE"] = cand
+            from oracle import ref_import
+
+            ref_import.REF_ROOT = cand
+            sam, dino = ref_import.build_sam(sam_sd, ARCH), ref_import.build_dino(dino_sd, DINO)
+            m = ref_import.build_crowdsam(sam, dino, cfg)
+            return (lambda img: m.generate(img)), "reference", f"real reference at {cand} (crowdsam.model.CrowdSAM.generate, CPU fp32)"
+    from oracle import restate
+
+    _, depth, heads, glob = weights.SAM_ARCHS[ARCH]
+    _, ddepth, dheads = weights.DINO_ARCHS[DINO]
+    m = restate.OracleCrowdSAM(sam_sd, dino_sd, (depth, heads, glob), (ddepth, dheads), cfg)
+    return (lambda img: m.generate(img)), "port", ("oracle port of crowdsam.model.CrowdSAM.generate (oracle/restate.py, CPU fp32; "
+                                                   "no reference tree at baseline/_ref or /root/reference on this host)")
+
+
+def time_cpu_images(gen, first_index: int, max_images: int, budget_s: float):
+    """Whole images through the CPU path until `max_images` or the budget is reached (at least one)."""
+    import torch
+    from crowdsam_b200 import synthetic as weights
+
+    secs = []
     with torch.no_grad():
-        t0 = time.perf_counter()
-        x = restate.preprocess(img)
-        # SAM encoder with the first depth/frac blocks (global block 5 included)
-        sd = sam_sd
-        feats = restate.sam_encoder(sd, x, depth // frac_blocks, heads, glob)
-        t_sam = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        x2 = torch.nn.functional.interpolate(x, (1022, 1022), mode="bilinear")
-        dino = restate.dino_forward(dino_sd, x2, ddepth // frac_blocks, dheads).view(1, 73, 73, -1)
-        t_dino = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        from oracle import fixtures
-
-        pts = fixtures.grid_points(GRID)[:n_prompts]
-        coords = torch.as_tensor(restate.apply_coords(pts, (1024, 1024)))[:, None, :]
-        labels = torch.ones(n_prompts, dtype=torch.int)[:, None]
-        sparse = restate.embed_points(sd, coords, labels)
-        low, iou, cls = restate.mask_decoder(sd, feats, restate.dense_pe(sd), sparse, dino)
-        full = restate.postprocess_masks(low, (1024, 1024), (1024, 1024))
-        score = torch.clamp(iou, 0.0) * cls.squeeze(2).sigmoid()
-        sel = score.max(dim=-1)[1]
-        m = full[torch.arange(n_prompts), sel]
-        restate.stability_score(m, 0.0, 1.0)
-        boxes = restate.mask_to_box(m > 0.0)
-        restate.nms_reference(boxes.float().numpy(), score.max(dim=-1)[0].numpy(), 0.65)
-        t_dec = time.perf_counter() - t0
-    total = t_sam * frac_blocks + t_dino * frac_blocks + t_dec * (GRID * GRID / n_prompts)
-    desc = (f"oracle port, {depth // frac_blocks}/{depth} SAM ViT-L blocks + {ddepth // frac_blocks}/{ddepth} DINOv2 blocks "
-            f"+ {n_prompts}/{GRID * GRID} prompts (decoder+post+NMS), extrapolated linearly; "
-            f"measured {t_sam:.2f}s+{t_dino:.2f}s+{t_dec:.2f}s")
-    return total, desc
+        while len(secs) < max_images:
+            img = weights.synthetic_image(first_index + len(secs))
+            np.random.seed(42)
+            t0 = time.perf_counter()
+            res = gen(img)
+            secs.append(time.perf_counter() - t0)
+            n_det = len(res["boxes"])
+            if sum(secs) + max(secs) > budget_s:
+                break
+    return secs, n_det
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     import torch
-    from oracle import weights
 
-    torch.set_num_threads(os.cpu_count() or 1)
-    sam_sd, dino_sd = weights.make_sam_state(ARCH), weights.make_dino_state(DINO)
-    # Size of one step's bounded sample so that the whole K + W run stays within a few minutes: the full sample
-    # (both encoders + 64 prompts) is ~12 s on a 16-core host, the half one ~6.5 s, the quarter one ~3.3 s.
-    n_runs = max(1, args.steps + args.warmup)
-    frac, npr = (1, 64) if n_runs <= 10 else ((2, 32) if n_runs <= 24 else (4, 16))
-    for i in range(args.warmup):
-        cpu_sample_seconds(sam_sd, dino_sd, i, frac, npr)
-    secs, desc = [], ""
-    for i in range(args.steps):
-        s, desc = cpu_sample_seconds(sam_sd, dino_sd, args.warmup + i, frac, npr)
-        secs.append(s)
+    gen, kind, what = make_cpu_model()
+    budget = float(os.environ.get("CSAM_REF_BUDGET_S", "200"))
+    secs, n_det = time_cpu_images(gen, args.warmup, max(1, args.steps), budget)
     per_img = sum(secs) / len(secs)
     value = 1.0 / per_img
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": per_img * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "arch": ARCH, "grid": GRID, "prompts": GRID * GRID, "device": "cpu"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": desc},
+    sample = (f"{what}; {len(secs)} whole image(s) timed end to end, un-extrapolated ({', '.join(f'{x:.1f}' for x in secs)} s; "
+              f"requested {args.steps}, time budget {budget:.0f} s), {CPU_POINTS_PER_BATCH} prompts per decoder batch, no warm-up image")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(secs),
+            "steps_requested": args.steps, "warmup": 0, "ms_per_step": per_img * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": bench_config(ARCH, max(1, args.gpus)),
+            "run": {"points_per_batch": CPU_POINTS_PER_BATCH, "masks_into_nms": None, "detections": n_det},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def bench_config(arch, world):
+    """The workload, identical on both arms (the driver compares `config`); how each arm batched the prompts and
+    what it found goes under `run`."""
+    return {"workload": WORKLOAD, "arch": arch, "dino": DINO, "grid": GRID, "prompts": GRID * GRID,
+            "filters": "pred_iou 0.1, stability 0.8 @ offset 1, box NMS 0.65 (YAML defaults), EPS pruning off, small-region pass off",
+            "l2": "working set (weights 2.5 GB + per-batch activations > 10 GB) far exceeds the 126 MB L2",
+            "parallelism": f"images sharded one per rank x{world}, all-gather of detections"}
+
+
+def post_fixture(P: int, dev):
+    """Instance-like low-res logits [P,4,256,256] on the device (plateau +6 inside an ellipse, -6 outside, edge width
+    0.4-3 px, N(0,0.5) pixel noise: the shape of oracle/fixtures.py injected_decoder_outputs) + a selected plane."""
+    import torch
+
+    g = torch.Generator(device=dev).manual_seed(0)
+    yy, xx = torch.meshgrid(torch.arange(256, device=dev, dtype=torch.float32),
+                            torch.arange(256, device=dev, dtype=torch.float32), indexing="ij")
+    cx, cy = (torch.rand(P, 1, 1, 1, device=dev, generator=g) * 255 for _ in range(2))
+    r = 4 + 18 * torch.rand(P, 1, 1, 1, device=dev, generator=g)
+    tau = 0.4 + 2.6 * torch.rand(P, 1, 1, 1, device=dev, generator=g)
+    asp = 0.6 + 1.2 * torch.rand(P, 1, 1, 1, device=dev, generator=g)
+    grow = torch.tensor([0.6, 0.9, 1.2, 1.5], device=dev).view(1, 4, 1, 1)
+    low = torch.empty((P, 4, 256, 256), device=dev)
+    for s0 in range(0, P, 128):
+        sl = slice(s0, min(s0 + 128, P))
+        d = torch.sqrt((xx - cx[sl]) ** 2 + ((yy - cy[sl]) / asp[sl]) ** 2)
+        low[sl] = 6.0 * torch.tanh((r[sl] * grow - d) / tau[sl])
+    low += 0.5 * torch.randn(low.shape, device=dev, generator=g)
+    sel = torch.randint(0, 4, (P,), device=dev, generator=g).to(torch.int32)
+    return low.contiguous(), sel
 
 
 # ------------------------------------------------------------------------------------------------
@@ -199,7 +231,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from crowdsam_b200 import lib, ops, parallel
+    from crowdsam_b200 import graphs, lib, ops, parallel
     from crowdsam_b200.build import _build_sam
     from crowdsam_b200.modules import DinoVisionTransformer
     from crowdsam_b200.pipeline import CrowdSAM
@@ -241,7 +273,7 @@ def main():
     def gather_dets(dets):
         """The one exchange step: all-gather of padded [K, Nmax, 6] detections + counts."""
         if world > 1:
-            parallel.gather_detections(dets, nmax=64, device=dev)
+            parallel.gather_detections(dets, device=dev)
 
     # ---------------- device-resident leg (value) ----------------
     for i in range(args.warmup):
@@ -250,7 +282,7 @@ def main():
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = lib.launch_count()
+    l0 = lib.launch_count() + graphs.replayed_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dets, nk = [], (0, 0)
     ev0.record()
@@ -265,11 +297,12 @@ def main():
     ms_total = ev0.elapsed_time(ev1)
     print(f"[bench rank {rank}] resident leg: {ms_total / args.steps:.1f} ms/step, masks into NMS {nk[0]}, kept {nk[1]}",
           file=sys.stderr)
-    launches = lib.launch_count() - l0
+    launches = lib.launch_count() + graphs.replayed_launches - l0      # eager launches + kernels inside graph replays
     clocks = sampler.stop()
     # Per-kernel-class CUDA-event timing (the roofline numbers) runs as a SECOND pass over the same K images:
     # two event records around each of ~460 launches cost ~5 ms per step, which must not sit inside `value`.
-    # Same kernels, same inputs, same stream; each class's share is taken against this pass's own step time.
+    # Same kernels, same inputs, same stream, launched one by one (no graph replay: events cannot be timed inside a
+    # graph); each class's share is taken against this pass's own step time.
     ops.PROFILER = ops.Profiler(detail=args.gemm_shapes)
     pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pv0.record()
@@ -295,32 +328,39 @@ def main():
     value = world * args.steps / (ms_total / 1e3)
 
     # ---------------- K-POST at full size: the "all-survive" run of SURVEY §8d (N = P = 1024 masks) ----------
+    # stats pass + write pass TOGETHER on instance-like logits (plateau blobs with ragged edges, as the injected
+    # parity fixture): per prompt the two passes read the selected 256x256 fp32 plane once each and write one
+    # 1024x1024 bool mask = 1,572,864 B (SURVEY §8d counts all four planes once: 2,097,216 B; also reported).
     post_roof = None
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
     if rank == 0:
-        g = torch.Generator(device="cpu").manual_seed(0)
-        low = (torch.randn(256, 4, 64, 64, generator=g) * 8).to(dev)
-        low = torch.nn.functional.interpolate(low, (256, 256), mode="nearest").repeat(4, 1, 1, 1).contiguous()   # [1024,4,256,256]
-        sel = torch.randint(0, 4, (1024,), generator=g).to(torch.int32).to(dev)
+        low, sel = post_fixture(1024, dev)
         for _ in range(3):
+            ops.mask_post_stats(low, sel, (1024, 1024), (1024, 1024), 0.0, 1.0)
             ops.mask_post_write(low, sel, None, (1024, 1024), (1024, 1024), 0.0)
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
-        p0.record()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        reps, ms_s, ms_w = 5, 0.0, 0.0
         for _ in range(reps):
+            evs[0].record()
+            ops.mask_post_stats(low, sel, (1024, 1024), (1024, 1024), 0.0, 1.0)
+            evs[1].record()
             mk, _ = ops.mask_post_write(low, sel, None, (1024, 1024), (1024, 1024), 0.0)
-        p1.record()
-        torch.cuda.synchronize()
-        ms = p0.elapsed_time(p1) / reps
-        nbytes = 1024 * (262144.0 + 1048576.0)
+            evs[2].record()
+            torch.cuda.synchronize()
+            ms_s += evs[0].elapsed_time(evs[1]) / reps
+            ms_w += evs[1].elapsed_time(evs[2]) / reps
+        nbytes = 1024 * (2 * 262144.0 + 1048576.0)
         pk = load_peaks()
-        post_roof = {"kernel": "mask_post_write@P=1024 (all-survive, 1.34 GB / launch > L2)", "bound": "hbm",
-                     "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": nbytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": traffic.get("mask_post_write_p1024"),
-                     "avg_launch_ms": ms, "peak_source": pk["source"]}
+        ach = nbytes / ((ms_s + ms_w) * 1e-3) / 1e9
+        post_roof = {"kernel": "mask_post stats+write @P=1024 (all-survive, instance-like logits, 1.6 GB / pass pair > L2)",
+                     "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                     "traffic": traffic.get("mask_post_p1024"), "avg_launch_ms": ms_s + ms_w, "stats_ms": ms_s,
+                     "write_ms": ms_w, "bytes_per_prompt": 1572864, "frac_survey_bytes": ach / pk["hbm_gbs"] * 2097216 / 1572864,
+                     "write_only_frac": 1024 * (262144.0 + 1048576.0) / (ms_w * 1e-3) / 1e9 / pk["hbm_gbs"],
+                     "peak_source": pk["source"]}
         del low, sel, mk
         torch.cuda.empty_cache()
 
@@ -340,7 +380,10 @@ def main():
             sum(len(r["counts"]) for r in res["rles"])
     e1.record()
     barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3 * 0.0)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    # host work after the last kernel (RLE string of the last image) is part of the call a user makes: the step ends
+    # when generate() returns, so the larger of the device-side and the host-side span is the end-to-end time
+    e2e_ms = max(e0.elapsed_time(e1), wall_ms)
     t = torch.tensor([e2e_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -374,9 +417,10 @@ def main():
     split_mode = os.environ.get("CSAM_PRECISION", "x3") != "x1"
     for r in roofs:
         if r["bound"] == "tensor":
-            # achieved counts ALGORITHMIC flops (2MNK); in the hi/lo split mode the tensor cores execute 3 MMAs
-            # per algorithmic one, so the pipe is 3x busier than `frac` says
-            r["mma_multiplier"] = 3 if split_mode else 1
+            # achieved counts ALGORITHMIC flops; in the hi/lo split mode the tensor cores execute 3 MMAs per
+            # algorithmic GEMM MMA (hi*hi + lo*hi + hi*lo) and 2.5 per attention MMA (QK^T x3, P*V x2: the
+            # probabilities are a single fp16), so the pipe is that much busier than `frac` says
+            r["mma_multiplier"] = (2.5 if r["kernel"] == "vit_attention" else 3) if split_mode else 1
             r["frac_executed"] = r["frac"] * r["mma_multiplier"]
         t = traffic.get(r["kernel"])
         if t:
@@ -387,23 +431,25 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        torch.set_num_threads(os.cpu_count() or 1)
-        secs, desc = cpu_sample_seconds(sam_sd, dino_sd, 0)
-        cpu = {"value": 1.0 / secs, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": desc}
+        gen, kind, what = make_cpu_model()
+        secs, _ = time_cpu_images(gen, args.warmup, 1, 0.0)
+        cpu = {"value": 1.0 / secs[0], "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+               "sample": f"{what}; ONE whole image of this workload end to end, un-extrapolated ({secs[0]:.1f} s), "
+                         f"{CPU_POINTS_PER_BATCH} prompts per decoder batch"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16x3(fp32-accurate hi/lo split), fp32 accumulate" if os.environ.get("CSAM_PRECISION", "x3") != "x1" else "f16, fp32 accumulate",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "arch": arch, "dino": DINO, "grid": GRID, "prompts": GRID * GRID,
-                       "points_per_batch": args.points_per_batch, "masks_into_nms": nk[0], "detections": nk[1],
-                       "l2": "working set (weights 2.5 GB + per-batch activations > 10 GB) far exceeds the 126 MB L2",
-                       "parallelism": f"images sharded one per rank x{world}, all-gather of detections"},
+            "config": bench_config(arch, world),
+            "run": {"points_per_batch": args.points_per_batch, "masks_into_nms": nk[0], "detections": nk[1]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(imgs_np[0].nbytes),
                     "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": dominant, "rooflines": roofs,
+            "gpu_launches": int(launches), "graph_captures": int(graphs.captures), "clocks": clocks, "roofline": dominant, "rooflines": roofs,
             "kernel_ms_per_step": {k: v["total_ms"] / args.steps for k, v in prof.items()},
             "profiled_pass_ms_per_step": prof_ms_total / args.steps,
+            "step_minus_profiled_kernels_ms": ms_total / args.steps - sum(v["total_ms"] for k, v in prof.items()
+                                                                  if k not in ("gemm_tensor", "gemm_hbm")) / args.steps,
             "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
