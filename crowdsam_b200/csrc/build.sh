@@ -7,7 +7,7 @@ mkdir -p "$OUT"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr"
 pids=()
-for f in abi gemm elementwise attention_simt attention_tc decoder_fused post nms cc; do
+for f in abi gemm gemm_pair elementwise attention_simt attention_tc decoder_fused post nms cc; do
   $NVCC $FLAGS "$@" -c "$HERE/$f.cu" -o "$OUT/$f.o" &
   pids+=($!)
 done

@@ -21,26 +21,10 @@
 //
 // Replaces the nn.Linear / conv call sites listed in include/csam.h (K-GEMM).
 #include "common.cuh"
+#include "gemm_shared.cuh"
 #include <mutex>
 
 namespace csam {
-
-struct GemmEpi {
-  int M, N;
-  const float* bias; const float* row_scale; const float* col_scale; int act;
-  const float* residual; int ldr; int res_mod;
-  const int* row_map;
-  float* out_f32; int ldo;
-  __half* out_hi; __half* out_lo; int ldh;
-  int vec_ok;   // all strides / bases allow 16-byte vector access
-  int direct;   // N % 16 == 0 and all strides / bases allow 32-byte row-per-lane access
-  int l2_prefetch;   // resident-weight mode: tiles of look-ahead for the A operand's L2 prefetch (0 = off)
-  // fused epilogues
-  const float* gamma; const float* beta; float eps;
-  const float* pe; int ldpe; int pe_mod; __half* out2_hi; __half* out2_lo;
-  const float* hyper; float* masks;
-  const __half* res_hi; const __half* res_lo; int ldrh;   // EPI_LN: residual given as an h16 pair
-};
 
 enum { EPI_STD = 0, EPI_LN = 1, EPI_UP1 = 2, EPI_UP2 = 3 };
 
@@ -907,6 +891,11 @@ extern "C" int csam_gemm(const csam_gemm_args* a, void* stream) {
     return split ? launch_tc<128, 3, true>(a, e, st) : launch_tc<128, 1, true>(a, e, st);
   }
   if (small_n) return split ? launch_tc<64, 3, false>(a, e, st) : launch_tc<64, 1, false>(a, e, st);
+  if (!wres_ok(128)) {
+    // big encoder / DINOv2 shapes: 256 x 256 tiles on CTA pairs (half the L2->SM fill per MMA cycle), gemm_pair.cu
+    const int rc = launch_gemm_pair(a, e, st);
+    if (rc >= 0) return rc;
+  }
   if (wres_ok(128))
     return split ? launch_tc<128, 3, false, EPI_STD, true>(a, e, st) : launch_tc<128, 1, false, EPI_STD, true>(a, e, st);
   return split ? launch_tc<128, 3, false>(a, e, st) : launch_tc<128, 1, false>(a, e, st);

@@ -108,6 +108,40 @@ def test_gemm_epilogue(impl):
 
 
 @pytest.mark.skipif(0 not in IMPLS, reason="tcgen05 only")
+@pytest.mark.parametrize("M,N,K", [(4096, 1024, 1024), (4900, 3072, 1024), (5330, 1024, 4096), (5330, 4096, 1024), (700, 2048, 256)])
+def test_gemm_pair_tiles_encoder_shapes(M, N, K):
+    """The 2-CTA (cta_group::2) 256x256 pair-tile kernel on the encoder / DINOv2 shapes, incl. ragged M (last pair tile
+    partly or wholly beyond M for one CTA of the pair), with the epilogue options the encoders use: bias + GELU +
+    LayerScale + in-place fp32 residual through a row scatter map, and fp32 + h16-pair outputs.  fp64 reference."""
+    o = ops()
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    bias, ls = torch.randn(N, generator=g), 1.0 + 0.1 * torch.randn(N, generator=g)
+    ah, wh = _h16(a, True), _h16(w, True)
+    acc = ah.float().cpu().double() @ wh.float().cpu().double().T
+    # (1) plain: bias, fp32 + h16 outputs
+    out, outh = o.gemm(ah, wh, bias=bias.to(DEV), want_f32=True, want_h16=True, impl=0)
+    ref = acc + bias.double()
+    assert _rel(out, ref) < 2e-5 and _rel(outh.float(), ref) < 3e-5, (_rel(out, ref), _rel(outh.float(), ref))
+    # (2) GELU + LayerScale + residual added in place, rows scattered through a map with holes (window un-partition)
+    n_out = M + 37
+    perm = torch.randperm(n_out, generator=g)[:M].to(torch.int32)
+    perm[::11] = -1                                        # padded window rows: dropped
+    x0 = torch.randn(n_out, N, generator=g)
+    x = x0.clone().to(DEV)
+    o.gemm(ah, wh, bias=bias.to(DEV), act=o.ACT_GELU, col_scale=ls.to(DEV), residual=x, out_f32=x, row_map=perm.to(DEV), impl=0)
+    want = x0.double().clone()
+    val = torch.nn.functional.gelu(acc + bias.double()) * ls.double()
+    keep = perm >= 0
+    want[perm[keep].long()] += val[keep]
+    assert _rel(x, want) < 2e-5, _rel(x, want)
+    # (3) agrees with the single-CTA kernel's arithmetic to accumulation order (same operands, same 3-MMA scheme)
+    out1, _ = o.gemm(ah, wh, bias=bias.to(DEV), want_f32=True, impl=1)
+    assert _rel(out, out1) < 2e-5
+
+
+@pytest.mark.skipif(0 not in IMPLS, reason="tcgen05 only")
 @pytest.mark.parametrize("split", [False, True])
 def test_gemm_b_mn_major(split):
     """W given as [K,N] row-major (MN-major UMMA operand) — the layout the attention PV product uses."""
