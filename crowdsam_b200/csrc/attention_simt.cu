@@ -325,6 +325,66 @@ __global__ void __launch_bounds__(256) relpos_rows_kernel(const __half* __restri
   }
 }
 
+
+// Global blocks (S = 64, head dim 64): one block per (query row qh, head), one thread per (query, quarter of the 128
+// outputs) with its q row in REGISTERS and the table rows read as broadcast / conflict-free float4: the generic
+// kernel above does two scalar shared loads per FMA (1.07 G loads per layer: 190 us, shared-memory bound); here it is
+// one 16-byte load per 4 FMAs.
+__global__ void __launch_bounds__(256) relpos_rows64_kernel(const __half* __restrict__ qhi, const __half* __restrict__ qlo,
+                                                            int ld, int tokens, int heads,
+                                                            const float* __restrict__ rel_h, const float* __restrict__ rel_w,
+                                                            float* __restrict__ out) {
+  constexpr int S = 64, HD = 64, LDT = HD + 4;
+  extern __shared__ __align__(16) float sm64[];
+  float* th = sm64;                     // [64][LDT]   row kh = rel_h[qh - kh + 63]
+  float* tw = th + S * LDT;             // [127][LDT]
+  const int qh = blockIdx.x, h = blockIdx.y, g = blockIdx.z, t = threadIdx.x;
+  for (int i = t; i < S * (HD / 4); i += 256) {
+    const int r = i >> 4, d4 = (i & 15) * 4;
+    *reinterpret_cast<float4*>(th + r * LDT + d4) = *reinterpret_cast<const float4*>(rel_h + (size_t)(qh - r + S - 1) * HD + d4);
+  }
+  for (int i = t; i < (2 * S - 1) * (HD / 4); i += 256) {
+    const int r = i >> 4, d4 = (i & 15) * 4;
+    *reinterpret_cast<float4*>(tw + r * LDT + d4) = *reinterpret_cast<const float4*>(rel_w + (size_t)r * HD + d4);
+  }
+  const int qw = t & 63, part = t >> 6;
+  float q[HD];
+  const size_t qo = ((size_t)g * tokens + (size_t)qh * S + qw) * ld + (size_t)h * HD;
+#pragma unroll
+  for (int d = 0; d < HD; d += 8) {
+    const uint4 a = *reinterpret_cast<const uint4*>(qhi + qo + d);
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(ah[k]); q[d + 2 * k] = f.x; q[d + 2 * k + 1] = f.y; }
+    if (qlo) {
+      const uint4 b = *reinterpret_cast<const uint4*>(qlo + qo + d);
+      const __half2* bl = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(bl[k]); q[d + 2 * k] += f.x; q[d + 2 * k + 1] += f.y; }
+    }
+  }
+  __syncthreads();
+  float* o = out + (((size_t)g * heads + h) * tokens + (size_t)qh * S + qw) * 2 * S + part * 32;
+#pragma unroll 1
+  for (int j0 = 0; j0 < 32; j0 += 4) {
+    float acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = (part & 1) * 32 + j0 + u;                       // kh (parts 0, 1) or kw (parts 2, 3)
+      const float* row = (part < 2) ? th + j * LDT : tw + (qw - j + S - 1) * LDT;
+      float a0 = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; d += 4) {
+        const float4 r4 = *reinterpret_cast<const float4*>(row + d);
+        a0 = fmaf(q[d], r4.x, a0); a0 = fmaf(q[d + 1], r4.y, a0);
+        a0 = fmaf(q[d + 2], r4.z, a0); a0 = fmaf(q[d + 3], r4.w, a0);
+      }
+      acc[u] = a0;
+    }
+    *reinterpret_cast<float4*>(o + j0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+
 // Window blocks (S = 14): one block per (group, head), one thread per query with its q row in registers and both
 // tables in shared memory.  The row-per-block kernel above launches 5600 blocks of 392 outputs for 25 windows x 16
 // heads (78 us per layer, as long as the window attention itself); this one is a 400-block launch.
@@ -390,6 +450,15 @@ int compute_relpos(const csam_attn_args* a, cudaStream_t st) {
         static_cast<const __half*>(a->qkv_hi), static_cast<const __half*>(a->qkv_lo), a->ld_qkv, a->heads, a->rel_h,
         a->rel_w, a->scratch);
     return check_launch("relpos_win14_kernel");
+  }
+  if (a->S == 64 && a->hd == 64 && a->tokens == 4096 && (a->ld_qkv & 7) == 0 && a->groups <= 65535 &&
+      !(getenv("CSAM_RELPOS_ROWS64") && atoi(getenv("CSAM_RELPOS_ROWS64")) == 0)) {
+    constexpr int SM64 = (64 + 127) * 68 * 4;
+    CSAM_DYN_SMEM(relpos_rows64_kernel, SM64, "relpos_rows64_kernel");
+    relpos_rows64_kernel<<<dim3(64, a->heads, a->groups), 256, SM64, st>>>(
+        static_cast<const __half*>(a->qkv_hi), static_cast<const __half*>(a->qkv_lo), a->ld_qkv, a->tokens, a->heads,
+        a->rel_h, a->rel_w, a->scratch);
+    return check_launch("relpos_rows64_kernel");
   }
   const size_t smem = (size_t)(4 * a->S - 1) * (a->hd + 1) * sizeof(float);
   CSAM_REQUIRE(smem <= 100 * 1024 && a->groups <= 65535, "csam_vit_attention: rel-pos table too large");

@@ -702,8 +702,11 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
       // ---- end of prompt: column sums over all keys, then XBAR = accumulator / l
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
+        // per-warp partial sums, added in a FIXED order below: a shared-memory atomicAdd here made the denominators
+        // (and with them every score downstream) depend on the arrival order of the four warps, i.e. differ in the
+        // last bit from run to run.  st_wmax is free here: its readers passed the last barrier of the final tile.
         const float v = warp_sum(lsum[c]);
-        if (lane == 0) atomicAdd(&st_l[ch * 32 + c], v);
+        if (lane == 0) st_wmax[wq * 64 + ch * 32 + c] = v;
       }
       mbar_wait(&bars->pv_done, (tl - 1) & 1);
       tc_fence_after();
@@ -717,7 +720,8 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const int col = hh * 32 + c;
-          xo[(size_t)col * 256 + ch * 128 + r] = __uint_as_float(o[c]) / st_l[col];
+          const float l = ((st_wmax[col] + st_wmax[64 + col]) + st_wmax[128 + col]) + st_wmax[192 + col];
+          xo[(size_t)col * 256 + ch * 128 + r] = __uint_as_float(o[c]) / l;
         }
       }
       tc_fence_before();

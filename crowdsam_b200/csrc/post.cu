@@ -31,7 +31,10 @@ __device__ __forceinline__ float stage1(const float* __restrict__ L, int y, int 
 __device__ __forceinline__ float eval_logit(const float* __restrict__ L, const PostGeom& g, int Y, int X) {
   if (g.identity) return stage1(L, Y, X);
   // stage 2: crop to (in_h,in_w) then bilinear to (out_h,out_w)
-  float sy = fmaxf(g.s2h * (Y + 0.5f) - 0.5f, 0.f), sx = fmaxf(g.s2w * (X + 0.5f) - 0.5f, 0.f);
+  // source index as ATen computes it on the CPU (area_pixel_compute_source_index: scale * (dst + 0.5) - 0.5 with a
+  // ROUNDED product): an FMA contraction here moves the source coordinate by an ulp of ~600, i.e. the interpolation
+  // weight by ~6e-5, enough to flip pixels next to a threshold
+  float sy = fmaxf(__fsub_rn(__fmul_rn(g.s2h, Y + 0.5f), 0.5f), 0.f), sx = fmaxf(__fsub_rn(__fmul_rn(g.s2w, X + 0.5f), 0.5f), 0.f);
   const int y0 = min((int)sy, g.in_h - 1), x0 = min((int)sx, g.in_w - 1);
   const int y1 = y0 + (y0 < g.in_h - 1 ? 1 : 0), x1 = x0 + (x0 < g.in_w - 1 ? 1 : 0);
   const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;

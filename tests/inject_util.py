@@ -62,15 +62,17 @@ def inject_predictor(pred, seed: int, log=None):
     return pred
 
 
-def compare_result(res, g, exact_rle=True, prefix=""):
+def compare_result(res, g, exact_rle=True, prefix="", float_rtol=0.0):
     """res: mapping with boxes / points / categories / scores / stability_score / rles (COCO dicts)."""
     gb = g[prefix + "boxes"]
     assert len(res["boxes"]) == len(gb), (len(res["boxes"]), len(gb))
     np.testing.assert_array_equal(np.asarray(res["boxes"]), gb)
     np.testing.assert_array_equal(np.asarray(res["points"]), g[prefix + "points"])
     np.testing.assert_array_equal(np.asarray(res["categories"]), g[prefix + "categories"])
-    np.testing.assert_array_equal(np.asarray(res["scores"]), g[prefix + "scores"])
-    np.testing.assert_array_equal(np.asarray(res["stability_score"]), g[prefix + "stability_score"])
+    # floating point: the PWD score clamp(iou) * sigmoid(cls) goes through the device's expf (1 ulp from ATen's CPU
+    # sigmoid); the stability ratio is a quotient of integer counts.  north_star bar is 1e-3; observed <= 2.2e-7.
+    np.testing.assert_allclose(np.asarray(res["scores"]), g[prefix + "scores"], rtol=float_rtol, atol=0)
+    np.testing.assert_allclose(np.asarray(res["stability_score"]), g[prefix + "stability_score"], rtol=float_rtol, atol=0)
     ref = [str(s) for s in g[prefix + "rle_counts"]]
     got = [r["counts"] for r in res["rles"]]
     if exact_rle:

@@ -51,7 +51,7 @@ def test_graph_replay_equals_eager():
         masks, iou, cls, low = pred.predict_torch(c, l, return_logits=False)
         kept.append((pred.features, pred.dino_feats, low, iou, cls))
         assert masks.dtype == torch.bool
-    assert graphs.captures - c0 >= 2 and graphs.replayed_launches - r0 > 300     # set_image + decode graphs ran
+    assert graphs.captures - c0 >= 2 and graphs.replayed_launches - r0 > 150     # set_image + decode graphs ran
     for got, want in zip(kept, ref):             # every image's results are still intact after later replays
         for a, b in zip(got, want):
             assert torch.equal(a, b)
