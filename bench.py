@@ -276,6 +276,21 @@ def main():
             parallel.gather_detections(dets, device=dev)
 
     # ---------------- device-resident leg (value) ----------------
+    # One-time setup outside the W warm-up steps: the CUDA graphs of set_image / decode are captured on the second /
+    # third call with a given shape, and torch.cuda.graph() empties the allocator cache on entry, so the first step
+    # after a capture pays cudaMalloc for ~2 GB of result buffers.  Prime until no further capture happens.
+    def prime(fn):
+        n = 0
+        for _ in range(6):
+            c0 = graphs.captures
+            np.random.seed(42)
+            fn()
+            n += 1
+            if graphs.captures == c0 and n >= 2:
+                break
+        return n
+
+    priming = prime(lambda: model.run_resident(resident[0]))
     for i in range(args.warmup):
         np.random.seed(42)
         model.run_resident(resident[i])
@@ -365,6 +380,7 @@ def main():
         torch.cuda.empty_cache()
 
     # ---------------- end-to-end leg through the public API ----------------
+    priming += prime(lambda: model.generate(imgs_np[0]))
     for i in range(min(args.warmup, 3)):
         np.random.seed(42)
         model.generate(imgs_np[i])
@@ -445,7 +461,7 @@ def main():
             "run": {"points_per_batch": args.points_per_batch, "masks_into_nms": nk[0], "detections": nk[1]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(imgs_np[0].nbytes),
                     "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches), "graph_captures": int(graphs.captures), "clocks": clocks, "roofline": dominant, "rooflines": roofs,
+            "gpu_launches": int(launches), "graph_captures": int(graphs.captures), "setup_steps_before_warmup": int(priming), "clocks": clocks, "roofline": dominant, "rooflines": roofs,
             "kernel_ms_per_step": {k: v["total_ms"] / args.steps for k, v in prof.items()},
             "profiled_pass_ms_per_step": prof_ms_total / args.steps,
             "step_minus_profiled_kernels_ms": ms_total / args.steps - sum(v["total_ms"] for k, v in prof.items()

@@ -8,7 +8,7 @@ from crowdsam_b200.build import _build_sam
 from crowdsam_b200.modules import DinoVisionTransformer
 from crowdsam_b200.pipeline import CrowdSAM
 from crowdsam_b200.predictor import SamPredictor
-from oracle import weights, fixtures
+from crowdsam_b200 import synthetic as weights
 import bench
 
 n_steps = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 2
@@ -24,7 +24,7 @@ model = CrowdSAM(cfg, None, predictor=pred)
 imgs = [torch.as_tensor(weights.synthetic_image(i)).permute(2, 0, 1).contiguous().to(dev) for i in range(n_steps)]
 if "--stats" in sys.argv:
     pred.set_torch_image(imgs[0][None], (1024, 1024))
-    pts = fixtures.grid_points(32)[::4]
+    pts = weights.grid_points(32)[::4]
     coords = torch.as_tensor(pred.transform.apply_coords(pts, (1024, 1024)))[:, None, :]
     labels = torch.ones(len(pts), dtype=torch.int)[:, None]
     low, iou, cls = pred.decode_low_res(coords, labels)
