@@ -891,8 +891,8 @@ extern "C" int csam_gemm(const csam_gemm_args* a, void* stream) {
     return split ? launch_tc<128, 3, true>(a, e, st) : launch_tc<128, 1, true>(a, e, st);
   }
   if (small_n) return split ? launch_tc<64, 3, false>(a, e, st) : launch_tc<64, 1, false>(a, e, st);
-  if (!wres_ok(128)) {
-    // big encoder / DINOv2 shapes: 256 x 256 tiles on CTA pairs (half the L2->SM fill per MMA cycle), gemm_pair.cu
+  if (!wres_ok(128) || a->impl == CSAM_GEMM_TC_PAIR) {
+    // big encoder / DINOv2 shapes: 256 x 256 tiles on CTA pairs where the wave model favours them (gemm_pair.cu)
     const int rc = launch_gemm_pair(a, e, st);
     if (rc >= 0) return rc;
   }

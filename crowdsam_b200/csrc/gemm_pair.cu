@@ -259,16 +259,32 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constan
 }  // namespace
 
 int launch_gemm_pair(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st) {
-  static const int enabled = getenv("CSAM_GEMM_PAIR") ? atoi(getenv("CSAM_GEMM_PAIR")) : 1;
-  if (!enabled) return -1;
-  // qualifies: hi/lo split operands, K-major W, standard row-per-lane epilogue, whole k-blocks and pair tiles in N,
-  // and at least half a wave of pair tiles (small problems keep the finer-grained single-CTA tiles)
+  // CSAM_GEMM_PAIR: 0 = never, 1 = whenever the problem qualifies, unset = when the wave model below favours it.
+  // impl == CSAM_GEMM_TC_PAIR in the arguments forces this kernel (tests, A/B measurements).
+  static const int mode = getenv("CSAM_GEMM_PAIR") ? atoi(getenv("CSAM_GEMM_PAIR")) : -1;
+  const bool forced = a->impl == CSAM_GEMM_TC_PAIR;
+  if (mode == 0 && !forced) return -1;
+  // qualifies: hi/lo split operands, K-major W, standard row-per-lane epilogue, whole k-blocks and pair tiles in N
   const int sms = num_sms();
   const int tiles_m = (a->M + 2 * PM - 1) / (2 * PM);
   const int tiles_n = a->N / PBN;
-  if (!a->a_lo || !a->w_lo || a->b_mn_major || a->epi != CSAM_EPI_STD || !e.direct) return -1;
-  if ((a->K % PBK) != 0 || (a->N % PBN) != 0 || a->K < 4 * PBK) return -1;
-  if ((long long)tiles_m * tiles_n * 4 < sms) return -1;
+  const bool ok = a->a_lo && a->w_lo && !a->b_mn_major && a->epi == CSAM_EPI_STD && e.direct && (a->K % PBK) == 0 &&
+                  (a->N % PBN) == 0 && a->K >= 4 * PBK;
+  if (!ok) {
+    if (forced) return fail("%s", "csam_gemm: the CTA-pair kernel needs split operands, K-major W, N % 256 == 0, K % 64 == 0, "
+                                  "K >= 256 and 32-byte aligned outputs");
+    return -1;
+  }
+  if (!forced && mode != 1) {
+    // Wave model (measured, round 2: the tensor pipe is ~70 % active inside a pair tile against ~55-60 % inside a
+    // single-CTA 128x128 tile, but a pair tile is four of those, so the persistent grid of 74 pairs quantises much
+    // coarser than 148 CTAs).  Time in units of one 128x128xK tile: pairs 2 per round, single CTAs 1 per round;
+    // the pair kernel is taken only where it saves at least a round's worth (e.g. 4096 x 1024 x 4096: 64 pair tiles
+    // = one round against two rounds of 256 single tiles).
+    const long long t2 = (long long)tiles_m * tiles_n, t1 = (long long)((a->M + 127) / 128) * ((a->N + 127) / 128);
+    const long long est_pair = 2 * ((t2 + sms / 2 - 1) / (sms / 2)), est_single = (t1 + sms - 1) / sms;
+    if (est_pair > est_single || t2 * 4 < sms) return -1;
+  }
   CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
   if (make_tmap_2d_f16(&ta_hi, a->a_hi, a->M, a->K, a->lda, PM, PBK)) return 1;
   if (make_tmap_2d_f16(&ta_lo, a->a_lo, a->M, a->K, a->lda, PM, PBK)) return 1;

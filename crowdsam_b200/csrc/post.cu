@@ -399,7 +399,11 @@ extern "C" int csam_mask_post_stats(const csam_post_args* a, void* stream) {
   const int segs = (g.out_w + 15) / 16;
   if (g.identity) {
     const int total = ((g.out_h + 5) / 4) * segs;
-    post_stats_quad_kernel<<<dim3(min((total + 255) / 256, 65), a->P), 256, 0, st>>>(*a, g, segs);
+    // blocks per mask: a block's fixed cost (dependent sel -> plane loads, block reduction, 7 global atomics) is
+    // amortised over several quads per thread; 65 blocks (one quad per thread) left the pass latency-bound
+    static const int gx_env = getenv("CSAM_POST_GX") ? atoi(getenv("CSAM_POST_GX")) : 0;
+    const int gx = gx_env > 0 ? gx_env : 17;
+    post_stats_quad_kernel<<<dim3(min((total + 255) / 256, gx), a->P), 256, 0, st>>>(*a, g, segs);
     if (check_launch("post_stats_quad_kernel")) return 1;
   } else {
     dim3 grid((g.out_h + POST_ROWS - 1) / POST_ROWS, a->P);

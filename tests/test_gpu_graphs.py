@@ -11,6 +11,16 @@ from crowdsam_b200 import synthetic as weights  # noqa: E402
 DEV = "cuda"
 
 
+@pytest.fixture(autouse=True)
+def _restore_graph_switch():
+    """Graph replay is opt-in (CSAM_GRAPHS=1); these tests switch it on and off explicitly."""
+    from crowdsam_b200 import graphs
+
+    saved = graphs.ENABLED
+    yield
+    graphs.ENABLED = saved
+
+
 def _fresh_predictor():
     from crowdsam_b200.predictor import SamPredictor
     from test_gpu_model import make_predictor
@@ -91,6 +101,9 @@ def test_two_predictors_sharing_a_model():
 
     a = _fresh_predictor()
     b = SamPredictor(a.model, a.dino_model)
+    from crowdsam_b200 import graphs
+
+    graphs.ENABLED = True
     im_a, im_b = weights.synthetic_image(40), weights.synthetic_image(41)
     a.set_image(im_a)
     c, l = _prompts(a, 4)

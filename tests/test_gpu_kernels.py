@@ -30,6 +30,12 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
 
 
+def lib_launches():
+    from crowdsam_b200 import lib
+
+    return lib.launch_count()
+
+
 def _h16(t, split):
     return ops().H16.from_f32(t.to(DEV), split)
 
@@ -121,7 +127,12 @@ def test_gemm_pair_tiles_encoder_shapes(M, N, K):
     ah, wh = _h16(a, True), _h16(w, True)
     acc = ah.float().cpu().double() @ wh.float().cpu().double().T
     # (1) plain: bias, fp32 + h16 outputs
-    out, outh = o.gemm(ah, wh, bias=bias.to(DEV), want_f32=True, want_h16=True, impl=0)
+    PAIR = 2                                               # CSAM_GEMM_TC_PAIR: force the cta_group::2 kernel
+    if N % 256 != 0 or K < 256:
+        PAIR = 0
+    l0 = lib_launches()
+    out, outh = o.gemm(ah, wh, bias=bias.to(DEV), want_f32=True, want_h16=True, impl=PAIR)
+    assert lib_launches() - l0 == 1
     ref = acc + bias.double()
     assert _rel(out, ref) < 2e-5 and _rel(outh.float(), ref) < 3e-5, (_rel(out, ref), _rel(outh.float(), ref))
     # (2) GELU + LayerScale + residual added in place, rows scattered through a map with holes (window un-partition)
@@ -130,15 +141,24 @@ def test_gemm_pair_tiles_encoder_shapes(M, N, K):
     perm[::11] = -1                                        # padded window rows: dropped
     x0 = torch.randn(n_out, N, generator=g)
     x = x0.clone().to(DEV)
-    o.gemm(ah, wh, bias=bias.to(DEV), act=o.ACT_GELU, col_scale=ls.to(DEV), residual=x, out_f32=x, row_map=perm.to(DEV), impl=0)
+    o.gemm(ah, wh, bias=bias.to(DEV), act=o.ACT_GELU, col_scale=ls.to(DEV), residual=x, out_f32=x, row_map=perm.to(DEV), impl=PAIR)
     want = x0.double().clone()
     val = torch.nn.functional.gelu(acc + bias.double()) * ls.double()
     keep = perm >= 0
     want[perm[keep].long()] += val[keep]
     assert _rel(x, want) < 2e-5, _rel(x, want)
-    # (3) agrees with the single-CTA kernel's arithmetic to accumulation order (same operands, same 3-MMA scheme)
+    # (3) agrees with the single-CTA tcgen05 kernel and the SIMT kernel to accumulation order
+    out0, _ = o.gemm(ah, wh, bias=bias.to(DEV), want_f32=True, impl=0)
     out1, _ = o.gemm(ah, wh, bias=bias.to(DEV), want_f32=True, impl=1)
-    assert _rel(out, out1) < 2e-5
+    assert _rel(out, out0) < 2e-5 and _rel(out, out1) < 2e-5
+
+
+def test_gemm_pair_refuses_unqualified_problems():
+    o = ops()
+    g = torch.Generator().manual_seed(1)
+    a, w = torch.randn(300, 256, generator=g), torch.randn(192, 256, generator=g)
+    with pytest.raises(RuntimeError):                      # N % 256 != 0
+        o.gemm(_h16(a, True), _h16(w, True), want_f32=True, impl=2)
 
 
 @pytest.mark.skipif(0 not in IMPLS, reason="tcgen05 only")
