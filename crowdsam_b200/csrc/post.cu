@@ -400,9 +400,9 @@ extern "C" int csam_mask_post_stats(const csam_post_args* a, void* stream) {
   if (g.identity) {
     const int total = ((g.out_h + 5) / 4) * segs;
     // blocks per mask: a block's fixed cost (dependent sel -> plane loads, block reduction, 7 global atomics) is
-    // amortised over several quads per thread; 65 blocks (one quad per thread) left the pass latency-bound
+    // amortised over several quads per thread; 65 blocks (one quad per thread) left the pass latency-bound (0.32 ms at P = 1024 on instance masks; 9 blocks: 0.21 ms)
     static const int gx_env = getenv("CSAM_POST_GX") ? atoi(getenv("CSAM_POST_GX")) : 0;
-    const int gx = gx_env > 0 ? gx_env : 17;
+    const int gx = gx_env > 0 ? gx_env : 9;
     post_stats_quad_kernel<<<dim3(min((total + 255) / 256, gx), a->P), 256, 0, st>>>(*a, g, segs);
     if (check_launch("post_stats_quad_kernel")) return 1;
   } else {

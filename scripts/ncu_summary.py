@@ -8,7 +8,8 @@ WANT = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "lts__t_bytes.sum", "sm__cycles_elapsed.max"]
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "lts__t_bytes.sum", "lts__t_sectors_op_read.sum",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__cycles_active.avg", "sm__cycles_elapsed.max"]
 
 w = csv.writer(sys.stdout)
 first = True
