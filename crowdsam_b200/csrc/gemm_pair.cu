@@ -282,8 +282,11 @@ int launch_gemm_pair(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st)
     // the pair kernel is taken only where it saves at least a round's worth (e.g. 4096 x 1024 x 4096: 64 pair tiles
     // = one round against two rounds of 256 single tiles).
     const long long t2 = (long long)tiles_m * tiles_n, t1 = (long long)((a->M + 127) / 128) * ((a->N + 127) / 128);
-    const long long est_pair = 2 * ((t2 + sms / 2 - 1) / (sms / 2)), est_single = (t1 + sms - 1) / sms;
-    if (est_pair > est_single || t2 * 4 < sms) return -1;
+    const long long rounds_pair = (t2 + sms / 2 - 1) / (sms / 2);
+    const long long est_pair = 2 * rounds_pair, est_single = (t1 + sms - 1) / sms;
+    // ties: measured 5330 x 4096 x 1024 (5 pair rounds against 10 single rounds) 365 against 372 TFLOP/s for the
+    // single-CTA kernel, 4096 x 1024 x 4096 (1 against 2) 377 against 357 for the pairs
+    if (est_pair > est_single || (est_pair == est_single && rounds_pair > 1) || t2 * 4 < sms) return -1;
   }
   CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
   if (make_tmap_2d_f16(&ta_hi, a->a_hi, a->M, a->K, a->lda, PM, PBK)) return 1;
