@@ -63,6 +63,11 @@ class CrowdSAM:
                   "box_nms_thresh", "points_per_batch", "crop_n_layers", "crop_nms_thresh", "crop_overlap_ratio",
                   "min_mask_region_area", "pos_sim_thresh", "output_rles"):
             setattr(self, k, t[k])
+        # extension: `test.nms_mode: "mask_iou"` replaces the per-crop box NMS by the reference's
+        # mask-overlap NMS (crowdsam/utils.py:422-459, dead code upstream) on K-MIOU; default "box" = the reference path
+        self.nms_mode = t.get("nms_mode", "box")
+        if self.nms_mode not in ("box", "mask_iou"):
+            raise NotImplementedError(f"unknown test.nms_mode {self.nms_mode!r}")
         if config["model"].get("trainfree"):
             raise NotImplementedError("trainfree mode is outside the B200 hot path")
         if self.fuse_simmap or self.apply_box_offsets:
@@ -183,7 +188,13 @@ class CrowdSAM:
         if len(data.items()) == 0 or len(data["masks"]) == 0:
             return None
         n_into_nms = len(data["boxes"])
-        keep = ops.box_nms(data["boxes"].float(), data["iou_preds"], self.box_nms_thresh)       # model.py:257-263
+        if self.nms_mode == "mask_iou":
+            from .dropin.crowdsam.utils import mask_iou_nms
+
+            kept = mask_iou_nms(data["boxes"], data["iou_preds"].cpu().numpy(), data["masks"], self.box_nms_thresh)
+            keep = torch.as_tensor(np.asarray(kept, dtype=np.int64), device=data["boxes"].device)
+        else:
+            keep = ops.box_nms(data["boxes"].float(), data["iou_preds"], self.box_nms_thresh)   # model.py:257-263
         data.filter(keep)
         if self.min_mask_region_area > 0:
             data = self.postprocess_small_regions(data, self.min_mask_region_area,

@@ -525,7 +525,11 @@ def test_mask_post_vs_oracle_and_golden(tag, inp, orig, golden_dir):
     # a box may move only if a near-zero pixel sits on its border
     lo_b, hi_b = restate.mask_to_box(m > eps), restate.mask_to_box(m > -eps)
     ok = exact | (((boxes.cpu().long() - lo_b).abs() <= (hi_b - lo_b).abs()).all(1))
-    assert ok.all() and exact.float().mean() > 0.9
+    n_exact = int(exact.sum())
+    print(f"[mask_post {tag}] boxes identical to the reference: {n_exact}/{P}")
+    # the smooth Gaussian blobs of this fixture put near-zero pixels on many box borders (the band test above bounds those);
+    # with the identity second resize the kernel follows ATen's operation order, so every box must be identical
+    assert ok.all() and n_exact >= (P if tag != "ns" else int(0.9 * P)), n_exact
     keep = torch.arange(0, P, 3, dtype=torch.int32, device=DEV)
     masks, logits = o.mask_post_write(low.to(DEV), sel, keep, inp, orig, 0.0, want_masks=True, want_logits=True)
     mk = m[keep.cpu().long()]
@@ -536,7 +540,9 @@ def test_mask_post_vs_oracle_and_golden(tag, inp, orig, golden_dir):
         g = np.load(os.path.join(golden_dir, "stage_post_nms.npz"))
         np.testing.assert_array_equal(sel.cpu().numpy(), g[f"{tag}_sel"])
         np.testing.assert_allclose(stab.cpu().numpy(), g[f"{tag}_stability"], atol=1e-4, equal_nan=True)
-        assert (boxes.cpu().numpy() == g[f"{tag}_boxes"]).all(1).mean() > 0.9
+        n_gold = int((boxes.cpu().numpy() == g[f"{tag}_boxes"]).all(1).sum())
+        print(f"[mask_post {tag}] boxes identical to the reference golden: {n_gold}/{P}")
+        assert n_gold >= (P if tag != "ns" else int(0.9 * P)), n_gold
         np.testing.assert_allclose(score.cpu().numpy(), g[f"{tag}_score"], rtol=1e-5, atol=1e-6)
         kp = o.box_nms(torch.as_tensor(g[f"{tag}_boxes"]).float().to(DEV), torch.as_tensor(g[f"{tag}_score"]).to(DEV), 0.65)
         np.testing.assert_array_equal(kp.cpu().numpy(), g[f"{tag}_nms_keep"])

@@ -183,3 +183,23 @@ def test_automatic_mask_generator_vs_patched_reference(tag, extra, golden_dir):
     np.testing.assert_array_equal(np.array([r["crop_box"] for r in recs]), g[f"{tag}_crop_box"])
     assert [r["segmentation"]["counts"] for r in recs] == [str(x) for x in g[f"{tag}_rle"]]
     assert all(r["segmentation"]["size"] == [int(x) for x in g[f"{tag}_hw"]] for r in recs)
+
+
+def test_mask_iou_nms_as_selection_mode(golden_dir):
+    """Extension of SURVEY §8f-4: `test.nms_mode = "mask_iou"` selects instances with the reference's mask-overlap NMS
+    (crowdsam/utils.py:422-459) instead of box NMS.  Checked against the oracle restatement of that function applied to
+    the same pre-NMS masks (which the box-mode run with NMS disabled exposes)."""
+    g = np.load(os.path.join(golden_dir, "pipeline_inj_p64.npz"))
+    img = iu.golden_image(g)
+    # all masks that reach the NMS stage: box mode with a threshold nothing exceeds, small-region pass off
+    model = _model(g, box_nms_thresh=2.0, min_mask_region_area=0, filter_thresh=2.0, output_rles=True)
+    np.random.seed(42)
+    pre = dict(model.generate(img).items())
+    masks = np.stack([restate.coco_rle_decode(r["counts"], r["size"]) for r in pre["rles"]])
+    want = restate.mask_iou_nms(np.asarray(pre["scores"]), torch.as_tensor(masks), 0.5)
+    model2 = _model(g, nms_mode="mask_iou", box_nms_thresh=0.5, min_mask_region_area=0, filter_thresh=2.0)
+    np.random.seed(42)
+    got = dict(model2.generate(img).items())
+    assert 0 < len(want) < len(masks)
+    np.testing.assert_array_equal(np.asarray(got["boxes"]), np.asarray(pre["boxes"])[want])
+    np.testing.assert_array_equal(np.asarray(got["scores"]), np.asarray(pre["scores"])[want])
