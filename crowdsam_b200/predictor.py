@@ -32,7 +32,12 @@ class SamPredictor:
             image = image[..., ::-1]
         resized = self.transform.apply_image(np.ascontiguousarray(image))
         # interleaved HWC bytes go to the device as they are (one H2D copy); the patch-gather kernel reads HWC
-        hwc = torch.as_tensor(resized).to(self.device, non_blocking=True)
+        # blocking copy: `resized` may be a temporary (PIL / cv2 resize output) that is freed as soon as this method
+        # returns, and a caller may overwrite its own image buffer right after the call; an asynchronous copy from such
+        # memory is only safe through the driver's staging of pageable memory, which is not a contract worth relying on
+        # (under compute-sanitizer two otherwise bit-identical runs differed in the last digits).  The stream is idle
+        # here anyway: the previous image ended with a device-to-host read of its results.
+        hwc = torch.as_tensor(resized).to(self.device)
         mask_t = None
         if mask is not None:
             mask_t = torch.as_tensor(self.transform.apply_image(mask), device=self.device).permute(2, 0, 1).contiguous()[None]
