@@ -70,22 +70,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f with the 1.5 * 2^23 trick, degree-4 polynomial
-// of 2^f on [-0.5, 0.5] (max relative error 3.6e-6; the result is rounded to fp16 right after), 2^n by adding n to
-// the exponent field.  The softmax of the attention kernels is bound by MUFU.EX2 (16 per clock per SM: 64 keys x
-// 256 query rows = 1024 clocks per key tile against 1280 clocks of MMAs); evaluating every fourth exponential here moves
-// a quarter of that work into issue slots that are otherwise idle while the MUFU pipe is busy (the FlashAttention-4
-// trick).  x is clamped at -120 (masked keys arrive as -inf): 2^-120 rounds to 0 in fp16 and is negligible in the row sum.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -120.f);
-  const float t = x + 12582912.f;
-  const float f = x - (t - 12582912.f);
-  float p = fmaf(0.00966636836528778f, f, 0.055921975523233414f);
-  p = fmaf(p, f, 0.2402234971523285f);
-  p = fmaf(p, f, 0.6931210160255432f);
-  p = fmaf(p, f, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
 
 
 // The running maximum is allowed to lag the true row maximum by up to 2^AT_TAU (probabilities stay <= 256, well
@@ -423,7 +407,7 @@ struct AttnTsBars {
 template <int SPLIT, int BIAS, int NQ, int HD>
 __global__ void __launch_bounds__(128 + 128 * NQ, 1)
 vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_constant__ CUtensorMap t_lo,
-                        csam_attn_args a, const float* __restrict__ rel, int n_full, int n_single, int poly) {
+                        csam_attn_args a, const float* __restrict__ rel, int n_full, int n_single) {
   using Cfg = AttnTsCfg<SPLIT, BIAS, NQ, HD>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int TS = Cfg::TSTRIDE;
@@ -671,38 +655,23 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
         l *= alpha;
         m = m_new;
       }
-      float psum = 0.f, psum2 = 0.f;
+      // (Measured, round 2: evaluating every fourth exponential as a polynomial on the FMA pipe -- the FlashAttention-4
+      //  trick against the MUFU.EX2 limit -- made this kernel 5 % SLOWER, and so did nothing for it shortening the
+      //  dependency chains above: the key-tile period is the MMAs' 1280 clocks PLUS the 1024 clocks the two softmax
+      //  warpgroups need to read S back at the TMEM read rate of 64 B/clk, which do not overlap.)
+      float psum = 0.f;
       uint32_t ph[32];
-      if (poly) {
 #pragma unroll
-        for (int c = 0; c < 64; c += 4) {              // 3 of 4 exponentials on the MUFU pipe, 1 of 4 on the FMA pipe
-          float p0 = (BIAS == 0) ? fmaf(s[c], scale2, -m) : s[c] - m;
-          float p1 = (BIAS == 0) ? fmaf(s[c + 1], scale2, -m) : s[c + 1] - m;
-          float p2 = (BIAS == 0) ? fmaf(s[c + 2], scale2, -m) : s[c + 2] - m;
-          float p3 = (BIAS == 0) ? fmaf(s[c + 3], scale2, -m) : s[c + 3] - m;
-          p0 = ex2_approx(p0);
-          p1 = ex2_approx(p1);
-          p2 = ex2_approx(p2);
-          p3 = ex2_poly(p3);
-          psum += p0 + p1;
-          psum2 += p2 + p3;
-          const __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
-          ph[c >> 1] = *reinterpret_cast<const uint32_t*>(&h01);
-          ph[(c >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h23);
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 64; c += 2) {
-          float p0 = (BIAS == 0) ? fmaf(s[c], scale2, -m) : s[c] - m;
-          float p1 = (BIAS == 0) ? fmaf(s[c + 1], scale2, -m) : s[c + 1] - m;
-          p0 = ex2_approx(p0);
-          p1 = ex2_approx(p1);
-          psum += p0 + p1;
-          const __half2 h2 = __floats2half2_rn(p0, p1);
-          ph[c >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-        }
+      for (int c = 0; c < 64; c += 2) {
+        float p0 = (BIAS == 0) ? fmaf(s[c], scale2, -m) : s[c] - m;
+        float p1 = (BIAS == 0) ? fmaf(s[c + 1], scale2, -m) : s[c + 1] - m;
+        p0 = ex2_approx(p0);
+        p1 = ex2_approx(p1);
+        psum += p0 + p1;
+        const __half2 h2 = __floats2half2_rn(p0, p1);
+        ph[c >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
       }
-      l += psum + psum2;
+      l += psum;
       tmem_st32(lane_addr + b * AT_BN, ph);          // P(j) over the first half of S(j)
       tmem_st_wait();
       tc_fence_before();
@@ -759,9 +728,7 @@ static int launch_attn_ts(const csam_attn_args* a, const float* rel, cudaStream_
     if (tail_env && p > 0 && s1 > 0 && s1 * HG <= 148 && (n_full * HG) % 148 != 0) { n_full = p; n_single = s1; }
   }
   dim3 grid((n_full + n_single) * HG);
-  // CSAM_ATTN_POLY=0 keeps every exponential on MUFU.EX2 (A/B measurements); default: one in four on the FMA pipe
-  static const int poly = getenv("CSAM_ATTN_POLY") ? atoi(getenv("CSAM_ATTN_POLY")) : 1;
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(t_hi, t_lo, *a, rel, n_full, n_single > 0 ? n_single : 1, poly);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(t_hi, t_lo, *a, rel, n_full, n_single > 0 ? n_single : 1);
   return check_launch("vit_attention_ts_kernel");
 }
 
