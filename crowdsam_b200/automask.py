@@ -3,9 +3,13 @@
 The reference copy cannot be constructed as shipped (`SamPredictor(model)` lacks `dino_model`,
 automatic_mask_generator.py:123) nor unpack predict_torch's 4 returns (:279); patched at run time for those two
 lines it runs (tests/golden/make_golden.py amg_case), and this class matches it record for record
-(tests/test_gpu_pipeline_injected.py): 32x32 grid, 64 points per batch, all 4 masks per point (:287-291),
-pred_iou 0.88 / stability 0.95 / box NMS 0.7, small-region cleanup after the NMS (:158-164,326-372).
+(tests/test_gpu_pipeline_injected.py), single- and multi-crop: point grid per crop layer (:101-106), 64 points per
+batch, all 4 masks per point (:287-291), pred_iou 0.88 / stability 0.95 filters, crop-edge filter (:311-313),
+per-crop box NMS (:250-257), cross-crop NMS preferring smaller crops (:205-215), small-region cleanup after the
+NMS (:158-164,326-372).
 `dino_model` is optional: without it the PWD-Net class head, which AMG never reads, is skipped.
+Per-prompt work stays on the device: K-POST stats -> filters -> K-POST write of the survivors only -> K-NMS -> RLE
+kernel; what the reference keeps as RLE lists between stages are bool masks in HBM here.
 """
 from __future__ import annotations
 
@@ -18,36 +22,56 @@ from . import amg, ops
 from .predictor import SamPredictor
 
 
+def _near_crop_edge(boxes: torch.Tensor, crop_box, orig_box, atol: float = 20.0) -> torch.Tensor:
+    """amg.py:78-88 (the AMG variant: no downscale)."""
+    cb = torch.as_tensor(crop_box, dtype=torch.float, device=boxes.device)
+    ob = torch.as_tensor(orig_box, dtype=torch.float, device=boxes.device)
+    b = amg.uncrop_boxes_xyxy(boxes, crop_box).float()
+    near_c = torch.isclose(b, cb[None, :], atol=atol, rtol=0)
+    near_i = torch.isclose(b, ob[None, :], atol=atol, rtol=0)
+    return torch.any(near_c & ~near_i, dim=1)
+
+
 class SamAutomaticMaskGenerator:
     def __init__(self, model, dino_model=None, points_per_side: Optional[int] = 32, points_per_batch: int = 64,
                  pred_iou_thresh: float = 0.88, stability_score_thresh: float = 0.95,
                  stability_score_offset: float = 1.0, box_nms_thresh: float = 0.7, crop_n_layers: int = 0,
-                 min_mask_region_area: int = 0, output_mode: str = "binary_mask", crop_nms_thresh: float = 0.7,
-                 **unused) -> None:
-        assert output_mode in ("binary_mask", "uncompressed_rle", "coco_rle")
-        if crop_n_layers != 0:
-            raise NotImplementedError("multi-crop AMG is outside the B200 hot path")
+                 crop_nms_thresh: float = 0.7, crop_overlap_ratio: float = 512 / 1500,
+                 crop_n_points_downscale_factor: int = 1, point_grids: Optional[List[np.ndarray]] = None,
+                 min_mask_region_area: int = 0, output_mode: str = "binary_mask") -> None:
+        assert (points_per_side is None) != (point_grids is None), \
+            "Exactly one of points_per_side or point_grid must be provided."
+        assert output_mode in ("binary_mask", "uncompressed_rle", "coco_rle"), f"Unknown output_mode {output_mode}."
+        if points_per_side is not None:     # build_all_layer_point_grids (amg.py:189-198)
+            self.point_grids = [amg.build_point_grid(int(points_per_side / (crop_n_points_downscale_factor ** i)))
+                                for i in range(crop_n_layers + 1)]
+        else:
+            self.point_grids = point_grids
         self.predictor = SamPredictor(model, dino_model)
-        self.point_grid = amg.build_point_grid(points_per_side)
         self.points_per_batch = points_per_batch
         self.pred_iou_thresh = pred_iou_thresh
         self.stability_score_thresh = stability_score_thresh
         self.stability_score_offset = stability_score_offset
         self.box_nms_thresh = box_nms_thresh
+        self.crop_n_layers = crop_n_layers
         self.crop_nms_thresh = crop_nms_thresh
+        self.crop_overlap_ratio = crop_overlap_ratio
         self.min_mask_region_area = min_mask_region_area
         self.output_mode = output_mode
 
-    @torch.no_grad()
-    def generate(self, image: np.ndarray) -> List[Dict[str, Any]]:
+    # ------------------------------------------------------------------ one crop (automatic_mask_generator.py:221-323)
+    def _process_crop(self, image: np.ndarray, crop_box, layer: int, orig_hw):
         pr = self.predictor
-        pr.set_image(image)
-        h, w = image.shape[:2]
-        pts = self.point_grid * np.array([[w, h]])
+        x0, y0, x1, y1 = crop_box
+        crop = image[y0:y1, x0:x1, :]
+        ch, cw = crop.shape[:2]
+        H, W = orig_hw
+        pr.set_image(crop)
+        pts = self.point_grids[layer] * np.array([[cw, ch]])
         thr = float(pr.model.mask_threshold)
-        all_masks, all_iou, all_stab, all_boxes, all_pts = [], [], [], [], []
+        out = dict(masks=[], iou=[], stab=[], boxes=[], pts=[])
         for (chunk,) in amg.batch_iterator(self.points_per_batch, pts):
-            coords = torch.as_tensor(pr.transform.apply_coords(chunk, (h, w)))[:, None, :]
+            coords = torch.as_tensor(pr.transform.apply_coords(chunk, (ch, cw)))[:, None, :]
             labels = torch.ones(coords.shape[0], dtype=torch.int)[:, None]
             low, iou, _ = pr.decode_low_res(coords, labels)
             flat = low.reshape(-1, 256, 256)
@@ -55,22 +79,42 @@ class SamAutomaticMaskGenerator:
             stab = counts[:, 0] / counts[:, 1]
             iou_f = iou.reshape(-1)
             keep = torch.ones_like(iou_f, dtype=torch.bool)
-            if self.pred_iou_thresh > 0.0:                       # automatic_mask_generator.py:294-296
+            if self.pred_iou_thresh > 0.0:                       # :294-296
                 keep &= iou_f > self.pred_iou_thresh
             if self.stability_score_thresh > 0.0:                # :302-304
                 keep &= stab >= self.stability_score_thresh
+            keep &= ~_near_crop_edge(boxes, crop_box, [0, 0, W, H])          # :311-313
             idx = keep.nonzero()[:, 0]
             masks, _ = ops.mask_post_write(flat, None, idx.to(torch.int32), pr.input_size, pr.original_size, thr)
-            all_masks.append(masks); all_iou.append(iou_f[idx]); all_stab.append(stab[idx]); all_boxes.append(boxes[idx])
-            all_pts.append(torch.as_tensor(chunk).repeat_interleave(4, dim=0)[idx.cpu()])
+            out["masks"].append(masks); out["iou"].append(iou_f[idx]); out["stab"].append(stab[idx])
+            out["boxes"].append(boxes[idx])
+            out["pts"].append(torch.as_tensor(chunk).repeat_interleave(4, dim=0)[idx.cpu()])
         pr.reset_image()
-        masks = torch.cat(all_masks); iou = torch.cat(all_iou); stab = torch.cat(all_stab)
-        boxes = torch.cat(all_boxes); ptsk = torch.cat(all_pts)
-        keep = ops.box_nms(boxes.float(), iou, self.box_nms_thresh)
-        masks, iou, stab, boxes, ptsk = masks[keep], iou[keep], stab[keep], boxes[keep], ptsk[keep.cpu()]
+        masks, iou, stab = torch.cat(out["masks"]), torch.cat(out["iou"]), torch.cat(out["stab"])
+        boxes, pts_k = torch.cat(out["boxes"]), torch.cat(out["pts"])
+        keep = ops.box_nms(boxes.float(), iou, self.box_nms_thresh)                          # :250-257
+        masks, iou, stab, boxes, pts_k = masks[keep], iou[keep], stab[keep], boxes[keep], pts_k[keep.cpu()]
+        if not (x0 == 0 and y0 == 0 and x1 == W and y1 == H):                                # uncrop_masks, amg.py:246-256
+            masks = torch.nn.functional.pad(masks, (x0, W - x1, y0, H - y1), value=False)
+        boxes = amg.uncrop_boxes_xyxy(boxes, crop_box)
+        pts_k = amg.uncrop_points(pts_k, crop_box)
+        crops = torch.tensor([crop_box for _ in range(len(masks))], dtype=torch.int64).reshape(-1, 4)
+        return masks, iou, stab, boxes, pts_k, crops
+
+    @torch.no_grad()
+    def generate(self, image: np.ndarray) -> List[Dict[str, Any]]:
+        H, W = image.shape[:2]
+        crop_boxes, layers = amg.generate_crop_boxes((H, W), self.crop_n_layers, self.crop_overlap_ratio)
+        parts = [self._process_crop(image, cb, li, (H, W)) for cb, li in zip(crop_boxes, layers)]
+        masks, iou, stab, boxes, ptsk, crops = (torch.cat([p[i] for p in parts]) for i in range(6))
+        if len(crop_boxes) > 1:                                                              # :205-215
+            area = ((crops[:, 2] - crops[:, 0]) * (crops[:, 3] - crops[:, 1])).float()
+            keep = ops.box_nms(boxes.float(), (1.0 / area).to(boxes.device), self.crop_nms_thresh)
+            masks, iou, stab, boxes = masks[keep], iou[keep], stab[keep], boxes[keep]
+            ptsk, crops = ptsk[keep.cpu()], crops[keep.cpu()]
         if self.min_mask_region_area > 0 and len(masks) > 0:
-            # upstream postprocess_small_regions (automatic_mask_generator.py:326-372) on the device: fill holes /
-            # drop islands below the area, recompute boxes, NMS that prefers the masks that needed no change
+            # postprocess_small_regions (:326-372) on the device: fill holes / drop islands below the area, recompute
+            # boxes, NMS that prefers the masks that needed no change
             m8 = masks.to(torch.uint8).contiguous().clone()
             c1 = ops.remove_small_regions(m8, int(np.ceil(self.min_mask_region_area)), "holes")
             c2 = ops.remove_small_regions(m8, int(np.ceil(self.min_mask_region_area)), "islands")
@@ -81,7 +125,8 @@ class SamAutomaticMaskGenerator:
             if upd.numel() > 0:
                 masks[upd] = m8[upd].to(masks.dtype)
                 boxes[upd] = nb[upd].to(boxes.dtype)
-            masks, iou, stab, boxes, ptsk = masks[keep2], iou[keep2], stab[keep2], boxes[keep2], ptsk[keep2.cpu()]
+            masks, iou, stab, boxes = masks[keep2], iou[keep2], stab[keep2], boxes[keep2]
+            ptsk, crops = ptsk[keep2.cpu()], crops[keep2.cpu()]
         if self.output_mode == "binary_mask":
             segs = [m for m in masks.cpu().numpy()]
         else:
@@ -90,9 +135,9 @@ class SamAutomaticMaskGenerator:
         areas = masks.flatten(1).sum(1).tolist()
         out = []
         for i in range(len(segs)):
-            b = boxes[i].tolist()
+            b, c = boxes[i].tolist(), crops[i].tolist()
             out.append({"segmentation": segs[i], "area": int(areas[i]),
                         "bbox": [b[0], b[1], b[2] - b[0], b[3] - b[1]], "predicted_iou": float(iou[i]),
                         "point_coords": [ptsk[i].tolist()], "stability_score": float(stab[i]),
-                        "crop_box": [0, 0, w, h]})
+                        "crop_box": [c[0], c[1], c[2] - c[0], c[3] - c[1]]})
         return out

@@ -363,7 +363,9 @@ def amg_case():
     out = {"inject_seed": np.array(seed)}
     try:
         for tag, hw, kw in (("sq", (1024, 1024), dict(min_mask_region_area=0)),
-                            ("ns", (600, 900), dict(min_mask_region_area=100))):
+                            ("ns", (600, 900), dict(min_mask_region_area=100)),
+                            ("crops", (600, 900), dict(min_mask_region_area=100, crop_n_layers=1,
+                                                       crop_n_points_downscale_factor=2))):
             gen = ramg.SamAutomaticMaskGenerator(sam, points_per_side=12, points_per_batch=32, pred_iou_thresh=0.5,
                                                  stability_score_thresh=0.85, box_nms_thresh=0.7,
                                                  output_mode="coco_rle", **kw)
@@ -401,6 +403,9 @@ def injected_cases():
 if __name__ == "__main__":
     assert ref_import.available(), "needs /root/reference"
     torch.manual_seed(0)
+    if "--amg" in sys.argv:
+        amg_case()
+        sys.exit(0)
     if "--extra" in sys.argv:
         extra_stage_case()
         amg_case()

@@ -159,10 +159,14 @@ def test_kpost_all_planes_p64_vs_reference(tag, inp, orig, golden_dir):
     assert np.array_equal(masks.flatten(1).sum(1).cpu().numpy(), g[f"p64_{tag}_area"])
 
 
-@pytest.mark.parametrize("tag,extra", [("sq", dict(min_mask_region_area=0)), ("ns", dict(min_mask_region_area=100))])
+@pytest.mark.parametrize("tag,extra", [("sq", dict(min_mask_region_area=0)), ("ns", dict(min_mask_region_area=100)),
+                                       ("crops", dict(min_mask_region_area=100, crop_n_layers=1,
+                                                      crop_n_points_downscale_factor=2))])
 def test_automatic_mask_generator_vs_patched_reference(tag, extra, golden_dir):
     """SamAutomaticMaskGenerator against the reference class patched at run time (make_golden.py amg_case): ~200
-    records, every field exact (bbox, area, predicted_iou, point_coords, stability_score, crop_box, COCO RLE)."""
+    records, every field exact (bbox, area, predicted_iou, point_coords, stability_score, crop_box, COCO RLE); the
+    "crops" case runs 5 crops with a coarser point grid on the second layer, the crop-edge filter, mask un-cropping
+    and the cross-crop NMS."""
     from crowdsam_b200.automask import SamAutomaticMaskGenerator
     from oracle import weights
     from test_gpu_model import make_predictor
