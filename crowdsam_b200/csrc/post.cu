@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(256) post_stats_quad_kernel(csam_post_args a, 
 __global__ void __launch_bounds__(256) post_write_quad_kernel(csam_post_args a, PostGeom g, int segs_per_row) {
   const int i = blockIdx.y;
   const int p = a.keep ? a.keep[i] : i;
+  if (p < 0) return;                       // slot without a survivor (keep lists compacted on the device carry -1 tails)
   const float* L = plane_of(a, p);
   const int groups = (g.out_h + 2 + 3) / 4;
   const int total = groups * segs_per_row;
@@ -338,6 +339,7 @@ __global__ void __launch_bounds__(256) post_stats_kernel(csam_post_args a, PostG
 __global__ void __launch_bounds__(256) post_write_kernel(csam_post_args a, PostGeom g, int segs_per_row) {
   const int i = blockIdx.y;
   const int p = a.keep ? a.keep[i] : i;
+  if (p < 0) return;                       // slot without a survivor (keep lists compacted on the device carry -1 tails)
   const float* L = plane_of(a, p);
   const int total = g.out_h * segs_per_row;
   uint8_t* mo = a.masks ? a.masks + (size_t)i * g.out_h * g.out_w : nullptr;

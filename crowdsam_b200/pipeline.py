@@ -168,18 +168,18 @@ class CrowdSAM:
         self.last_counts = (0, 0)
         points = self.candidate_points(self.image.shape[:2])
         parts = []
-        # EPS iterator (model.py:229-248): same RNG consumption, occupancy tested on the device
+        # EPS iterator (model.py:229-248): same RNG consumption.  Which prompts form the next batch depends on this
+        # batch's masks, so one host decision per batch is inherent; everything else stays on the device: the keep
+        # list is compacted there, the survivors' masks are written there, the occupancy of the remaining candidates is
+        # tested there, and ONE device-to-host read per batch brings back the keep flags and the occupancy flags.
         points = points.astype("int")
         np.random.shuffle(points)
         count, bs = 0, self.points_per_batch
         while len(points) > 0 and count < self.max_prompts:
             bs = min(len(points), bs)
             sel, points = points[:bs], points[bs:]
-            batch = self._process_batch(sel, self.predictor.original_size, crop_box)
-            if len(points) > 0:
-                flag = (batch["iou_preds"] > self.filter_thresh).to(torch.uint8)
-                pts_d = torch.as_tensor(points, dtype=torch.int32, device=self.device)
-                occ = ops.points_occupied(batch["masks"], flag, pts_d).cpu().numpy().astype(bool)
+            batch, occ = self._process_batch(sel, self.predictor.original_size, crop_box, rest=points)
+            if occ is not None:
                 points = points[~occ]
             parts.append(batch)
             count += bs
@@ -214,8 +214,10 @@ class CrowdSAM:
         data["fboxes"] = data["boxes"]
         return data
 
-    def _process_batch(self, points: np.ndarray, im_size, crop_box) -> MaskData:
-        """model.py:334-390 with the selection stages fused on the device."""
+    def _process_batch(self, points: np.ndarray, im_size, crop_box, rest: Optional[np.ndarray] = None):
+        """model.py:334-390 with the selection stages fused on the device.  `rest` = the candidate points still waiting
+        (EPS): when given, also returns which of them this batch's confident masks occupy (model.py:240,246).
+        -> (MaskData of the batch, occupancy bool [len(rest)] or None)."""
         pr = self.predictor
         thr = float(pr.model.mask_threshold)
         coords = torch.as_tensor(pr.transform.apply_coords(points, im_size))[:, None, :]
@@ -243,11 +245,30 @@ class CrowdSAM:
             keep &= stab >= self.stability_score_thresh
         orig_h, orig_w = self.orig_image.shape[:2]
         keep &= ~_near_crop_edge(boxes, crop_box, [0, 0, orig_w, orig_h], self.downscale)
-        idx = keep.nonzero()[:, 0]                              # the one host sync of the batch
-        masks, _ = ops.mask_post_write(low, sel, idx.to(torch.int32), pr.input_size, pr.original_size, thr)
-        idx_c = idx.cpu()
-        return MaskData(masks=masks, iou_preds=score[idx], points=torch.as_tensor(points)[idx_c],
-                        categories=cat[idx].long(), stability_score=stab[idx], boxes=boxes[idx].long())
+        pts_t = torch.as_tensor(points)
+        if rest is None or len(rest) == 0:
+            idx = keep.nonzero()[:, 0]                          # the one host sync of the batch
+            masks, _ = ops.mask_post_write(low, sel, idx.to(torch.int32), pr.input_size, pr.original_size, thr)
+            idx_c, occ = idx.cpu(), None
+        else:
+            # more candidates wait: compact the keep list on the device (kept prompts first, in prompt order, -1 for the
+            # rest), write the survivors' masks, test the remaining candidates against the masks whose score exceeds
+            # filter_thresh (model.py:240,246), then read keep flags + occupancy flags back together
+            bs = keep.shape[0]
+            order = torch.argsort((~keep).to(torch.uint8), stable=True)
+            kept_sorted = keep[order]
+            klist = torch.where(kept_sorted, order, torch.full_like(order, -1)).to(torch.int32)
+            masks_all, _ = ops.mask_post_write(low, sel, klist, pr.input_size, pr.original_size, thr)
+            flag = (kept_sorted & (score[order] > self.filter_thresh)).to(torch.uint8)
+            pts_d = torch.as_tensor(rest, dtype=torch.int32, device=self.device)
+            occ_d = ops.points_occupied(masks_all, flag, pts_d)
+            both = torch.cat([keep.to(torch.uint8), occ_d]).cpu().numpy().astype(bool)     # the one host sync
+            n_keep = int(both[:bs].sum())
+            idx_c = torch.as_tensor(np.flatnonzero(both[:bs]))
+            idx, masks, occ = order[:n_keep], masks_all[:n_keep], both[bs:]
+        data = MaskData(masks=masks, iou_preds=score[idx], points=pts_t[idx_c], categories=cat[idx].long(),
+                        stability_score=stab[idx], boxes=boxes[idx].long())
+        return data, occ
 
     @staticmethod
     def postprocess_small_regions(mask_data: MaskData, min_area: int, nms_thresh: float) -> MaskData:

@@ -259,7 +259,8 @@ CSAM_API int csam_select_candidates(const float* iou /*[P,4]*/, const float* cls
  * (256 -> 1024, crop to (in_h,in_w), -> (out_h,out_w)) are evaluated on the fly.
  *  stats : per prompt  counts[p] = {#(m > thr+off), #(m > thr-off), #(m > thr)}, box[p] =
  *          inclusive XYXY of (m > thr) or zeros; nothing else is written.
- *  write : for each i < n_keep: masks[i] = (m[keep[i]] > thr) as uint8 [out_h,out_w];
+ *  write : for each i < n_keep: masks[i] = (m[keep[i]] > thr) as uint8 [out_h,out_w]; an entry keep[i] < 0 leaves
+ *          slot i untouched (a keep list compacted on the device without a host round trip ends in -1s);
  *          optionally logits fp32 [n_keep,out_h,out_w].
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
