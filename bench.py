@@ -219,9 +219,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points-per-batch", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--arch", default=ARCH)
+    ap.add_argument("--arch", default=ARCH, help="vit_l (headline) | vit_h (BASELINE configs[3]) | vit_b")
+    ap.add_argument("--grid", type=int, default=GRID, help="prompt grid side: 32 (headline), 64 = BASELINE configs[2]")
     ap.add_argument("--gemm-shapes", action="store_true", help="stderr: per-shape GEMM time table")
     args = ap.parse_args()
+    if args.grid != GRID or args.arch != ARCH:
+        # a non-headline workload: name it, and let test_cfg / bench_config follow
+        globals()["GRID"] = args.grid
+        globals()["WORKLOAD"] = f"{args.arch}_1024px_grid{args.grid}_pwd_nms"
+        if args.points_per_batch == 1024:
+            args.points_per_batch = args.grid * args.grid
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
