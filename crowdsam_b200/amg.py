@@ -222,6 +222,35 @@ def _coco_string(counts: Sequence[int]) -> str:
     return out.tobytes().decode("ascii")
 
 
+def coco_encode_rles(rles: List[Dict[str, Any]]) -> List[Dict[str, Any]]:
+    """coco_encode_rle for a whole list in ONE library call (csam_coco_rle_strings, host C): the per-mask interpreter
+    overhead of hundreds of instances per crowd image disappears.  Same strings as `_coco_string` / pycocotools."""
+    if not rles:
+        return []
+    try:
+        from pycocotools import mask as mask_utils  # type: ignore  # noqa: F401
+
+        return [coco_encode_rle(r) for r in rles]       # the reference's own dependency, when it is installed
+    except ImportError:
+        pass
+    import ctypes as C
+
+    from . import lib as L
+
+    cnt = [np.ascontiguousarray(r["counts"], dtype=np.int32) for r in rles]
+    flat = np.concatenate(cnt) if len(cnt) > 1 else cnt[0]
+    offs = np.zeros(len(cnt) + 1, dtype=np.int64)
+    np.cumsum([c.size for c in cnt], out=offs[1:])
+    out = np.empty(max(7 * int(flat.size), 1), dtype=np.uint8)
+    out_offs = np.empty(len(cnt) + 1, dtype=np.int64)
+    L.check(L.load().csam_coco_rle_strings(flat.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p), len(cnt),
+                                           out.ctypes.data_as(C.c_void_p), out.size, out_offs.ctypes.data_as(C.c_void_p)),
+            "csam_coco_rle_strings")
+    buf = out[: int(out_offs[-1])].tobytes().decode("ascii")
+    return [{"size": [int(r["size"][0]), int(r["size"][1])], "counts": buf[int(out_offs[i]):int(out_offs[i + 1])]}
+            for i, r in enumerate(rles)]
+
+
 def coco_encode_rle(uncompressed_rle: Dict[str, Any]) -> Dict[str, Any]:
     """Uses pycocotools when importable (as the reference does), else the built-in encoder."""
     h, w = uncompressed_rle["size"]

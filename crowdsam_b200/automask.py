@@ -131,7 +131,7 @@ class SamAutomaticMaskGenerator:
             segs = [m for m in masks.cpu().numpy()]
         else:
             rles = amg.mask_to_rle_pytorch(masks)
-            segs = [amg.coco_encode_rle(r) for r in rles] if self.output_mode == "coco_rle" else rles
+            segs = amg.coco_encode_rles(rles) if self.output_mode == "coco_rle" else rles
         areas = masks.flatten(1).sum(1).tolist()
         out = []
         for i in range(len(segs)):

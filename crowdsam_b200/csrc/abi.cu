@@ -21,3 +21,31 @@ extern "C" int csam_vit_attention(const csam_attn_args* a, void* stream) {
   if (a->impl == 1) return vit_attention_simt(a, (cudaStream_t)stream);
   return vit_attention_tc(a, (cudaStream_t)stream);
 }
+
+// Host-side COCO run-length string encoder (pycocotools maskApi.c rleToString), batched over masks.  A crowd image
+// yields hundreds of instances; encoding them one by one through numpy cost ~50 us of interpreter time per mask.
+extern "C" int csam_coco_rle_strings(const int* counts, const long long* offsets, int n_masks, char* out, long long cap,
+                                     long long* out_offsets) {
+  CSAM_REQUIRE(counts && offsets && out && out_offsets && n_masks >= 0, "csam_coco_rle_strings: null argument");
+  long long p = 0;
+  for (int m = 0; m < n_masks; ++m) {
+    out_offsets[m] = p;
+    const int* c = counts + offsets[m];
+    const long long n = offsets[m + 1] - offsets[m];
+    if (p + 7 * n > cap) return fail("%s", "csam_coco_rle_strings: output buffer too small (7 bytes per run suffice)");
+    for (long long i = 0; i < n; ++i) {
+      long long x = c[i];
+      if (i > 2) x -= c[i - 2];
+      bool more = true;
+      while (more) {
+        char ch = (char)(x & 0x1f);
+        x >>= 5;
+        more = (ch & 0x10) ? x != -1 : x != 0;
+        if (more) ch |= 0x20;
+        out[p++] = (char)(ch + 48);
+      }
+    }
+  }
+  out_offsets[n_masks] = p;
+  return 0;
+}

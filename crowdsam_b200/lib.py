@@ -114,6 +114,7 @@ _SIGS = {
     "csam_remove_small_regions": (ci, [vp, ci, ci, ci, ci, ci, vp, vp, cll, vp]),
     "csam_rle_count": (ci, [vp, ci, ci, ci, vp, vp]),
     "csam_rle_fill": (ci, [vp, ci, ci, ci, vp, vp, vp]),
+    "csam_coco_rle_strings": (ci, [vp, vp, ci, vp, cll, vp]),
 }
 
 EXPORTS = tuple(_SIGS.keys())
@@ -144,7 +145,7 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.csam_abi_version() != 8:
+    if lib.csam_abi_version() != 9:
         raise RuntimeError("libcsam_sm100.so ABI version mismatch")
     _lib = lib
     return lib

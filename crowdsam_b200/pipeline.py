@@ -131,7 +131,7 @@ class CrowdSAM:
         else:
             data["boxes"] = torch.zeros(0, 4)
             data["scores"] = torch.zeros(0, 4)
-        data["rles"] = [amg.coco_encode_rle(r) for r in data["rles"]] if "rles" in data._stats else []
+        data["rles"] = amg.coco_encode_rles(data["rles"]) if "rles" in data._stats else []
         data.to_numpy()
         return data
 

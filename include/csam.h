@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSAM_ABI_VERSION 8
+#define CSAM_ABI_VERSION 9
 #if defined(__GNUC__)
 #define CSAM_API __attribute__((visibility("default")))
 #else
@@ -317,6 +317,15 @@ CSAM_API int csam_remove_small_regions(uint8_t* masks, int n, int h, int w, int 
  * prefix sum of n_runs, computed by the caller). */
 CSAM_API int csam_rle_count(const uint8_t* masks, int n, int h, int w, int* n_runs, void* stream);
 CSAM_API int csam_rle_fill(const uint8_t* masks, int n, int h, int w, const long long* offsets, int* runs, void* stream);
+
+/* HOST function (no device work): COCO compressed RLE strings of n_masks run-length lists, replacing the per-mask
+ * `coco_encode_rle` -> pycocotools `frPyObjects` call of amg.py:294-300 / model.py:184-185 (pycocotools' rleToString:
+ * counts beyond the third are delta coded against counts[i-2]; 5-bit groups, little endian, bit 5 = continuation,
+ * + 48).  counts = all run lengths concatenated (host pointer, what csam_rle_fill produced, read back), offsets[n_masks+1]
+ * = start of each mask's runs; out receives the strings back to back (capacity cap bytes; 7 bytes per run always
+ * suffice), out_offsets[n_masks+1] their starts.  Returns 0, or 1 when cap is too small. */
+CSAM_API int csam_coco_rle_strings(const int* counts, const long long* offsets, int n_masks, char* out, long long cap,
+                                   long long* out_offsets);
 
 #ifdef __cplusplus
 }

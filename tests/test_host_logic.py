@@ -43,3 +43,18 @@ def test_rle_round_trip():
     rle = {"size": [37, 53], "counts": counts}
     assert np.array_equal(amg.rle_to_mask(rle), m)
     assert amg.area_from_rle(rle) == int(m.sum())
+
+
+def test_coco_string_batched_library_call_matches_scalar():
+    """csam_coco_rle_strings (host C, one call for all masks of an image) against the scalar restatement of
+    maskApi.c rleToString, incl. empty run lists, single runs and values needing up to 5 characters."""
+    rng = np.random.default_rng(11)
+    rles = []
+    for n, hi in ((0, 10), (1, 10), (2, 1 << 20), (3, 70000), (4, 15), (500, 3000), (5000, 1 << 20), (7, 1 << 20)):
+        rles.append({"size": [1024, 1024], "counts": rng.integers(0, hi, size=n)})
+    rles.append({"size": [4, 4], "counts": np.array([16])})
+    rles.append({"size": [4, 4], "counts": [0, 16]})
+    got = amg.coco_encode_rles(rles)
+    assert [g["counts"] for g in got] == [_coco_string_scalar(list(r["counts"])) for r in rles]
+    assert [g["size"] for g in got] == [list(r["size"]) for r in rles]
+    assert amg.coco_encode_rles([]) == []
