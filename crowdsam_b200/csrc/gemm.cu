@@ -333,44 +333,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
           // and the residual of the lane's row slice is requested before the accumulator is waited for.
           int orow = -1;
           if (r < e.M) orow = e.row_map ? e.row_map[r] : r;
-          float res[HALF];
-          const int cbase = n0 + ch * HALF;
-          if (orow >= 0 && e.residual) {
-            const float* pr = e.residual + (size_t)(e.res_mod > 0 ? (orow % e.res_mod) : orow) * e.ldr + cbase;
+          // the lane's HALF columns go in passes of at most 64 (register budget: 128 x 256 tiles have HALF = 128)
+          constexpr int PART = HALF > 64 ? 64 : HALF;
+          const float* pres = nullptr;
+          if (orow >= 0 && e.residual) pres = e.residual + (size_t)(e.res_mod > 0 ? (orow % e.res_mod) : orow) * e.ldr;
+#pragma unroll 1
+          for (int part = 0; part < HALF / PART; ++part) {
+            float res[PART];
+            const int cbase = n0 + ch * HALF + part * PART;
+            if (pres) {
 #pragma unroll
-            for (int c = 0; c < HALF; c += 8)
-              if (cbase + c < e.N) ldg256f(pr + c, res + c);
-          } else {
+              for (int c = 0; c < PART; c += 8)
+                if (cbase + c < e.N) ldg256f(pres + cbase + c, res + c);
+            } else {
 #pragma unroll
-            for (int c = 0; c < HALF; ++c) res[c] = 0.f;
-          }
-          mbar_wait(&tfull_bar[buf], bphase);
-          tc_fence_after();
+              for (int c = 0; c < PART; ++c) res[c] = 0.f;
+            }
+            if (part == 0) {
+              mbar_wait(&tfull_bar[buf], bphase);
+              tc_fence_after();
+            }
 #pragma unroll
-          for (int c = 0; c < HALF; c += 16) {
-            const int col0 = cbase + c;
-            if (col0 < e.N) {                          // warp-uniform (N is a multiple of 16 here)
-              uint32_t raw[16];
-              tmem_ld16(col_addr + c, raw);
-              tmem_ld_wait();
-              float v[16];
+            for (int c = 0; c < PART; c += 16) {
+              const int col0 = cbase + c;
+              if (col0 < e.N) {                          // warp-uniform (N is a multiple of 16 here)
+                uint32_t raw[16];
+                tmem_ld16(col_addr + part * PART + c, raw);
+                tmem_ld_wait();
+                float v[16];
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                float4 b = make_float4(0.f, 0.f, 0.f, 0.f), cs = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (e.bias) b = *reinterpret_cast<const float4*>(e.bias + col0 + j);
-                if (e.col_scale) cs = *reinterpret_cast<const float4*>(e.col_scale + col0 + j);
-                v[j + 0] = apply_act(__uint_as_float(raw[j + 0]) * rs + b.x, e.act) * cs.x + res[c + j + 0];
-                v[j + 1] = apply_act(__uint_as_float(raw[j + 1]) * rs + b.y, e.act) * cs.y + res[c + j + 1];
-                v[j + 2] = apply_act(__uint_as_float(raw[j + 2]) * rs + b.z, e.act) * cs.z + res[c + j + 2];
-                v[j + 3] = apply_act(__uint_as_float(raw[j + 3]) * rs + b.w, e.act) * cs.w + res[c + j + 3];
-              }
-              if (orow >= 0) {
-                if (e.out_f32) {
-                  float* po = e.out_f32 + (size_t)orow * e.ldo + col0;
-                  stg256f(po, v);
-                  stg256f(po + 8, v + 8);
+                for (int j = 0; j < 16; j += 4) {
+                  float4 b = make_float4(0.f, 0.f, 0.f, 0.f), cs = make_float4(1.f, 1.f, 1.f, 1.f);
+                  if (e.bias) b = *reinterpret_cast<const float4*>(e.bias + col0 + j);
+                  if (e.col_scale) cs = *reinterpret_cast<const float4*>(e.col_scale + col0 + j);
+                  v[j + 0] = apply_act(__uint_as_float(raw[j + 0]) * rs + b.x, e.act) * cs.x + res[c + j + 0];
+                  v[j + 1] = apply_act(__uint_as_float(raw[j + 1]) * rs + b.y, e.act) * cs.y + res[c + j + 1];
+                  v[j + 2] = apply_act(__uint_as_float(raw[j + 2]) * rs + b.z, e.act) * cs.z + res[c + j + 2];
+                  v[j + 3] = apply_act(__uint_as_float(raw[j + 3]) * rs + b.w, e.act) * cs.w + res[c + j + 3];
                 }
-                if (e.out_hi) store_pair16(e.out_hi, e.out_lo, (size_t)orow * e.ldh + col0, v);
+                if (orow >= 0) {
+                  if (e.out_f32) {
+                    float* po = e.out_f32 + (size_t)orow * e.ldo + col0;
+                    stg256f(po, v);
+                    stg256f(po + 8, v + 8);
+                  }
+                  if (e.out_hi) store_pair16(e.out_hi, e.out_lo, (size_t)orow * e.ldh + col0, v);
+                }
               }
             }
           }
@@ -898,5 +906,18 @@ extern "C" int csam_gemm(const csam_gemm_args* a, void* stream) {
   }
   if (wres_ok(128))
     return split ? launch_tc<128, 3, false, EPI_STD, true>(a, e, st) : launch_tc<128, 1, false, EPI_STD, true>(a, e, st);
+  if (split && e.direct && (a->N % 256) == 0 && a->K >= 512) {
+    // 128 x 256 tiles (experiment, CSAM_GEMM_BN256=1): the 128 x 128 tile is bound by the L2 -> SM fill (64 KB per 768
+    // MMA clocks = 85 B/clk per SM against the ~44 the L2 sustains chip-wide, measured lts__t_bytes = 6.6 KB/clk); the
+    // wider tile needs 62.5 B/clk.  Measured (round 2): SLOWER on every encoder shape (5330x4096x1024 341 against 368
+    // TFLOP/s, 4096x4096x1024 305 / 359, 5330x3072x1024 343 / 375) -- its 96 KB stages leave room for a 2-stage ring
+    // only, and the refill latency of a stage then sits on the critical path.  Off unless asked for.
+    static const int mode = getenv("CSAM_GEMM_BN256") ? atoi(getenv("CSAM_GEMM_BN256")) : 0;
+    const long long sms = num_sms();
+    const long long tm = (a->M + BM - 1) / BM;
+    const long long r128 = (tm * ((a->N + 127) / 128) + sms - 1) / sms, r256 = (tm * (a->N / 256) + sms - 1) / sms;
+    (void)r128; (void)r256;
+    if (mode == 1) return launch_tc<256, 3, false>(a, e, st);
+  }
   return split ? launch_tc<128, 3, false>(a, e, st) : launch_tc<128, 1, false>(a, e, st);
 }
