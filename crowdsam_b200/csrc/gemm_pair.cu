@@ -28,15 +28,18 @@ namespace csam {
 namespace {
 
 constexpr int PM = 128;             // rows of A per CTA
-constexpr int PBN = 256;            // pair tile N; each CTA stages PBN / 2 rows of W
 constexpr int PBK = 64;
 constexpr int P_A_BYTES = PM * PBK * 2;            // 16 KB
-constexpr int P_W_BYTES = (PBN / 2) * PBK * 2;     // 16 KB
-constexpr int P_STAGE_BYTES = 2 * (P_A_BYTES + P_W_BYTES);   // hi + lo of both operands: 64 KB
-constexpr int P_STAGES = 3;
 constexpr int P_EPI_WARPS = 8;
 constexpr int P_THREADS = 128 + 32 * P_EPI_WARPS;
-constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 1024 + 256;
+// PBN = pair tile N (256 or 128); each CTA stages PBN / 2 rows of W.  256: 64 KB stages, 3 of them; 128: 48 KB, 4.
+template <int PBN>
+struct PairCfg {
+  static constexpr int W_BYTES = (PBN / 2) * PBK * 2;
+  static constexpr int STAGE_BYTES = 2 * (P_A_BYTES + W_BYTES);   // hi + lo of both operands
+  static constexpr int STAGES = PBN == 256 ? 3 : 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
 constexpr uint64_t TMA_EVICT_NORMAL = 0x1000000000000000ull;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -90,10 +93,14 @@ __device__ __forceinline__ void tmem_dealloc_pair_512(uint32_t addr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(addr) : "memory");
 }
 
+template <int PBN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant__ CUtensorMap ta_lo,
                  const __grid_constant__ CUtensorMap tw_hi, const __grid_constant__ CUtensorMap tw_lo,
                  GemmEpi e, int K, int tiles_m, int tiles_n) {
+  using Cfg = PairCfg<PBN>;
+  constexpr int P_W_BYTES = Cfg::W_BYTES, P_STAGE_BYTES = Cfg::STAGE_BYTES, P_STAGES = Cfg::STAGES;
+  constexpr int EC = PBN / 2;                    // columns per epilogue warp
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* ring = smem;
@@ -133,7 +140,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constan
       int stage = 0; uint32_t phase = 0;
       for (int t = pair; t < num_tiles; t += num_pairs) {
         const int m0 = (t / tiles_n) * (2 * PM) + rank * PM;            // this CTA's 128 rows of A
-        const int n0 = (t % tiles_n) * PBN + rank * (PBN / 2);          // this CTA's 128-row half of W
+        const int n0 = (t % tiles_n) * PBN + rank * (PBN / 2);          // this CTA's half of W's rows
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = ring + stage * P_STAGE_BYTES;
@@ -184,7 +191,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constan
     // ------------------------------------------------------------------ epilogue (each CTA: its 128 rows x 256 columns)
     const int ew = warp - 4;
     const int q = ew & 3;                        // TMEM lane quadrant == warp % 4
-    const int ch = ew >> 2;                      // which half of the 256 columns
+    const int ch = ew >> 2;                      // which half of the tile's columns
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     int local = 0;
     for (int t = pair; t < num_tiles; t += num_pairs, ++local) {
@@ -199,8 +206,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constan
       const float* pres = nullptr;
       if (orow >= 0 && e.residual) pres = e.residual + (size_t)(e.res_mod > 0 ? (orow % e.res_mod) : orow) * e.ldr;
 #pragma unroll 1
-      for (int part = 0; part < 2; ++part) {     // 128 columns per warp in two passes of 64 (register budget)
-        const int cbase = n0 + ch * 128 + part * 64;
+      for (int part = 0; part < EC / 64; ++part) {     // EC columns per warp in passes of 64 (register budget)
+        const int cbase = n0 + ch * EC + part * 64;
         float res[64];
         if (pres) {
 #pragma unroll
@@ -214,7 +221,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constan
           mbar_wait(&tfull_bar[buf], bphase);
           tc_fence_after();
         }
-        const uint32_t col_addr = lane_addr + buf * PBN + ch * 128 + part * 64;
+        const uint32_t col_addr = lane_addr + buf * PBN + ch * EC + part * 64;
 #pragma unroll
         for (int c = 0; c < 64; c += 16) {
           const int col0 = cbase + c;
@@ -258,22 +265,42 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constan
 
 }  // namespace
 
+template <int PBN>
+static int launch_pair_t(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st, int tiles_m) {
+  using Cfg = PairCfg<PBN>;
+  const int tiles_n = a->N / PBN;
+  CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+  if (make_tmap_2d_f16(&ta_hi, a->a_hi, a->M, a->K, a->lda, PM, PBK)) return 1;
+  if (make_tmap_2d_f16(&ta_lo, a->a_lo, a->M, a->K, a->lda, PM, PBK)) return 1;
+  if (make_tmap_2d_f16(&tw_hi, a->w_hi, a->N, a->K, a->ldw, PBN / 2, PBK)) return 1;
+  if (make_tmap_2d_f16(&tw_lo, a->w_lo, a->N, a->K, a->ldw, PBN / 2, PBK)) return 1;
+  CSAM_DYN_SMEM(gemm_pair_kernel<PBN>, Cfg::SMEM_BYTES, "gemm_pair_kernel");
+  const int pairs = min(tiles_m * tiles_n, num_sms() / 2);
+  gemm_pair_kernel<PBN><<<2 * pairs, P_THREADS, Cfg::SMEM_BYTES, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, e, a->K, tiles_m, tiles_n);
+  return check_launch("gemm_pair_kernel");
+}
+
 int launch_gemm_pair(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st) {
-  // CSAM_GEMM_PAIR: 0 = never, 1 = whenever the problem qualifies, unset = when the wave model below favours it.
-  // impl == CSAM_GEMM_TC_PAIR in the arguments forces this kernel (tests, A/B measurements).
+  // CSAM_GEMM_PAIR: 0 = never, 1 = 256-wide pair tiles whenever the problem qualifies, 2 = 128-wide pair tiles whenever
+  // it qualifies (experiment), unset = 256-wide where the wave model below favours them.
+  // impl == CSAM_GEMM_TC_PAIR in the arguments forces the 256-wide kernel (tests, A/B measurements).
   static const int mode = getenv("CSAM_GEMM_PAIR") ? atoi(getenv("CSAM_GEMM_PAIR")) : -1;
   const bool forced = a->impl == CSAM_GEMM_TC_PAIR;
   if (mode == 0 && !forced) return -1;
   // qualifies: hi/lo split operands, K-major W, standard row-per-lane epilogue, whole k-blocks and pair tiles in N
   const int sms = num_sms();
   const int tiles_m = (a->M + 2 * PM - 1) / (2 * PM);
-  const int tiles_n = a->N / PBN;
+  const int tiles_n = a->N / 256;
   const bool ok = a->a_lo && a->w_lo && !a->b_mn_major && a->epi == CSAM_EPI_STD && e.direct && (a->K % PBK) == 0 &&
-                  (a->N % PBN) == 0 && a->K >= 4 * PBK;
+                  (a->N % 256) == 0 && a->K >= 4 * PBK;
   if (!ok) {
     if (forced) return fail("%s", "csam_gemm: the CTA-pair kernel needs split operands, K-major W, N % 256 == 0, K % 64 == 0, "
                                   "K >= 256 and 32-byte aligned outputs");
     return -1;
+  }
+  if (!forced && mode == 2) {
+    if ((long long)tiles_m * (a->N / 128) * 2 < sms) return -1;
+    return launch_pair_t<128>(a, e, st, tiles_m);
   }
   if (!forced && mode != 1) {
     // Wave model (measured, round 2: the tensor pipe is ~70 % active inside a pair tile against ~55-60 % inside a
@@ -288,15 +315,7 @@ int launch_gemm_pair(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st)
     // single-CTA kernel, 4096 x 1024 x 4096 (1 against 2) 377 against 357 for the pairs
     if (est_pair > est_single || (est_pair == est_single && rounds_pair > 1) || t2 * 4 < sms) return -1;
   }
-  CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
-  if (make_tmap_2d_f16(&ta_hi, a->a_hi, a->M, a->K, a->lda, PM, PBK)) return 1;
-  if (make_tmap_2d_f16(&ta_lo, a->a_lo, a->M, a->K, a->lda, PM, PBK)) return 1;
-  if (make_tmap_2d_f16(&tw_hi, a->w_hi, a->N, a->K, a->ldw, PBN / 2, PBK)) return 1;
-  if (make_tmap_2d_f16(&tw_lo, a->w_lo, a->N, a->K, a->ldw, PBN / 2, PBK)) return 1;
-  CSAM_DYN_SMEM(gemm_pair_kernel, P_SMEM_BYTES, "gemm_pair_kernel");
-  const int pairs = min(tiles_m * tiles_n, sms / 2);
-  gemm_pair_kernel<<<2 * pairs, P_THREADS, P_SMEM_BYTES, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, e, a->K, tiles_m, tiles_n);
-  return check_launch("gemm_pair_kernel");
+  return launch_pair_t<256>(a, e, st, tiles_m);
 }
 
 }  // namespace csam
