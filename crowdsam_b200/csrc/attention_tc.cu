@@ -125,7 +125,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(&bars->q_full, NQ * Cfg::NOPS * Cfg::Q_BYTES);
       for (int t = 0; t < NQ; ++t)
         for (int half = 0; half < 2; ++half) {
@@ -154,7 +154,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
     // ------------------------------------------------------------------ MMA issuer #1: S = Q K^T
     // Two issuing threads (this one and warp 1 for P V): a narrow MMA (N = 64) executes in 32 cycles, less than
     // one thread needs to issue it, so a single issuer held the tensor pipe back (x3: 20 MMAs per key tile).
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_f16(AT_BM, AT_BN, 0, 0);
       mbar_wait(&bars->q_full, 0);
       tc_fence_after();
@@ -184,7 +184,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer #2: O += P V
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_pv = umma_idesc_f16(AT_BM, AT_HD, 0, 1);
       for (int j = 0; j < n_tiles; ++j) {
         const int b = j & 1;
@@ -458,7 +458,7 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (K / V only)
-    if (lane == 0) {
+    if (elect_one()) {
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % STAGES;
         mbar_wait(&bars->kv_empty[st], ((j / STAGES) & 1) ^ 1);
@@ -479,7 +479,7 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------------ MMA issuer #1: S = Q K^T, Q from TMEM
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_f16(AT_BM, AT_BN, 0, 0);
 #pragma unroll
       for (int t = 0; t < NQ; ++t)
@@ -512,7 +512,7 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer #2: O += P V, P from TMEM
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_pv = umma_idesc_f16(AT_BM, HD, 0, 1);
       for (int j = 0; j < n_tiles; ++j) {
         const int b = j & 1;

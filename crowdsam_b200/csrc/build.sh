@@ -2,7 +2,7 @@
 # Build libcsam_sm100.so in-tree (sm_100a only).  Usage: build.sh [extra nvcc flags]
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
-OUT="$HERE/../_C"
+OUT="${CSAM_BUILD_OUT:-$HERE/../_C}"     # CSAM_BUILD_OUT: side builds (e.g. -DCSAM_TRACE) next to the product library
 mkdir -p "$OUT"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr"

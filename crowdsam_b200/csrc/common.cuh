@@ -283,6 +283,18 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// One lane of a CONVERGED warp, chosen by the hardware.  Role branches must use this and not `lane == 0`: behind
+// `elect.sync` ptxas knows that exactly one thread is active and issues the uniform-datapath instructions
+// (UTCHMMA, UTMALDG, UTCBAR) back to back with their descriptors precomputed in uniform registers; behind a
+// divergent `lane == 0` it wraps EVERY such instruction in an ELECT / BRA.U.ANY loop of ~8 dependent instructions
+// (cuobjdump: 329 ELECT for 156 UTCHMMA in gemm.o), and the issuing thread needed ~140 clocks per MMA where a
+// 128 x 64 x 16 MMA executes in 32 (timeline of K-T2I, scripts/trace_dec.py).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

@@ -10,7 +10,11 @@
 //     MMA1  S[128,64]  = [X | PEQ] (K = 384) * B1^T          (tcgen05, 3 MMAs per k-step: hi/lo split operands)
 //     E1    P = softmax over the 7 tokens of each head       (fp32, four threads per row, P stored as an h16 pair)
 //     MMA2  O[128,256] = P (K = 64) * B2^T
-//     E2    x' = LayerNorm(x + O + b_o) -> h16 pair          (residual x re-read from L2, where MMA1's TMA left it)
+//     MMAr  O[128,256] = X * I                               (the residual enters the accumulator THROUGH the tensor core:
+//                                                             while k-block kb of X is resident for MMA1, hi * I + lo * I
+//                                                             with a 64 x 64 identity writes x (exactly: hi + lo fits fp32)
+//                                                             into columns 64 kb .. 64 kb + 63 of O; MMA2 then accumulates)
+//     E2    x' = LayerNorm(O + b_o) -> h16 pair
 // so the [P*4096,128] q and attention-output streams and the separate out_proj GEMM of the unfused path never
 // exist: the layer reads X once (1 KB per row) and writes X' once (1 KB per row).
 //   warp 0       TMA producer  (A / B1 k-blocks through a 2-stage ring; B2 once per prompt)
@@ -23,6 +27,25 @@
 
 namespace csam {
 
+// Timeline instrumentation (builds with -DCSAM_TRACE only, scripts/trace_dec.py): CTA 0 stamps clock64 at the
+// hand-over points of the pipelines below; the product build compiles the macro away.
+#ifdef CSAM_TRACE
+__device__ unsigned long long g_trace[2 * 16384];
+__device__ unsigned int g_trace_n;
+#define CSAM_TR(tag, val)                                                                      \
+  do {                                                                                         \
+    if (blockIdx.x == 0) {                                                                     \
+      const unsigned int ti_ = atomicAdd(&g_trace_n, 1u);                                      \
+      if (ti_ < 16384u) {                                                                      \
+        g_trace[2 * ti_] = (unsigned long long)clock64();                                      \
+        g_trace[2 * ti_ + 1] = ((unsigned long long)(tag) << 32) | (unsigned int)(val);        \
+      }                                                                                        \
+    }                                                                                          \
+  } while (0)
+#else
+#define CSAM_TR(tag, val) do { } while (0)
+#endif
+
 constexpr int I2T_BM = 128;
 constexpr int I2T_THREADS = 640;                 // 4 control warps + 16 epilogue warps (4 per TMEM lane quadrant)
 constexpr int I2T_KB1 = 6;                       // 4 k-blocks of X (256) + 2 of PEQ (128)
@@ -34,7 +57,8 @@ constexpr int I2T_B2_BYTES = 256 * 64 * 2;       // 32 KB per half
 constexpr int I2T_P_BYTES = 128 * 64 * 2;        // 16 KB per half
 constexpr int I2T_OFF_B2 = I2T_STAGES * I2T_STAGE_BYTES;
 constexpr int I2T_OFF_P = I2T_OFF_B2 + 2 * I2T_B2_BYTES;
-constexpr int I2T_OFF_BAR = I2T_OFF_P + 2 * I2T_P_BYTES;
+constexpr int I2T_OFF_ID = I2T_OFF_P + 2 * I2T_P_BYTES;      // 64 x 64 fp16 identity, K-major, 128B swizzle (8 KB)
+constexpr int I2T_OFF_BAR = I2T_OFF_ID + 64 * 64 * 2;
 constexpr int I2T_OFF_EPI = I2T_OFF_BAR + 256;
 constexpr int I2T_SMEM_BYTES = I2T_OFF_EPI + (8 * 128 + 3 * 256) * 4;
 static_assert(I2T_SMEM_BYTES <= 227 * 1024, "i2t layer shared memory budget");
@@ -42,15 +66,13 @@ static_assert(I2T_SMEM_BYTES <= 227 * 1024, "i2t layer shared memory budget");
 struct I2TBars {
   uint64_t full[I2T_STAGES], empty[I2T_STAGES];
   uint64_t s_full[2], s_empty[2];
-  uint64_t p_full, o_full, o_empty, b2_full, b2_empty, tile_go;
+  uint64_t p_full, o_full, o_empty, b2_full, b2_empty;
   uint32_t tmem_slot;
 };
 
 struct I2TParams {
   int x_shared;              // 1: the same 4096 key rows for every prompt (layer 0)
-  int gate;                  // 1: MMA1 of the next tile waits for the epilogue to reach the current one
   int tiles;                 // P * 32
-  const __half* x_hi; const __half* x_lo;     // residual = the keys themselves (hi + lo is fp32-accurate)
   const float* bias; const float* gamma; const float* beta; float eps;
   __half* out_hi; __half* out_lo;
 };
@@ -88,10 +110,24 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
     mbar_init(&bars->o_empty, 16);
     mbar_init(&bars->b2_full, 1);
     mbar_init(&bars->b2_empty, 1);
-    mbar_init(&bars->tile_go, 16);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(&bars->tmem_slot);
+  {
+    // identity operand of the residual MMAs: row n holds K elements 8c .. 8c+7 in 16-byte chunk c ^ (n & 7)
+    uint4* idm = reinterpret_cast<uint4*>(smem + I2T_OFF_ID);
+    for (int i = threadIdx.x; i < 512; i += I2T_THREADS) {
+      const int n = i >> 3, c = (i & 7) ^ (n & 7);             // physical chunk i & 7 of row n holds logical chunk c
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (c == (n >> 3)) {
+        const uint32_t one = 0x3C00u << (16 * (n & 1));         // fp16 1.0 at element n & 7 of the chunk
+        const int w = (n & 7) >> 1;
+        v.x = w == 0 ? one : 0u; v.y = w == 1 ? one : 0u; v.z = w == 2 ? one : 0u; v.w = w == 3 ? one : 0u;
+      }
+      idm[i] = v;
+    }
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -100,29 +136,31 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0; int b2_cnt = 0;
-      const uint64_t keep = l2_policy_evict_last();
       for (int t = t0; t < t1; ++t) {
         const int p = t >> 5, mrow = (t & 31) * I2T_BM;
         const int arow = a.x_shared ? mrow : t * I2T_BM;
-        if (a.gate && t > t0) {
-          // tile t may enter L2 only once the epilogue has reached tile t-1 (see the MMA issuer); the k-blocks
-          // beyond the ring depth are requested from HBM right away so the ring's loads find them in L2
-          mbar_wait(&bars->tile_go, (t - t0 - 1) & 1);
-          for (int kb = I2T_STAGES; kb < 4; ++kb) {
-            tma_prefetch_l2_2d(&tx_hi, kb * 64, arow);
-            tma_prefetch_l2_2d(&tx_lo, kb * 64, arow);
+        if (!a.x_shared) {
+          // nothing re-reads X any more (the residual rides through the tensor core), so the stream may run ahead in
+          // L2 as far as is useful: two tiles ahead takes HBM latency off the 2-stage ring
+          const int tfirst = t == t0 ? t + 1 : t + 2;
+          for (int tp = tfirst; tp <= t + 2 && tp < t1; ++tp) {
+            for (int kb = 0; kb < 4; ++kb) {
+              tma_prefetch_l2_2d(&tx_hi, kb * 64, tp * I2T_BM);
+              tma_prefetch_l2_2d(&tx_lo, kb * 64, tp * I2T_BM);
+            }
           }
         }
         for (int kb = 0; kb < I2T_KB1; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
+          CSAM_TR(100 + kb, t - t0);
           uint8_t* sa = smem + stage * I2T_STAGE_BYTES;
           uint8_t* sb = sa + 2 * I2T_A_BYTES;
           mbar_expect_tx(&bars->full[stage], I2T_STAGE_BYTES);
           if (kb < 4) {
-            tma_load_2d_hint(sa, &tx_hi, &bars->full[stage], kb * 64, arow, keep);
-            tma_load_2d_hint(sa + I2T_A_BYTES, &tx_lo, &bars->full[stage], kb * 64, arow, keep);
+            tma_load_2d(sa, &tx_hi, &bars->full[stage], kb * 64, arow);
+            tma_load_2d(sa + I2T_A_BYTES, &tx_lo, &bars->full[stage], kb * 64, arow);
           } else {
             tma_load_2d(sa, &tq_hi, &bars->full[stage], (kb - 4) * 64, mrow);
             tma_load_2d(sa + I2T_A_BYTES, &tq_lo, &bars->full[stage], (kb - 4) * 64, mrow);
@@ -144,17 +182,22 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc1 = umma_idesc_f16(I2T_BM, 64, 0, 0);
       constexpr uint32_t idesc2 = umma_idesc_f16(I2T_BM, 256, 0, 0);
+      constexpr uint32_t idesc_r = umma_idesc_f16(I2T_BM, 16, 0, 0);
+      const uint32_t idd = umma_desc_lo(smem_u32(smem + I2T_OFF_ID), 16);
       int stage = 0; uint32_t phase = 0; int b2_cnt = 0;
       auto mma1 = [&](int li) {
         const int b = li & 1;
         mbar_wait(&bars->s_empty[b], ((li >> 1) & 1) ^ 1);
+        mbar_wait(&bars->o_empty, (li & 1) ^ 1);     // the residual MMAs below overwrite O: tile li-1 must be drained
+        CSAM_TR(121, li);
         tc_fence_after();
         const uint32_t d = tmem_base + b * 64;
         for (int kb = 0; kb < I2T_KB1; ++kb) {
           mbar_wait(&bars->full[stage], phase);
+          CSAM_TR(110 + kb, li);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * I2T_STAGE_BYTES);
           const uint32_t ad = umma_desc_lo(sa, 16);
@@ -164,6 +207,16 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
             umma_f16_w(d, ad + 2 * k, bd + 2 * k, idesc1, (kb | k) ? 1u : 0u);
             umma_f16_w(d, ad + (I2T_A_BYTES >> 4) + 2 * k, bd + 2 * k, idesc1, 1u);
             umma_f16_w(d, ad + 2 * k, bd + (I2T_B1_BYTES >> 4) + 2 * k, idesc1, 1u);
+          }
+          if (kb < 4) {
+            // residual: O[:, 64 kb + 16 k ..+16) = X_hi * I + X_lo * I over the 16 features of k-step k (N = 16 MMAs
+            // against rows 16 k ..+16 of the identity: 2048 k bytes further, plus the usual 32 k bytes along K)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t dr = tmem_base + 128 + kb * 64 + k * 16;
+              umma_f16_w(dr, ad + 2 * k, idd + 130 * k, idesc_r, 0u);
+              umma_f16_w(dr, ad + (I2T_A_BYTES >> 4) + 2 * k, idd + 130 * k, idesc_r, 1u);
+            }
           }
           umma_commit(&bars->empty[stage]);
           if (++stage == I2T_STAGES) { stage = 0; phase ^= 1; }
@@ -175,26 +228,20 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
       for (int t = t0; t < t1; ++t, ++li) {
         if (t == t0 || (t & 31) == 0) { mbar_wait(&bars->b2_full, b2_cnt & 1); ++b2_cnt; }
         mbar_wait(&bars->p_full, li & 1);
-        mbar_wait(&bars->o_empty, (li & 1) ^ 1);
+        CSAM_TR(120, li);
         tc_fence_after();
         const uint32_t pd = umma_desc_lo(smem_u32(smem + I2T_OFF_P), 16);
         const uint32_t bd = umma_desc_lo(smem_u32(smem + I2T_OFF_B2), 16);
         const uint32_t d = tmem_base + 128;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          umma_f16_w(d, pd + 2 * k, bd + 2 * k, idesc2, k ? 1u : 0u);
+          umma_f16_w(d, pd + 2 * k, bd + 2 * k, idesc2, 1u);            // on top of the residual MMA1 left there
           umma_f16_w(d, pd + (I2T_P_BYTES >> 4) + 2 * k, bd + 2 * k, idesc2, 1u);
           umma_f16_w(d, pd + 2 * k, bd + (I2T_B2_BYTES >> 4) + 2 * k, idesc2, 1u);
         }
         umma_commit(&bars->o_full);
         if (t + 1 == t1 || ((t + 1) & 31) == 0) umma_commit(&bars->b2_empty);   // last tile of this prompt here
-        // MMA1(li+1) pulls tile li+1 of the keys through L2; the epilogue re-reads the same rows as its residual one
-        // tile later.  Without this gate MMA1 ran up to 2.5 tiles ahead and the rows had left L2 by then (ncu: every
-        // residual byte came from HBM again); with it the reuse distance is under one tile.
-        if (t + 1 < t1) {
-          if (a.gate) mbar_wait(&bars->tile_go, li & 1);
-          mma1(li + 1);
-        }
+        if (t + 1 < t1) mma1(li + 1);
       }
     }
   } else if (warp < 4) {
@@ -227,7 +274,9 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
     // E1: softmax over the 7 tokens of each of this thread's 2 heads -> P (hi/lo) in the UMMA K-major layout
     auto softmax_tile = [&](int li) {
       const int b = li & 1;
+      if (warp == 4 && lane == 0) CSAM_TR(130, li);
       mbar_wait(&bars->s_full[b], (li >> 1) & 1);
+      if (warp == 4 && lane == 0) CSAM_TR(131, li);
       tc_fence_after();
       uint32_t raw[16];
       tmem_ld16(lane_addr + b * 64 + cq * 16, raw);
@@ -273,29 +322,10 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
     if (t0 < t1) softmax_tile(0);
     int li = 0;
     for (int t = t0; t < t1; ++t, ++li) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->tile_go);
-      // residual rows (this lane's 64 columns), requested before the accumulator is waited for.  The TMA producer
-      // brought the same bytes through L2 about one tile ago: evict-last on that load and evict-first on this
-      // kernel's output stores keep them there (without the hints ncu showed every residual byte re-read from HBM).
-      const size_t xrow = (size_t)(a.x_shared ? (t & 31) * I2T_BM + r : t * I2T_BM + r);
-      const __half* ph = a.x_hi + xrow * 256 + cq * 64;
-      const __half* pl = a.x_lo + xrow * 256 + cq * 64;
       float x[64];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint32_t hw[8], lw[8];
-        ldg256(ph + i * 16, hw);
-        ldg256(pl + i * 16, lw);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[k]));
-          const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[k]));
-          x[i * 16 + 2 * k] = hf.x + lf.x;
-          x[i * 16 + 2 * k + 1] = hf.y + lf.y;
-        }
-      }
+      if (warp == 4 && lane == 0) CSAM_TR(132, li);
       mbar_wait(&bars->o_full, li & 1);
+      if (warp == 4 && lane == 0) CSAM_TR(133, li);
       tc_fence_after();
       float sum = 0.f;
 #pragma unroll
@@ -305,10 +335,10 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          x[c + j + 0] += __uint_as_float(raw[j + 0]);
-          x[c + j + 1] += __uint_as_float(raw[j + 1]);
-          x[c + j + 2] += __uint_as_float(raw[j + 2]);
-          x[c + j + 3] += __uint_as_float(raw[j + 3]);
+          x[c + j + 0] = __uint_as_float(raw[j + 0]);      // residual + out_proj(attention), both from the tensor core
+          x[c + j + 1] = __uint_as_float(raw[j + 1]);
+          x[c + j + 2] = __uint_as_float(raw[j + 2]);
+          x[c + j + 3] = __uint_as_float(raw[j + 3]);
           if (has_bias) {        // only when the caller did not fold out_proj's bias into B2
             const float4 bb = *reinterpret_cast<const float4*>(s_bias + cq * 64 + c + j);
             x[c + j + 0] += bb.x; x[c + j + 1] += bb.y; x[c + j + 2] += bb.z; x[c + j + 3] += bb.w;
@@ -320,6 +350,7 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->o_empty);
+      if (warp == 4 && lane == 0) CSAM_TR(134, li);
       ex_sum[cq * 128 + r] = sum;
       asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
       const float mean = ((ex_sum[r] + ex_sum[128 + r]) + (ex_sum[256 + r] + ex_sum[384 + r])) * (1.0f / 256.0f);
@@ -348,6 +379,7 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
       }
       // E1 of the next tile last: MMA1(li+1) had this whole iteration to finish, and MMA2(li+1) runs under the next
       // iteration's residual fetch
+      if (warp == 4 && lane == 0) CSAM_TR(135, li);
       if (t + 1 < t1) softmax_tile(li + 1);
     }
   }
@@ -452,7 +484,7 @@ static_assert(T2I_SMEM_BYTES <= 227 * 1024, "t2i shared memory budget");
 constexpr float T2I_TAU = 8.f;
 
 struct T2IBars {
-  uint64_t x_full[4], x_empty[2], pek_full, pek_empty, b_full[2], b_empty[2];
+  uint64_t x_full[4], x_empty[2], pek_full, pek_empty, b_full[2], b_empty[2], v_full[2];
   uint64_t s_full, s_empty, p_full, pv_done;
   uint32_t tmem_slot;
 };
@@ -487,7 +519,7 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
     for (int i = 0; i < 4; ++i) mbar_init(&bars->x_full[i], 1);
     mbar_init(&bars->x_empty[0], 1); mbar_init(&bars->x_empty[1], 1);
     mbar_init(&bars->pek_full, 1); mbar_init(&bars->pek_empty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); mbar_init(&bars->v_full[i], 1); }
     mbar_init(&bars->s_full, 1); mbar_init(&bars->s_empty, 8);
     mbar_init(&bars->p_full, 8); mbar_init(&bars->pv_done, 1);
     fence_barrier_init();
@@ -500,23 +532,61 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
   const uint32_t tmem_base = bars->tmem_slot;      // S [0,64)  XBAR^T features 0..127 [64,128)  128..255 [128,192)
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int tl = 0, bcnt = 0, pcnt = 0;
+    // ------------------------------------------------------------------ TMA producer #1: the key tiles
+    // Two producers, so that the X loads of a tile are requested the moment MMA2 of the previous tile lets go of
+    // the slots.  (One thread used to walk X / PEK / B1 in k-block order: the X load of k-block kb + 2 then sat
+    // behind a wait on the 2-deep B1 ring, i.e. behind MMA1 of k-block kb, and the four load latencies of a tile
+    // were paid one after the other -- the softmax warps spent 69 % of their time waiting for S.)
+    if (elect_one()) {
+      int tl = 0;
       for (int p = blockIdx.x; p < a.P; p += gridDim.x) {
         for (int ti = 0; ti < 32; ++ti, ++tl) {
-          const int mrow = ti * 128;
-          const int arow = a.x_shared ? mrow : p * 4096 + mrow;
-          for (int i = 0; i < 6; ++i) {
-            const int kb = t2i_kb(i);
-            if (kb < 4) {
-              // slots 0,1 / 2,3 are released separately, as soon as MMA2 of the previous tile is done with them
-              if ((kb & 1) == 0) mbar_wait(&bars->x_empty[kb >> 1], (tl & 1) ^ 1);
+          const int arow = (a.x_shared ? 0 : p * 4096) + ti * 128;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            // slots 0,1 / 2,3 are released separately, as soon as MMA2 of the previous tile is done with them
+            mbar_wait(&bars->x_empty[half], (tl & 1) ^ 1);
+            CSAM_TR(10 + half, tl);
+#pragma unroll
+            for (int kb = 2 * half; kb < 2 * half + 2; ++kb) {
               uint8_t* sx = smem + kb * T2I_SLOT;
               mbar_expect_tx(&bars->x_full[kb], T2I_SLOT);
               tma_load_2d(sx, &tx_hi, &bars->x_full[kb], kb * 64, arow);
               tma_load_2d(sx + 16384, &tx_lo, &bars->x_full[kb], kb * 64, arow);
-            } else {
+            }
+            if (half == 0) {
+              // the NEXT tile of X goes to L2 now, so that its loads (which must wait for this tile's MMA2) are L2 hits
+              int nrow = -1;
+              if (ti + 1 < 32) nrow = arow + 128;
+              else if (!a.x_shared && p + (int)gridDim.x < a.P) nrow = (p + (int)gridDim.x) * 4096;
+              else if (a.x_shared && p + (int)gridDim.x < a.P) nrow = 0;
+              if (nrow >= 0) {
+                for (int k2 = 0; k2 < 4; ++k2) {
+                  tma_prefetch_l2_2d(&tx_hi, k2 * 64, nrow);
+                  tma_prefetch_l2_2d(&tx_lo, k2 * 64, nrow);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ TMA producer #2: PEK tiles and B1
+    // B1 (96 KB per prompt) does not fit next to the key tile, so its six k-blocks are streamed per tile.  A 2-slot
+    // ring for all six exposed one L2 latency per k-block (a slot is free only after its MMAs have COMPLETED): the
+    // timeline showed 1750 clocks per k-block, 10.5 k per tile.  Now the two dedicated slots serve the blocks whose
+    // loads hide under other work (PE blocks 4,5 under the previous softmax, X blocks 0,1 under softmax / MMA2), and
+    // X blocks 2,3 land in the P buffer, which is dead from MMA2(t-1) to softmax(t) -- exactly when the key slots
+    // 2,3 are refilled, so both arrive together.
+    if (elect_one()) {
+      int bcnt = 0, pcnt = 0, tl = 0;
+      for (int p = blockIdx.x; p < a.P; p += gridDim.x) {
+        for (int ti = 0; ti < 32; ++ti, ++tl) {
+          const int mrow = ti * 128;
+          for (int i = 0; i < 4; ++i) {
+            const int kb = t2i_kb(i);
+            if (kb >= 4) {
               mbar_wait(&bars->pek_empty, (pcnt & 1) ^ 1);
               uint8_t* sx = smem + T2I_OFF_PEK;
               mbar_expect_tx(&bars->pek_full, T2I_SLOT);
@@ -531,20 +601,20 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
             tma_load_2d(sb, &tb1_hi, &bars->b_full[bs], kb * 64, p * 64);
             tma_load_2d(sb + I2T_B1_BYTES, &tb1_lo, &bars->b_full[bs], kb * 64, p * 64);
             ++bcnt;
-            if (i == 1 && ti + 1 < 32) {
-              // the NEXT tile of X goes to L2 now, so that its loads (which must wait for this tile's MMA2) are L2 hits
-              for (int k2 = 0; k2 < 4; ++k2) {
-                tma_prefetch_l2_2d(&tx_hi, k2 * 64, arow + 128);
-                tma_prefetch_l2_2d(&tx_lo, k2 * 64, arow + 128);
-              }
-            }
+          }
+          if (tl > 0) mbar_wait(&bars->pv_done, (tl - 1) & 1);       // MMA2 of the previous tile has read P
+          for (int v = 0; v < 2; ++v) {
+            uint8_t* sb = smem + T2I_OFF_P + v * 2 * I2T_B1_BYTES;
+            mbar_expect_tx(&bars->v_full[v], 2 * I2T_B1_BYTES);
+            tma_load_2d(sb, &tb1_hi, &bars->v_full[v], (2 + v) * 64, p * 64);
+            tma_load_2d(sb + I2T_B1_BYTES, &tb1_lo, &bars->v_full[v], (2 + v) * 64, p * 64);
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc1 = umma_idesc_f16(128, 64, 0, 0);
       constexpr uint32_t idesc2 = umma_idesc_f16(128, 64, 1, 1);     // A = X^T and B = P, both MN-major
       int bcnt = 0, pcnt = 0;
@@ -557,24 +627,31 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
           uint32_t sa;
           if (kb < 4) {
             mbar_wait(&bars->x_full[kb], tl & 1);
+            CSAM_TR(20 + kb, tl);
             sa = smem_u32(smem + kb * T2I_SLOT);
           } else {
             mbar_wait(&bars->pek_full, pcnt & 1);
             sa = smem_u32(smem + T2I_OFF_PEK);
           }
           const int bs = bcnt & 1;
-          mbar_wait(&bars->b_full[bs], (bcnt >> 1) & 1);
+          uint32_t sbb;
+          if (i < 4) {
+            mbar_wait(&bars->b_full[bs], (bcnt >> 1) & 1);
+            sbb = smem_u32(smem + T2I_OFF_B1 + bs * 2 * I2T_B1_BYTES);
+          } else {
+            mbar_wait(&bars->v_full[i - 4], tl & 1);
+            sbb = smem_u32(smem + T2I_OFF_P + (i - 4) * 2 * I2T_B1_BYTES);
+          }
           tc_fence_after();
           const uint32_t ad = umma_desc_lo(sa, 16);
-          const uint32_t bd = umma_desc_lo(smem_u32(smem + T2I_OFF_B1 + bs * 2 * I2T_B1_BYTES), 16);
+          const uint32_t bd = umma_desc_lo(sbb, 16);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             umma_f16_w(tmem_base, ad + 2 * k, bd + 2 * k, idesc1, (i | k) ? 1u : 0u);
             umma_f16_w(tmem_base, ad + (16384 >> 4) + 2 * k, bd + 2 * k, idesc1, 1u);
             umma_f16_w(tmem_base, ad + 2 * k, bd + (I2T_B1_BYTES >> 4) + 2 * k, idesc1, 1u);
           }
-          umma_commit(&bars->b_empty[bs]);
-          ++bcnt;
+          if (i < 4) { umma_commit(&bars->b_empty[bs]); ++bcnt; }      // blocks 2,3 sit in the P buffer: freed by pv_done
           if (kb >= 4) { umma_commit(&bars->pek_empty); ++pcnt; }
         }
         if (i1 == 6) umma_commit(&bars->s_full);
@@ -589,6 +666,7 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
           mma1(tl + 1, 0, 2);
         }
         mbar_wait(&bars->p_full, tl & 1);        // P stored, accumulator rescaled if the maxima moved
+        CSAM_TR(30, tl);
         tc_fence_after();
         const uint32_t pd = umma_desc_lo(smem_u32(smem + T2I_OFF_P), 8192);
 #pragma unroll
@@ -621,7 +699,9 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
 #pragma unroll
       for (int c = 0; c < 32; ++c) lsum[c] = 0.f;
       for (int ti = 0; ti < 32; ++ti, ++tl) {
+        if (warp == 4 && lane == 0) CSAM_TR(40, tl);
         mbar_wait(&bars->s_full, tl & 1);
+        if (warp == 4 && lane == 0) CSAM_TR(41, tl);
         tc_fence_after();
         uint32_t raw[32];
         tmem_ld32(lane_addr + ch * 32, raw);
@@ -672,7 +752,9 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
             for (int c = 0; c < 32; ++c) lsum[c] *= st_alpha[ch * 32 + c];
           }
         }
+        if (warp == 4 && lane == 0) CSAM_TR(42, tl);
         if (tl > 0 && !waited_pv) { mbar_wait(&bars->pv_done, (tl - 1) & 1); tc_fence_after(); }   // P buffer free
+        if (warp == 4 && lane == 0) CSAM_TR(43, tl);
         uint8_t* pb = smem + T2I_OFF_P + r * 128;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -763,6 +845,21 @@ dec_t2i_out_kernel(const float* __restrict__ xbar, const float* __restrict__ wv_
 
 using namespace csam;
 
+#ifdef CSAM_TRACE
+// returns the number of (clock, tag << 32 | value) pairs copied to `host` and resets the device-side log
+extern "C" __attribute__((visibility("default"))) int csam_debug_trace(unsigned long long* host, int max_pairs) {
+  unsigned int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(n));
+  if (n > 16384u) n = 16384u;
+  if ((int)n > max_pairs) n = (unsigned int)max_pairs;
+  cudaMemcpyFromSymbol(host, g_trace, (size_t)n * 16);
+  const unsigned int zero = 0;
+  cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero));
+  return (int)n;
+}
+#endif
+
 extern "C" int csam_dec_fold_i2t(const float* kt, const float* vt, int P, const float* wq, const float* wo, const float* bo,
                                  void* b1_hi, void* b1_lo, void* b2_hi, void* b2_lo, void* stream) {
   CSAM_REQUIRE(kt && vt && wq && wo && b1_hi && b1_lo && b2_hi && b2_lo && P > 0, "csam_dec_fold_i2t: bad args");
@@ -797,9 +894,7 @@ extern "C" int csam_dec_i2t_layer(const csam_i2t_layer_args* a, void* stream) {
   CSAM_DYN_SMEM(dec_i2t_layer_kernel, I2T_SMEM_BYTES, "dec_i2t_layer_kernel");
   I2TParams p;
   p.x_shared = a->x_shared ? 1 : 0;
-  p.gate = (!a->x_shared && !(getenv("CSAM_I2T_GATE") && atoi(getenv("CSAM_I2T_GATE")) == 0)) ? 1 : 0;
   p.tiles = a->P * 32;
-  p.x_hi = static_cast<const __half*>(a->x_hi); p.x_lo = static_cast<const __half*>(a->x_lo);
   p.bias = a->bias; p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps;
   p.out_hi = static_cast<__half*>(a->out_hi); p.out_lo = static_cast<__half*>(a->out_lo);
   int dev = 0, sms = 148;

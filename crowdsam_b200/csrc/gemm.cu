@@ -182,7 +182,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if constexpr (REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       if (WRES) {
         // this CTA's slice of the weight matrix, once: the grid is a multiple of tiles_n, so every tile of a
@@ -239,7 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if constexpr (REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, B_MN ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int local = 0;

@@ -136,7 +136,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constan
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int t = pair; t < num_tiles; t += num_pairs) {
         const int m0 = (t / tiles_n) * (2 * PM) + rank * PM;            // this CTA's 128 rows of A
@@ -158,7 +158,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (rank == 0 && lane == 0) {
+    if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_f16(2 * PM, PBN, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int local = 0;
