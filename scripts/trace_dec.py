@@ -19,15 +19,15 @@ L = lib.load()
 raw = C.CDLL(lib.LIB_PATH)
 raw.csam_debug_trace.restype = C.c_int
 raw.csam_debug_trace.argtypes = [C.c_void_p, C.c_int]
-buf = np.zeros(2 * 16384, dtype=np.uint64)
+TAGS, TILES = 160, 64
+buf = np.zeros(TAGS * TILES, dtype=np.uint64)
 
 
 def read():
-    n = raw.csam_debug_trace(buf.ctypes.data, 16384)
-    t = buf[0:2 * n:2].astype(np.int64)
-    tag = (buf[1:2 * n:2] >> np.uint64(32)).astype(np.int64)
-    val = (buf[1:2 * n:2] & np.uint64(0xffffffff)).astype(np.int64)
-    return t, tag, val
+    raw.csam_debug_trace(buf.ctypes.data, TAGS * TILES)
+    tab = buf.reshape(TAGS, TILES).astype(np.int64)
+    tag, val = np.nonzero(tab)
+    return tab[tag, val], tag, val
 
 
 xr = 4096 if shared else P * 4096
@@ -41,7 +41,7 @@ if which == "t2i":
     wv_t = wv.t().contiguous()
     run = lambda: o.dec_t2i(x, shared, pe, b1, P, wv_t, bv)
     names = {10: "x_empty0", 11: "x_empty1", 20: "x_full0", 21: "x_full1", 22: "x_full2", 23: "x_full3", 24: "pek_full0", 25: "pek_full1",
-             30: "p_full(mma)", 40: "sm_start", 41: "s_full(sm)", 42: "sm_viol_done", 43: "pv_done(sm)"}
+             **{50 + w: f"p_arrive w{w}" for w in range(16)}, **{70 + w: f"p_stored w{w}" for w in range(16)}, 30: "p_full(mma)", 40: "sm_start", 41: "s_full(sm)", 42: "sm_viol_done", 43: "pv_done(sm)"}
 else:
     kt, vt = torch.randn(P, 7, 128, device=dev), torch.randn(P, 7, 128, device=dev)
     wq, wo = torch.randn(128, 256, device=dev) * 0.08, torch.randn(256, 128, device=dev) * 0.1
