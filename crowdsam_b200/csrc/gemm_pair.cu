@@ -281,10 +281,13 @@ static int launch_pair_t(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t
 }
 
 int launch_gemm_pair(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st) {
-  // CSAM_GEMM_PAIR: 0 = never, 1 = 256-wide pair tiles whenever the problem qualifies, 2 = 128-wide pair tiles whenever
-  // it qualifies (experiment), unset = 256-wide where the wave model below favours them.
+  // CSAM_GEMM_PAIR: unset / 0 = never (default), 1 = 256-wide pair tiles whenever the problem qualifies, 2 = 128-wide
+  // pair tiles whenever it qualifies (experiment), 3 = 256-wide where the wave model below favours them (the default
+  // until the MMA-issue fix of round 2: with `elect.sync` role branches the single-CTA kernel issues its MMAs back to
+  // back and the whole step measured 45.2 ms without pair tiles, 45.7 ms with the wave model, 46.2 ms with pair tiles
+  // everywhere -- and CUDA-graph replay no longer pays the cluster-launch penalty).
   // impl == CSAM_GEMM_TC_PAIR in the arguments forces the 256-wide kernel (tests, A/B measurements).
-  static const int mode = getenv("CSAM_GEMM_PAIR") ? atoi(getenv("CSAM_GEMM_PAIR")) : -1;
+  static const int mode = getenv("CSAM_GEMM_PAIR") ? atoi(getenv("CSAM_GEMM_PAIR")) : 0;
   const bool forced = a->impl == CSAM_GEMM_TC_PAIR;
   if (mode == 0 && !forced) return -1;
   // qualifies: hi/lo split operands, K-major W, standard row-per-lane epilogue, whole k-blocks and pair tiles in N
@@ -302,7 +305,7 @@ int launch_gemm_pair(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st)
     if ((long long)tiles_m * (a->N / 128) * 2 < sms) return -1;
     return launch_pair_t<128>(a, e, st, tiles_m);
   }
-  if (!forced && mode != 1) {
+  if (!forced && mode == 3) {
     // Wave model (measured, round 2: the tensor pipe is ~70 % active inside a pair tile against ~55-60 % inside a
     // single-CTA 128x128 tile, but a pair tile is four of those, so the persistent grid of 74 pairs quantises much
     // coarser than 148 CTAs).  Time in units of one 128x128xK tile: pairs 2 per round, single CTAs 1 per round;

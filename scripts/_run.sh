@@ -1,4 +1,8 @@
-timeout 300 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "decoder_fused" 2>&1 | tail -3
-for pf in 0 1; do echo "t2i pf=$pf"; CSAM_T2I_PF=$pf timeout 100 python scripts/prof_t2i.py 1024 2>&1 | tail -1; done
-export CSAM_LIB_PATH=$PWD/crowdsam_b200/_C_trace/libcsam_sm100.so
-timeout 100 python scripts/trace_dec.py t2i 296 > gpurun_out/trace_t2i.txt 2>&1
+for cfg in "0 0" "1 0" "0 1"; do set -- $cfg
+CSAM_GEMM_BN256=$1 CSAM_GEMM_PAIR=$2 timeout 600 python bench.py --steps 8 --warmup 3 > gpurun_out/r3g.json 2> gpurun_out/r3g.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/r3g.json').read().strip().splitlines()[-1])
+print('BN256=$1 PAIR=$2', round(d['ms_per_step'],2), {k:round(v,2) for k,v in d['kernel_ms_per_step'].items() if k.startswith('gemm')})
+PY
+done
