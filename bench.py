@@ -435,7 +435,8 @@ def main():
                 "share_of_step": r["total_ms"] / prof_ms_total, "peak_source": peaks["source"]}
 
     roofs = [x for x in (roof("gemm_tensor", "tensor"), roof("gemm_hbm", "hbm"), roof("vit_attention", "tensor"),
-                         roof("dec_i2t_layer", "hbm"), roof("dec_t2i", "hbm"),
+                         roof("dec_i2t_layer", "hbm"), roof("dec_i2t_layer_shared", "hbm"),
+                         roof("dec_t2i", "hbm"), roof("dec_t2i_shared", "tensor"),
                          roof("mask_post_write", "hbm"), roof("mask_post_stats", "hbm")) if x]
     split_mode = os.environ.get("CSAM_PRECISION", "x3") != "x1"
     for r in roofs:

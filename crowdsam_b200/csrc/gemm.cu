@@ -128,7 +128,14 @@ struct GemmCfg {
                                     8 * 2048 /*per-warp staging tiles*/;
 };
 
-template <int BN, int SPLIT, bool B_MN, int EPI, bool WRES>
+// WIDE (128 x 128 tiles, hi/lo split, K-major W, EPI_STD direct): the three products of a k-step are issued as TWO
+// MMAs -- A_hi x [W_hi | W_lo] as one N = 256 operand (the two halves of a stage are contiguous: 128 hi rows, then
+// 128 lo rows) into accumulator columns [0,128) | [128,256), then A_lo x W_hi (N = 128) into [0,128) -- and the
+// epilogue adds the two column blocks.  Same tensor-pipe time (128 + 64 clocks), but A_hi is fetched from shared
+// memory once instead of twice: 20 KB of operand reads per k-step instead of 24 KB.  SS-mode MMAs of this shape are
+// bound by shared-memory bandwidth (128 B/clk: 24 KB of reads + 16 KB of TMA writes per 192 MMA clocks), see
+// scripts/micro/pattern.cu for the same trick measured in isolation (449 against 576 clocks per k-block at N = 64).
+template <int BN, int SPLIT, bool B_MN, int EPI, bool WRES, bool WIDE = false>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant__ CUtensorMap ta_lo,
                const __grid_constant__ CUtensorMap tw_hi, const __grid_constant__ CUtensorMap tw_lo,
@@ -136,6 +143,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
   using Cfg = GemmCfg<BN, SPLIT, WRES>;
   constexpr int STAGES = Cfg::STAGES;
   static_assert(!(WRES && B_MN), "resident weights are K-major only");
+  static_assert(!WIDE || (BN == 128 && SPLIT == 3 && !B_MN && EPI == EPI_STD && !WRES), "WIDE: encoder configuration only");
+  constexpr int ACC = WIDE ? 2 * BN : BN;            // TMEM columns of one accumulator buffer
+  constexpr int TCOLS = 2 * ACC;
   // Dynamic shared memory is the only shared allocation of this kernel, so it starts at the (1024-byte
   // aligned) base of the CTA's window; keeping `smem` a plain __shared__ array (no integer round-trip) lets
   // the compiler emit LDS/STS instead of generic LD/ST for every staging access.
@@ -166,7 +176,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
     mbar_init(w_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 2) tmem_alloc<TCOLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -249,7 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
         const uint32_t bphase = (local >> 1) & 1;
         mbar_wait(&tempty_bar[buf], bphase ^ 1);
         tc_fence_after();
-        const uint32_t d_addr = tmem_base + buf * BN;
+        const uint32_t d_addr = tmem_base + buf * ACC;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -261,6 +271,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
           constexpr uint32_t WSTEP = B_MN ? (2048 >> 4) : (32 >> 4);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
+            if constexpr (WIDE) {
+              constexpr uint32_t idesc_w = umma_idesc_f16(BM, 2 * BN, 0, 0);
+              umma_f16_w(d_addr, ad + 2 * k, wd + WSTEP * k, idesc_w, (kb | k) ? 1u : 0u);           // A_hi x [W_hi | W_lo]
+              umma_f16_w(d_addr, ad + (Cfg::A_BYTES >> 4) + 2 * k, wd + WSTEP * k, idesc, 1u);        // A_lo x W_hi
+              continue;
+            }
             umma_f16_w(d_addr, ad + 2 * k, wd + WSTEP * k, idesc, (kb | k) ? 1u : 0u);
             if (SPLIT == 3) {
               umma_f16_w(d_addr, ad + (Cfg::A_BYTES >> 4) + 2 * k, wd + WSTEP * k, idesc, 1u);
@@ -322,7 +338,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
         tc_fence_after();
       }
       const int r = m0 + q * 32 + lane;
-      const uint32_t col_addr = lane_addr + buf * BN + ch * HALF;
+      const uint32_t col_addr = lane_addr + buf * ACC + ch * HALF;
       float* wb = epi_smem + 1024 + ew * 512;          // this warp's 32x16 staging tile
       const int row_base = m0 + q * 32;                // tile rows of this warp: row_base + 0..31
       if constexpr (EPI == EPI_STD) {
@@ -359,7 +375,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
               if (col0 < e.N) {                          // warp-uniform (N is a multiple of 16 here)
                 uint32_t raw[16];
                 tmem_ld16(col_addr + part * PART + c, raw);
-                tmem_ld_wait();
+                if constexpr (WIDE) {
+                  uint32_t raw2[16];
+                  tmem_ld16(col_addr + BN + part * PART + c, raw2);      // the A_hi x W_lo block
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
+                } else {
+                  tmem_ld_wait();
+                }
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
@@ -387,6 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
           if (lane == 0) mbar_arrive(&tempty_bar[buf]);
           continue;
         }
+        if constexpr (WIDE) __trap();                    // launched with e.direct only
         mbar_wait(&tfull_bar[buf], bphase);
         tc_fence_after();
 #pragma unroll 1
@@ -655,7 +680,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  if (warp == 2) tmem_dealloc<TCOLS>(tmem_base);
 }
 
 // =========================================================================================
@@ -779,7 +804,7 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int SPLIT, bool B_MN, int EPI = EPI_STD, bool WRES = false>
+template <int BN, int SPLIT, bool B_MN, int EPI = EPI_STD, bool WRES = false, bool WIDE = false>
 static int launch_tc(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st) {
   using Cfg = GemmCfg<BN, SPLIT, WRES>;
   CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
@@ -795,7 +820,7 @@ static int launch_tc(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st)
     tw_lo = tw_hi;
     if (SPLIT == 3 && make_tmap_2d_f16(&tw_lo, a->w_lo, a->K, a->N, a->ldw, BK, 64)) return 1;
   }
-  auto kern = gemm_tc_kernel<BN, SPLIT, B_MN, EPI, WRES>;
+  auto kern = gemm_tc_kernel<BN, SPLIT, B_MN, EPI, WRES, WIDE>;
   CSAM_DYN_SMEM(kern, Cfg::SMEM_BYTES, "gemm_tc_kernel");
   const int tiles_m = (a->M + BM - 1) / BM;
   const int tiles_n = (a->N + BN - 1) / BN;
@@ -918,6 +943,11 @@ extern "C" int csam_gemm(const csam_gemm_args* a, void* stream) {
     const long long r128 = (tm * ((a->N + 127) / 128) + sms - 1) / sms, r256 = (tm * (a->N / 256) + sms - 1) / sms;
     (void)r128; (void)r256;
     if (mode == 1) return launch_tc<256, 3, false>(a, e, st);
+  }
+  if (split && e.direct) {
+    // CSAM_GEMM_WIDE=0 switches the two-MMA k-step off (A/B measurements)
+    static const int wide = getenv("CSAM_GEMM_WIDE") ? atoi(getenv("CSAM_GEMM_WIDE")) : 1;
+    if (wide) return launch_tc<128, 3, false, EPI_STD, false, true>(a, e, st);
   }
   return split ? launch_tc<128, 3, false>(a, e, st) : launch_tc<128, 1, false>(a, e, st);
 }

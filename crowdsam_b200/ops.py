@@ -347,7 +347,8 @@ def dec_i2t_layer(x: H16, x_shared: bool, peq: H16, b1: H16, b2: H16, P: int, bi
     tok = _pb()
     L.check(L.load().csam_dec_i2t_layer(C.byref(g), _stream()), "csam_dec_i2t_layer")
     # algorithmic bytes: read x (hi+lo) once, write x' once
-    _pe("dec_i2t_layer", tok, float(P) * 4096 * 256 * 4 * (1 if x_shared else 2))
+    # algorithmic bytes: the keys once in (unless all prompts share the 4096 input rows: layer 0) and once out
+    _pe("dec_i2t_layer_shared" if x_shared else "dec_i2t_layer", tok, float(P) * 4096 * 256 * 4 * (1 if x_shared else 2))
     return out
 
 
@@ -380,7 +381,12 @@ def dec_t2i(x: H16, x_shared: bool, pek: H16, b1: H16, P: int, wv_t: torch.Tenso
     g.out_hi, g.out_lo = (_p(oh.hi), _p(oh.lo)) if oh is not None else (None, None)
     tok = _pb()
     L.check(L.load().csam_dec_t2i(C.byref(g), _stream()), "csam_dec_t2i")
-    _pe("dec_t2i", tok, float(P) * 4096 * 256 * 4 * (0 if x_shared else 1))     # algorithmic bytes: the keys, once
+    if x_shared:
+        # layer 0: every prompt attends over the SAME 4096 keys (4 MB, L2-resident): no HBM stream to speak of, the
+        # launch is bound by its MMAs -- work = algorithmic flops of scores (K = 384) + pooling per key row
+        _pe("dec_t2i_shared", tok, float(P) * 4096 * (2 * 64 * 384 + 2 * 256 * 64))
+    else:
+        _pe("dec_t2i", tok, float(P) * 4096 * 256 * 4)     # algorithmic bytes: the keys, once
     return of, oh
 
 

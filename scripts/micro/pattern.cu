@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(128, 1) pat_kernel(int variant, int iters, lon
       for (int rep = 0; rep < 2; ++rep) {
         const long long t0 = clock64();
         for (int i = 0; i < iters; ++i) {
-          if (variant != 2) {
+          if (variant < 2 || variant == 3) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               umma_f16_w(tm, ah + 2 * k, bh + 2 * k, id64, 1u);
@@ -48,6 +48,22 @@ __global__ void __launch_bounds__(128, 1) pat_kernel(int variant, int iters, lon
               const uint32_t dr = tm + 128 + (i & 3) * 64;
               umma_f16_w(dr, ah + 2 * k, idd + 2 * k, id64, k ? 1u : 0u);
               umma_f16_w(dr, al + 2 * k, idd + 2 * k, id64, 1u);
+            }
+          }
+          if (variant == 5) {                          // 12 x N=64, A_hi used by two CONSECUTIVE MMAs (operand reuse?)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_f16_w(tm, ah + 2 * k, bh + 2 * k, id64, 1u);
+              umma_f16_w(tm, ah + 2 * k, bl + 2 * k, id64, 1u);
+              umma_f16_w(tm, al + 2 * k, bh + 2 * k, id64, 1u);
+            }
+          }
+          if (variant == 6) {                          // 8 MMAs: A_hi x [B_hi | B_lo] as N = 128, then A_lo x B_hi (N = 64)
+            constexpr uint32_t id128 = umma_idesc_f16(128, 128, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_f16_w(tm, ah + 2 * k, bh + 2 * k, id128, 1u);
+              umma_f16_w(tm, al + 2 * k, bh + 2 * k, id64, 1u);
             }
           }
           if (variant == 4) {                          // S alternating between two buffers every MMA
@@ -75,8 +91,9 @@ int main() {
   cudaFuncSetAttribute(pat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int iters = 512;
   const char* names[] = {"12 x N=64 (S only)", "12 x N=64 + 4 x {2 x N=16} residual", "4 x {2 x N=16} residual only",
-                         "12 x N=64 + 8 x N=64 residual (one block)", "8 x N=64 alternating two accumulators"};
-  for (int v = 0; v < 5; ++v) {
+                         "12 x N=64 + 8 x N=64 residual (one block)", "8 x N=64 alternating two accumulators",
+                         "12 x N=64, hh hl lh order (A_hi twice in a row)", "4 x {N=128 [Bh|Bl], N=64} = the same products in 8 MMAs"};
+  for (int v = 0; v < 7; ++v) {
     pat_kernel<<<148, 128, 200 * 1024>>>(v, iters, out);
     long long t = 0; cudaMemcpy(&t, out, 8, cudaMemcpyDeviceToHost);
     cudaError_t e = cudaGetLastError();
