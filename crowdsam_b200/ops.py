@@ -62,7 +62,15 @@ def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    # the raw handle of torch's current stream on the current device.  torch.cuda.current_stream() builds a Python
+    # Stream object through three helper layers (~15 us); with ~430 launches per image that was 6.6 ms of host time
+    # per image, in front of every launch
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
