@@ -58,7 +58,7 @@ constexpr int I2T_STAGE_BYTES = 2 * I2T_A_BYTES + 2 * I2T_B1_BYTES;   // 48 KB
 constexpr int I2T_B2_BYTES = 256 * 64 * 2;       // 32 KB per half
 constexpr int I2T_OFF_B2 = I2T_STAGES * I2T_STAGE_BYTES;
 constexpr int I2T_OFF_ID = I2T_OFF_B2 + 2 * I2T_B2_BYTES;    // 64 x 64 fp16 identity, K-major, 128B swizzle (8 KB)
-constexpr int I2T_TM_O = 128, I2T_TM_PH = 384, I2T_TM_PL = 416;   // TMEM columns: S0 S1 | O | P hi | P lo
+constexpr int I2T_TM_O = 128, I2T_TM_PH = 384, I2T_TM_PL = 416;   // TMEM columns: S (hi | lo part) | O | P hi | P lo
 constexpr int I2T_OFF_BAR = I2T_OFF_ID + 64 * 64 * 2;
 constexpr int I2T_OFF_EPI = I2T_OFF_BAR + 256;
 constexpr int I2T_SMEM_BYTES = I2T_OFF_EPI + (8 * 128 + 3 * 256) * 4;
@@ -137,7 +137,7 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = bars->tmem_slot;      // S0 [0,64) S1 [64,128) O [128,384)
+  const uint32_t tmem_base = bars->tmem_slot;      // S hi part [0,64) lo part [64,128) | O [128,384) | P hi [384,416) lo [416,448)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -193,13 +193,15 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
       constexpr uint32_t idesc1 = umma_idesc_f16(I2T_BM, 64, 0, 0);
       constexpr uint32_t idesc2 = umma_idesc_f16(I2T_BM, 256, 0, 0);
       constexpr uint32_t idesc_r = umma_idesc_f16(I2T_BM, 16, 0, 0);
+      constexpr uint32_t idesc1w = umma_idesc_f16(I2T_BM, 128, 0, 0);
       const uint32_t idd = umma_desc_lo(smem_u32(smem + I2T_OFF_ID), 16);
       int stage = 0; uint32_t phase = 0; int b2_cnt = 0;
       auto mma1 = [&](int li) {
-        const int b = li & 1;
-        mbar_wait(&bars->s_empty[b], ((li >> 1) & 1) ^ 1);
+        // ONE 128-column score buffer (hi part | lo part, see below): MMA1(li) is issued after MMA2(li-1), i.e. after
+        // the softmax of tile li-1 has long read it, so the second buffer of the earlier design bought nothing
+        mbar_wait(&bars->s_empty[0], (li & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + b * 64;
+        const uint32_t d = tmem_base;
         for (int i = 0; i < I2T_KB1; ++i) {
           const int kb = i2t_kb(i);
           mbar_wait(&bars->full[stage], phase);
@@ -208,11 +210,12 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
           const uint32_t sa = smem_u32(smem + stage * I2T_STAGE_BYTES);
           const uint32_t ad = umma_desc_lo(sa, 16);
           const uint32_t bd = umma_desc_lo(sa + 2 * I2T_A_BYTES, 16);
+          // two MMAs per k-step: X_hi x [B1_hi | B1_lo] as ONE N = 128 operand (the two halves of a stage's B1 block are
+          // contiguous) into S columns [0,64) | [64,128), then X_lo x B1_hi into [0,64); E1 adds the halves
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            umma_f16_w(d, ad + 2 * k, bd + 2 * k, idesc1, (i | k) ? 1u : 0u);
+            umma_f16_w(d, ad + 2 * k, bd + 2 * k, idesc1w, (i | k) ? 1u : 0u);
             umma_f16_w(d, ad + (I2T_A_BYTES >> 4) + 2 * k, bd + 2 * k, idesc1, 1u);
-            umma_f16_w(d, ad + 2 * k, bd + (I2T_B1_BYTES >> 4) + 2 * k, idesc1, 1u);
           }
           if (kb == 0) {
             // the residual MMAs overwrite O: tile li-1 must be drained.  Everything issued above (the positional part
@@ -234,7 +237,7 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
           umma_commit(&bars->empty[stage]);
           if (++stage == I2T_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&bars->s_full[b]);
+        umma_commit(&bars->s_full[0]);
       };
       if (t0 < t1) mma1(0);
       int li = 0;
@@ -285,17 +288,22 @@ dec_i2t_layer_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_con
 
     // E1: softmax over the 7 tokens of each of this thread's 2 heads -> P (hi/lo) in tensor memory
     auto softmax_tile = [&](int li) {
-      const int b = li & 1;
       if (warp == 4 && lane == 0) CSAM_TR(130, li);
-      mbar_wait(&bars->s_full[b], (li >> 1) & 1);
+      mbar_wait(&bars->s_full[0], li & 1);
       if (warp == 4 && lane == 0) CSAM_TR(131, li);
       tc_fence_after();
       uint32_t raw[16];
-      tmem_ld16(lane_addr + b * 64 + cq * 16, raw);
-      tmem_ld_wait();
+      {
+        uint32_t raw2[16];
+        tmem_ld16(lane_addr + cq * 16, raw);
+        tmem_ld16(lane_addr + 64 + cq * 16, raw2);         // the X_hi x B1_lo part of the scores
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) raw[c] = __float_as_uint(__uint_as_float(raw[c]) + __uint_as_float(raw2[c]));
+      }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->s_empty[b]);
+      if (lane == 0) mbar_arrive(&bars->s_empty[0]);
       uint32_t hi[8], lo[8];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -541,7 +549,7 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // S [0,64) | XBAR^T features 0..127: A [64,128) B [128,192) | features 128..255: A [192,256) B [256,320)
+  // S: hi part [0,64) + lo part [64,128) | XBAR^T features 0..127: A [128,192) B [192,256) | features 128..255: A [256,320) B [320,384)
   // (A collects X_hi^T P_hi + X_lo^T P_hi, B collects X_hi^T P_lo; their sum is formed once per prompt)
   const uint32_t tmem_base = bars->tmem_slot;
 
@@ -569,14 +577,16 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
               tma_load_2d(sx, &tx_hi, &bars->x_full[kb], kb * 64, arow);
               tma_load_2d(sx + 16384, &tx_lo, &bars->x_full[kb], kb * 64, arow);
             }
-            if (half == 0) {
-              // the NEXT tile of X goes to L2 now, so that its loads (which must wait for this tile's MMA2) are L2 hits
+            if (half == (a.pf == 2 ? 1 : 0)) {
+              // (experiments, CSAM_T2I_PF) 1: the NEXT tile of X goes to L2 now, so that its loads (which must wait for
+              // this tile's MMA2) are L2 hits; 2: only its first two k-blocks, the ones MMA1 waits for, requested after
+              // this tile's loads.  Default 0: no look-ahead measured fastest (1134 us; 1: 1184 us)
               int nrow = -1;
               if (ti + 1 < 32) nrow = arow + 128;
               else if (!a.x_shared && p + (int)gridDim.x < a.P) nrow = (p + (int)gridDim.x) * 4096;
               else if (a.x_shared && p + (int)gridDim.x < a.P) nrow = 0;
               if (nrow >= 0 && a.pf) {
-                for (int k2 = 0; k2 < 4; ++k2) {
+                for (int k2 = 0; k2 < (a.pf == 2 ? 2 : 4); ++k2) {
                   tma_prefetch_l2_2d(&tx_hi, k2 * 64, nrow);
                   tma_prefetch_l2_2d(&tx_lo, k2 * 64, nrow);
                 }
@@ -635,6 +645,7 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
       constexpr uint32_t idesc1 = umma_idesc_f16(128, 64, 0, 0);
       constexpr uint32_t idesc2 = umma_idesc_f16(128, 64, 1, 1);     // A = X^T and B = P, both MN-major
       constexpr uint32_t idesc2w = umma_idesc_f16(128, 128, 1, 1);
+      constexpr uint32_t idesc1w = umma_idesc_f16(128, 128, 0, 0);
       int bcnt = 0, pcnt = 0;
       int n_tiles_total = 0;
       for (int p = blockIdx.x; p < a.P; p += gridDim.x) n_tiles_total += 32;
@@ -663,11 +674,14 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
           tc_fence_after();
           const uint32_t ad = umma_desc_lo(sa, 16);
           const uint32_t bd = umma_desc_lo(sbb, 16);
+          // two MMAs per k-step: X_hi x [B1_hi | B1_lo] as ONE N = 128 operand (a B1 block is 64 hi rows followed by
+          // 64 lo rows) into S columns [0,64) | [64,128), then X_lo x B1_hi into [0,64); the softmax adds the two
+          // halves.  X_hi is fetched once instead of twice: 14 KB instead of 18 KB of shared-memory operand reads per
+          // step for a kernel that is bound by exactly that (449 against 576 clocks per k-block in isolation)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            umma_f16_w(tmem_base, ad + 2 * k, bd + 2 * k, idesc1, (i | k) ? 1u : 0u);
+            umma_f16_w(tmem_base, ad + 2 * k, bd + 2 * k, idesc1w, (i | k) ? 1u : 0u);
             umma_f16_w(tmem_base, ad + (16384 >> 4) + 2 * k, bd + 2 * k, idesc1, 1u);
-            umma_f16_w(tmem_base, ad + 2 * k, bd + (I2T_B1_BYTES >> 4) + 2 * k, idesc1, 1u);
           }
           if (i < 4) { umma_commit(&bars->b_empty[bs]); ++bcnt; }      // blocks 2,3 sit in the P buffer: freed by pv_done
           if (kb >= 4) { umma_commit(&bars->pek_empty); ++pcnt; }
@@ -708,7 +722,7 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
 #pragma unroll
         for (int fb = 0; fb < 2; ++fb) {
           const uint32_t xd = umma_desc_lo(smem_u32(smem + 2 * fb * T2I_SLOT), T2I_SLOT);   // LBO: next 64 features
-          const uint32_t d = tmem_base + 64 + fb * 128;
+          const uint32_t d = tmem_base + 128 + fb * 128;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {           // 16 keys per step = 16 rows of 128 B
             umma_f16_w(d, xd + 128 * k, pd2 + 128 * k, idesc2w, (ti | k) ? 1u : 0u);
@@ -735,7 +749,7 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
     const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
     const float* my_m = st_m + cq * 16;
     // accumulator work (rescale, final read-out): this warp owns lanes 32 wq.. of feature half cq >> 1
-    const uint32_t acc_addr = lane_addr + 64 + (cq >> 1) * 128;
+    const uint32_t acc_addr = lane_addr + 128 + (cq >> 1) * 128;
     int tl = 0;
     for (int p = blockIdx.x; p < a.P; p += gridDim.x) {
       float lsum[16];
@@ -747,8 +761,14 @@ dec_t2i_kernel(const __grid_constant__ CUtensorMap tx_hi, const __grid_constant_
         if (warp == 4 && lane == 0) CSAM_TR(41, tl);
         tc_fence_after();
         uint32_t raw[16];
-        tmem_ld16(lane_addr + cq * 16, raw);
-        tmem_ld_wait();
+        {
+          uint32_t raw2[16];
+          tmem_ld16(lane_addr + cq * 16, raw);
+          tmem_ld16(lane_addr + 64 + cq * 16, raw2);       // the X_hi x B1_lo part of the scores
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) raw[c] = __float_as_uint(__uint_as_float(raw[c]) + __uint_as_float(raw2[c]));
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->s_empty);

@@ -1,4 +1,1 @@
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r3i_bench.json 2> gpurun_out/r3i_bench.err
-tail -c 400 gpurun_out/r3i_bench.err
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+for pf in 0 2 0 2; do echo "pf=$pf"; CSAM_T2I_PF=$pf timeout 100 python scripts/prof_t2i.py 1024 2>&1 | tail -1; done
