@@ -47,7 +47,10 @@ struct AttnCfg {
   static constexpr int FIXED_BYTES = NQ * NOPS * Q_BYTES + NQ * PBUF * PNOPS * P_BYTES +
                                      (BIAS == 1 ? NQ * AT_BM * AT_REL_LD * 4 : 0) + 512 + 1024;
   static constexpr int STAGES_FIT = (227 * 1024 - FIXED_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+  // window blocks with ONE query tile per CTA (experiment, CSAM_ATTN_WIN_NQ=1): 4 key tiles in all, so a 2-stage ring is
+  // enough and two CTAs (256 TMEM columns, ~82 KB each) share an SM and overlap each other's serial chains.
+  // Measured: no gain (attention class 9.7 against 9.4 ms per step with the default two-tile CTAs)
+  static constexpr int STAGES = (BIAS == 1 && NQ == 1 && HD == 64) ? 2 : (STAGES_FIT > 8 ? 8 : STAGES_FIT);
   static_assert(STAGES >= 2, "attention K/V ring");
   static constexpr int OFF_KV = NQ * NOPS * Q_BYTES;
   static constexpr int OFF_P = OFF_KV + STAGES * STAGE_BYTES;
@@ -388,7 +391,10 @@ struct AttnTsCfg {
   static constexpr int STAGE_BYTES = NOPS * 2 * KV_TILE;
   static constexpr int REL_BYTES = (BIAS == 1) ? NQ * AT_BM * AT_REL_LD * 4 : 0;
   static constexpr int STAGES_FIT = (227 * 1024 - REL_BYTES - 512 - 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+  // window blocks with ONE query tile per CTA (experiment, CSAM_ATTN_WIN_NQ=1): 4 key tiles in all, so a 2-stage ring is
+  // enough and two CTAs (256 TMEM columns, ~82 KB each) share an SM and overlap each other's serial chains.
+  // Measured: no gain (attention class 9.7 against 9.4 ms per step with the default two-tile CTAs)
+  static constexpr int STAGES = (BIAS == 1 && NQ == 1 && HD == 64) ? 2 : (STAGES_FIT > 8 ? 8 : STAGES_FIT);
   static constexpr int OFF_REL = STAGES * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_REL + REL_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
