@@ -47,10 +47,7 @@ struct AttnCfg {
   static constexpr int FIXED_BYTES = NQ * NOPS * Q_BYTES + NQ * PBUF * PNOPS * P_BYTES +
                                      (BIAS == 1 ? NQ * AT_BM * AT_REL_LD * 4 : 0) + 512 + 1024;
   static constexpr int STAGES_FIT = (227 * 1024 - FIXED_BYTES) / STAGE_BYTES;
-  // window blocks with ONE query tile per CTA (experiment, CSAM_ATTN_WIN_NQ=1): 4 key tiles in all, so a 2-stage ring is
-  // enough and two CTAs (256 TMEM columns, ~82 KB each) share an SM and overlap each other's serial chains.
-  // Measured: no gain (attention class 9.7 against 9.4 ms per step with the default two-tile CTAs)
-  static constexpr int STAGES = (BIAS == 1 && NQ == 1 && HD == 64) ? 2 : (STAGES_FIT > 8 ? 8 : STAGES_FIT);
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static_assert(STAGES >= 2, "attention K/V ring");
   static constexpr int OFF_KV = NQ * NOPS * Q_BYTES;
   static constexpr int OFF_P = OFF_KV + STAGES * STAGE_BYTES;
@@ -391,9 +388,8 @@ struct AttnTsCfg {
   static constexpr int STAGE_BYTES = NOPS * 2 * KV_TILE;
   static constexpr int REL_BYTES = (BIAS == 1) ? NQ * AT_BM * AT_REL_LD * 4 : 0;
   static constexpr int STAGES_FIT = (227 * 1024 - REL_BYTES - 512 - 1024) / STAGE_BYTES;
-  // window blocks with ONE query tile per CTA (experiment, CSAM_ATTN_WIN_NQ=1): 4 key tiles in all, so a 2-stage ring is
-  // enough and two CTAs (256 TMEM columns, ~82 KB each) share an SM and overlap each other's serial chains.
-  // Measured: no gain (attention class 9.7 against 9.4 ms per step with the default two-tile CTAs)
+  // window blocks with ONE query tile per CTA (the default, see use_nq2): 4 key tiles in all, so a 2-stage ring is
+  // enough and two CTAs (256 TMEM columns, ~82 KB, <= 128 registers each) share an SM
   static constexpr int STAGES = (BIAS == 1 && NQ == 1 && HD == 64) ? 2 : (STAGES_FIT > 8 ? 8 : STAGES_FIT);
   static constexpr int OFF_REL = STAGES * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_REL + REL_BYTES;
@@ -411,7 +407,7 @@ struct AttnTsBars {
 };
 
 template <int SPLIT, int BIAS, int NQ, int HD>
-__global__ void __launch_bounds__(128 + 128 * NQ, 1)
+__global__ void __launch_bounds__(128 + 128 * NQ, (BIAS == 1 && NQ == 1 && HD == 64) ? 2 : 1)
 vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_constant__ CUtensorMap t_lo,
                         csam_attn_args a, const float* __restrict__ rel, int n_full, int n_single) {
   using Cfg = AttnTsCfg<SPLIT, BIAS, NQ, HD>;
@@ -761,7 +757,11 @@ static bool use_nq2(const csam_attn_args* a, int bias) {
   static const int env = getenv("CSAM_ATTN_NQ") ? atoi(getenv("CSAM_ATTN_NQ")) : 0;
   static const int env_win = getenv("CSAM_ATTN_WIN_NQ") ? atoi(getenv("CSAM_ATTN_WIN_NQ")) : 0;
   if (a->tokens <= AT_BM) return false;
-  if (bias == 1) return env_win != 1;      // window blocks: 196 tokens = exactly the two query tiles of one CTA
+  // window blocks (196 tokens = two query tiles): ONE tile per CTA with a 2-stage ring, so that two CTAs share an SM
+  // and overlap each other's load -> S -> softmax -> PV chains (4 key tiles per CTA: the chain, not the MMAs, is what a
+  // window CTA spends its time on).  Measured: attention class 9.08 / 9.07 against 9.23 / 9.43 ms per step for
+  // two-tile CTAs (CSAM_ATTN_WIN_NQ=2 selects those).
+  if (bias == 1) return env_win == 2;
   return env != 1;
 }
 
