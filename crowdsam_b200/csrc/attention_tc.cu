@@ -387,11 +387,15 @@ struct AttnTsCfg {
   static constexpr int KV_TILE = NA * AT_BN * 64 * 2;        // 8 KB per atom
   static constexpr int STAGE_BYTES = NOPS * 2 * KV_TILE;
   static constexpr int REL_BYTES = (BIAS == 1) ? NQ * AT_BM * AT_REL_LD * 4 : 0;
-  static constexpr int STAGES_FIT = (227 * 1024 - REL_BYTES - 512 - 1024) / STAGE_BYTES;
+  // window blocks, head dim 64: the decomposed rel-pos terms q . Rh[qh - kh + 13], q . Rw[qw - kw + 13] are computed IN the
+  // kernel, as one small TS-mode MMA per query tile against both tables (27 + 27 rows of 64, hi | lo, K-major SW128)
+  static constexpr int TAB_BYTES = (BIAS == 1 && HD == 64) ? 2 * 8192 : 0;
+  static constexpr int STAGES_FIT = (227 * 1024 - REL_BYTES - TAB_BYTES - 512 - 1024) / STAGE_BYTES;
   // window blocks with ONE query tile per CTA (the default, see use_nq2): 4 key tiles in all, so a 2-stage ring is
   // enough and two CTAs (256 TMEM columns, ~82 KB, <= 128 registers each) share an SM
   static constexpr int STAGES = (BIAS == 1 && NQ == 1 && HD == 64) ? 2 : (STAGES_FIT > 8 ? 8 : STAGES_FIT);
-  static constexpr int OFF_REL = STAGES * STAGE_BYTES;
+  static constexpr int OFF_TAB = STAGES * STAGE_BYTES;        // 1024-byte aligned (stages are multiples of 16 KB)
+  static constexpr int OFF_REL = OFF_TAB + TAB_BYTES;
   static constexpr int OFF_BAR = OFF_REL + REL_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
   // TMEM columns per query tile: S0 | P0 [0,64)  S1 | P1 [64,128)  O [128,128+HD)  Q hi  Q lo (HD/2 columns each)
@@ -403,6 +407,7 @@ struct AttnTsCfg {
 struct AttnTsBars {
   uint64_t kv_full[8], kv_empty[8];
   uint64_t q_ready[2], s_full[2][2], p_full[2][2], pv_done[2][2];   // [query tile]([key tile parity])
+  uint64_t rel_full[2], rel_done[2];                                // in-kernel rel-pos terms: computed / read back
   uint32_t tmem_slot;
 };
 
@@ -444,6 +449,8 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
     for (int s = 0; s < STAGES; ++s) { mbar_init(&bars->kv_full[s], 1); mbar_init(&bars->kv_empty[s], 1); }
     for (int t = 0; t < NQ; ++t) {
       mbar_init(&bars->q_ready[t], 4);
+      mbar_init(&bars->rel_full[t], 1);
+      mbar_init(&bars->rel_done[t], 4);
       for (int b = 0; b < 2; ++b) {
         mbar_init(&bars->s_full[t][b], 1);
         mbar_init(&bars->p_full[t][b], 4);
@@ -453,6 +460,25 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(&bars->tmem_slot);
+  // rel == nullptr on a window launch: the rel-pos terms are computed here (see MMA issuer #1) instead of being read
+  // from a precomputed [groups * heads * tokens, 28] array (relpos_win14_kernel: 39 us per layer, 20 layers)
+  const bool rel_inkernel = (BIAS == 1) && Cfg::TAB_BYTES > 0 && rel == nullptr;
+  if (rel_inkernel) {
+    // B operand [64 rows = 27 of Rh | 27 of Rw | 10 zero][K = 64], hi then lo, 128B-swizzled K-major
+    uint8_t* tab = smem + Cfg::OFF_TAB;
+    for (int i = threadIdx.x; i < 64 * 64; i += Cfg::THREADS) {
+      const int n = i >> 6, k = i & 63;
+      float v = 0.f;
+      if (n < 27) v = a.rel_h[n * 64 + k];
+      else if (n < 54) v = a.rel_w[(n - 27) * 64 + k];
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      const int off = n * 128 + ((((k >> 3) ^ (n & 7))) << 4) + (k & 7) * 2;
+      *reinterpret_cast<__half*>(tab + off) = hi;
+      *reinterpret_cast<__half*>(tab + 8192 + off) = lo;
+    }
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -487,6 +513,26 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
       for (int t = 0; t < NQ; ++t)
         if (t < nqa) mbar_wait(&bars->q_ready[t], 0);
       tc_fence_after();
+      if (rel_inkernel) {
+        // T[128 queries, 64] = Q (tensor memory) x [Rh ; Rw]^T into the S1 columns, which the main loop does not touch
+        // before S(1): the softmax threads pick their 14 + 14 terms out of it and release it through rel_done
+        const uint32_t td = umma_desc_lo(smem_u32(smem + Cfg::OFF_TAB), 16);
+#pragma unroll
+        for (int t = 0; t < NQ; ++t) {
+          if (t >= nqa) break;
+          const uint32_t d = tmem_base + t * TS + AT_BN;
+          const uint32_t qa = tmem_base + t * TS + Cfg::COL_QH;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_f16_ts(d, qa + 8 * k, td + 2 * k, idesc_s, k ? 1u : 0u);
+            if (SPLIT == 3) {
+              umma_f16_ts(d, qa + HD / 2 + 8 * k, td + 2 * k, idesc_s, 1u);
+              umma_f16_ts(d, qa + 8 * k, td + (8192 >> 4) + 2 * k, idesc_s, 1u);
+            }
+          }
+          umma_commit(&bars->rel_full[t]);
+        }
+      }
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % STAGES;
         mbar_wait(&bars->kv_full[st], (j / STAGES) & 1);
@@ -496,6 +542,7 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
           if (t >= nqa) break;
           // S(j) overwrites the buffer that held S(j-2) and then P(j-2): P V(j-2) must have retired
           if (j >= 2) mbar_wait(&bars->pv_done[t][j & 1], ((j - 2) >> 1) & 1);
+          if (j == 1 && rel_inkernel) mbar_wait(&bars->rel_done[t], 0);     // the rel-pos terms have been read out of S1
           tc_fence_after();
           const uint32_t d = tmem_base + t * TS + (j & 1) * AT_BN;
           const uint32_t qa = tmem_base + t * TS + Cfg::COL_QH;
@@ -575,12 +622,35 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
     float relw[BIAS == 2 ? 64 : 1];
     const float* relq = nullptr;
     float* rel_r = rel_s + (qt * AT_BM + r) * AT_REL_LD;
-    if (BIAS != 0) relq = rel + (((size_t)g * a.heads + h) * a.tokens + qc) * 2 * a.S;
+    if (BIAS != 0 && !rel_inkernel) relq = rel + (((size_t)g * a.heads + h) * a.tokens + qc) * 2 * a.S;
     if (BIAS == 2) {
 #pragma unroll
       for (int c = 0; c < 64; ++c) relw[c] = relq[64 + c] * LOG2E;
     }
-    if (BIAS == 1) {
+    if (BIAS == 1 && rel_inkernel) {
+      // this row's 54 products q . Rh[n], q . Rw[n] out of tensor memory; the 14 + 14 it needs are
+      // Rh[qh - kh + 13] and Rw[qw - kw + 13] (image_encoder.py get_rel_pos / add_decomposed_rel_pos)
+      float tv[64];
+      {
+        uint32_t t0[32], t1[32];
+        mbar_wait(&bars->rel_full[qt], 0);
+        tc_fence_after();
+        tmem_ld32(lane_addr + AT_BN, t0);
+        tmem_ld32(lane_addr + AT_BN + 32, t1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->rel_done[qt]);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) { tv[c] = __uint_as_float(t0[c]); tv[32 + c] = __uint_as_float(t1[c]); }
+      }
+      const int qh = qc / 14, qw = qc % 14;
+#pragma unroll 1
+      for (int k = 0; k < 14; ++k) {
+        rel_r[k] = tv[qh - k + 13] * LOG2E;             // dynamic index: tv lives in local memory, once per CTA
+        rel_r[14 + k] = tv[27 + qw - k + 13] * LOG2E;
+      }
+    } else if (BIAS == 1) {
       float4 t4[7];
 #pragma unroll
       for (int i = 0; i < 7; ++i) t4[i] = *reinterpret_cast<const float4*>(relq + 4 * i);
@@ -776,9 +846,17 @@ int vit_attention_tc(const csam_attn_args* a, cudaStream_t st) {
   const float* rel = nullptr;
   if (a->rel_h) {
     CSAM_REQUIRE(a->S == 14 || a->S == 64, "csam_vit_attention(tcgen05): S must be 14 (window) or 64 (global)");
-    if (compute_relpos(a, st)) return 1;
-    rel = a->scratch;
     bias = a->S == 14 ? 1 : 2;
+    // window blocks with head dim 64 on the TS kernel compute their rel-pos terms themselves (rel stays nullptr)
+    static const int rel_env = getenv("CSAM_ATTN_REL_INKERNEL") ? atoi(getenv("CSAM_ATTN_REL_INKERNEL")) : 1;
+    const bool al32q = (reinterpret_cast<uintptr_t>(a->qkv_hi) & 31) == 0 && (a->ld_qkv % 16) == 0 &&
+                       (!split || (reinterpret_cast<uintptr_t>(a->qkv_lo) & 31) == 0);
+    static const int ts_env0 = getenv("CSAM_ATTN_TS") ? atoi(getenv("CSAM_ATTN_TS")) : 1;
+    const bool inkernel = rel_env && bias == 1 && a->hd == 64 && a->tokens == 196 && ts_env0 && al32q && !(split && a->p_split);
+    if (!inkernel) {
+      if (compute_relpos(a, st)) return 1;
+      rel = a->scratch;
+    }
   }
   {
     // Q / P in tensor memory (default): needs 32-byte aligned Q rows for the row copy; p_split keeps the SS kernel
