@@ -444,7 +444,9 @@ def main():
             # achieved counts ALGORITHMIC flops; in the hi/lo split mode the tensor cores execute 3 MMAs per
             # algorithmic GEMM MMA (hi*hi + lo*hi + hi*lo) and 2.5 per attention MMA (QK^T x3, P*V x2: the
             # probabilities are a single fp16), so the pipe is that much busier than `frac` says
-            r["mma_multiplier"] = (2.5 if r["kernel"] == "vit_attention" else 3) if split_mode else 1
+            from crowdsam_b200 import ops as _ops
+            attn_mult = {1: 3.0, 0: 2.5}.get(_ops.ATTN_PSPLIT, 2.0)     # P*V as 3 / 2 / 1 MMAs (ops.ATTN_PSPLIT)
+            r["mma_multiplier"] = (attn_mult if r["kernel"] == "vit_attention" else 3) if split_mode else 1
             r["frac_executed"] = r["frac"] * r["mma_multiplier"]
         t = traffic.get(r["kernel"])
         if t:

@@ -463,6 +463,9 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
   // rel == nullptr on a window launch: the rel-pos terms are computed here (see MMA issuer #1) instead of being read
   // from a precomputed [groups * heads * tokens, 28] array (relpos_win14_kernel: 39 us per layer, 20 layers)
   const bool rel_inkernel = (BIAS == 1) && Cfg::TAB_BYTES > 0 && rel == nullptr;
+  // p_split < 0: V enters P V as ONE fp16 (no V_lo load, one MMA per k-step instead of two).  P is a single fp16 already,
+  // so the product carries 2^-12 relative per factor instead of per probability only
+  const bool v_lo = (SPLIT == 3) && a.p_split >= 0;
   if (rel_inkernel) {
     // B operand [64 rows = 27 of Rh | 27 of Rw | 10 zero][K = 64], hi then lo, 128B-swizzled K-major
     uint8_t* tab = smem + Cfg::OFF_TAB;
@@ -492,7 +495,7 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
         mbar_wait(&bars->kv_empty[st], ((j / STAGES) & 1) ^ 1);
         uint8_t* sk = smem + st * Cfg::STAGE_BYTES;
         uint8_t* sv = sk + Cfg::NOPS * Cfg::KV_TILE;
-        mbar_expect_tx(&bars->kv_full[st], Cfg::STAGE_BYTES);
+        mbar_expect_tx(&bars->kv_full[st], v_lo ? Cfg::STAGE_BYTES : Cfg::STAGE_BYTES - (Cfg::NOPS - 1) * Cfg::KV_TILE);
         const int row = row_base + j * AT_BN;
 #pragma unroll
         for (int at = 0; at < Cfg::NA; ++at) {      // head dim 80: a second 64-wide box of which 16 columns are used
@@ -500,7 +503,7 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
           tma_load_2d(sv + at * 8192, &t_hi, &bars->kv_full[st], 2 * D + h * HD + at * 64, row);
           if (SPLIT == 3) {
             tma_load_2d(sk + Cfg::KV_TILE + at * 8192, &t_lo, &bars->kv_full[st], D + h * HD + at * 64, row);
-            tma_load_2d(sv + Cfg::KV_TILE + at * 8192, &t_lo, &bars->kv_full[st], 2 * D + h * HD + at * 64, row);
+            if (v_lo) tma_load_2d(sv + Cfg::KV_TILE + at * 8192, &t_lo, &bars->kv_full[st], 2 * D + h * HD + at * 64, row);
           }
         }
       }
@@ -577,7 +580,7 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
 #pragma unroll
           for (int k = 0; k < AT_BN / 16; ++k) {
             umma_f16_ts(d, pa + 8 * k, vd + 128 * k, idesc_pv, (j | k) ? 1u : 0u);
-            if (SPLIT == 3) umma_f16_ts(d, pa + 8 * k, vd + (Cfg::KV_TILE >> 4) + 128 * k, idesc_pv, 1u);
+            if (SPLIT == 3 && v_lo) umma_f16_ts(d, pa + 8 * k, vd + (Cfg::KV_TILE >> 4) + 128 * k, idesc_pv, 1u);
           }
           umma_commit(&bars->pv_done[t][b]);
         }
@@ -852,7 +855,7 @@ int vit_attention_tc(const csam_attn_args* a, cudaStream_t st) {
     const bool al32q = (reinterpret_cast<uintptr_t>(a->qkv_hi) & 31) == 0 && (a->ld_qkv % 16) == 0 &&
                        (!split || (reinterpret_cast<uintptr_t>(a->qkv_lo) & 31) == 0);
     static const int ts_env0 = getenv("CSAM_ATTN_TS") ? atoi(getenv("CSAM_ATTN_TS")) : 1;
-    const bool inkernel = rel_env && bias == 1 && a->hd == 64 && a->tokens == 196 && ts_env0 && al32q && !(split && a->p_split);
+    const bool inkernel = rel_env && bias == 1 && a->hd == 64 && a->tokens == 196 && ts_env0 && al32q && !(split && a->p_split > 0);
     if (!inkernel) {
       if (compute_relpos(a, st)) return 1;
       rel = a->scratch;
@@ -865,7 +868,7 @@ int vit_attention_tc(const csam_attn_args* a, cudaStream_t st) {
                       (!split || (reinterpret_cast<uintptr_t>(a->qkv_lo) & 31) == 0);
     if (a->hd == 80) {
       // ViT-H: one query tile per CTA (TMEM: 128 + 80 + 80 columns), K / V tiles of two swizzle atoms
-      CSAM_REQUIRE(al32 && !(split && a->p_split), "csam_vit_attention(tcgen05): head dim 80 needs 32-byte aligned rows, no p_split");
+      CSAM_REQUIRE(al32 && !(split && a->p_split > 0), "csam_vit_attention(tcgen05): head dim 80 needs 32-byte aligned rows, no p_split");
       if (split) {
         if (bias == 0) return launch_attn_ts<3, 0, 1, 80>(a, rel, st);
         if (bias == 1) return launch_attn_ts<3, 1, 1, 80>(a, rel, st);
@@ -875,7 +878,7 @@ int vit_attention_tc(const csam_attn_args* a, cudaStream_t st) {
       if (bias == 1) return launch_attn_ts<1, 1, 1, 80>(a, rel, st);
       return launch_attn_ts<1, 2, 1, 80>(a, rel, st);
     }
-    if (ts_env && al32 && !(split && a->p_split)) {
+    if (ts_env && al32 && !(split && a->p_split > 0)) {
       const bool nq2 = use_nq2(a, bias) && bias != 2;
       if (split) {
         if (bias == 0) return nq2 ? launch_attn_ts<3, 0, 2>(a, rel, st) : launch_attn_ts<3, 0, 1>(a, rel, st);
@@ -887,7 +890,7 @@ int vit_attention_tc(const csam_attn_args* a, cudaStream_t st) {
       return launch_attn_ts<1, 2, 1>(a, rel, st);
     }
   }
-  if (split && a->p_split) {
+  if (split && a->p_split > 0) {
     if (bias == 0) return launch_attn_tc<3, 0, true, 1>(a, rel, st);
     if (bias == 1) return launch_attn_tc<3, 1, true, 1>(a, rel, st);
     return launch_attn_tc<3, 2, true, 1>(a, rel, st);

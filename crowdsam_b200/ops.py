@@ -245,7 +245,7 @@ def vit_attention(qkv: H16, groups: int, tokens: int, heads: int, hd: int, scale
         a.scratch, a.scratch_bytes = _p(_attn_scratch[key]), need
     a.impl = ATTN_IMPL if impl is None else impl
     a.p_split = ATTN_PSPLIT if p_split is None else int(p_split)
-    if impl is None and (hd not in (64, 80) or (hd == 80 and a.p_split)):
+    if impl is None and (hd not in (64, 80) or (hd == 80 and a.p_split > 0)):
         a.impl = 1          # CUDA-core flash kernel; the tcgen05 kernels take head dim 64 and (without p_split) 80
     tok = _pb()
     L.check(L.load().csam_vit_attention(C.byref(a), _stream()), "csam_vit_attention")

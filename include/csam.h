@@ -134,7 +134,8 @@ typedef struct {
   float* scratch; long long scratch_bytes;   /* >= csam_vit_attention_scratch_bytes() */
   int impl;
   int p_split;   /* tcgen05 path: 1 = softmax probabilities also as hi+lo pair (3 MMAs for P*V); 0 = P as one
-                    fp16 (2 MMAs, relative error 2^-12 per probability) */
+                    fp16 (2 MMAs, relative error 2^-12 per probability); -1 = P and V each as one fp16 (1 MMA, no
+                    V_lo load; 2^-12 per probability and per value) */
 } csam_attn_args;
 CSAM_API long long csam_vit_attention_scratch_bytes(int groups, int tokens, int heads, int hd, int S);
 CSAM_API int csam_vit_attention(const csam_attn_args* a, void* stream);
