@@ -45,6 +45,58 @@ def _f(sd: SD, name: str, dev) -> torch.Tensor:
     return sd[name].detach().float().contiguous().to(dev)
 
 
+def run_steps(gen):
+    """Exhaust a `forward_steps` generator on the current stream and return its result."""
+    while True:
+        try:
+            next(gen)
+        except StopIteration as stop:
+            return stop.value
+
+
+_side_streams: Dict[int, "torch.cuda.Stream"] = {}
+_ORDER = (0, 1) if os.environ.get("CSAM_SIDE_FIRST", "1") == "0" else (1, 0)
+
+
+def two_streams_enabled() -> bool:
+    """The SAM encoder and the DINOv2 encoder of an image are independent until the decoder binds both
+    (predictor.py:88-110 runs them back to back).  Default: enqueue them on two streams so that each fills the other's
+    idle SMs -- last partial waves of the N = 1024 GEMMs (2.1-2.3 waves of tiles on 148 SMs), LayerNorm launches, kernel
+    ramps.  CSAM_TWO_STREAMS=0 keeps one stream.  Not used while a kernel-class profiler is timing launches (per-launch
+    event times are only meaningful serialised)."""
+    return os.environ.get("CSAM_TWO_STREAMS", "1") != "0" and ops.PROFILER is None
+
+
+def interleave_two_streams(gen_main, gen_side, dev):
+    """Drive two `forward_steps` generators, `gen_main` on the current stream and `gen_side` on a per-device side stream,
+    alternating block by block so that both streams stay fed; the current stream waits for the side stream at the end.
+    -> (result_main, result_side).  Tensors the side generator returns were allocated on the side stream: the caller
+    must `record_stream` them on the stream that consumes them."""
+    main = torch.cuda.current_stream(dev)
+    idx = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    side = _side_streams.get(idx)
+    if side is None:
+        side = _side_streams[idx] = torch.cuda.Stream(device=dev, priority=int(os.environ.get("CSAM_SIDE_PRIO", "0")))
+    side.wait_stream(main)
+    res = [None, None]
+    live = [True, True]
+    gens = (gen_main, gen_side)
+    while live[0] or live[1]:
+        for k in _ORDER:                        # side first: its result is needed last
+            if not live[k]:
+                continue
+            try:
+                if k == 1:
+                    with torch.cuda.stream(side):
+                        next(gens[k])
+                else:
+                    next(gens[k])
+            except StopIteration as stop:
+                res[k], live[k] = stop.value, False
+    main.wait_stream(side)
+    return res[0], res[1]
+
+
 # ============================================================================================
 # SAM ViT image encoder                       (segment_anything_cs/modeling/image_encoder.py)
 # ============================================================================================
@@ -90,10 +142,17 @@ class SamEncoder:
     def forward(self, img_u8_chw: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """uint8 [3,h,w] on device -> (features fp32 [1,256,64,64], token-major fp32 [4096,256]).
         ImageEncoderViT.forward (image_encoder.py:106-116) fused with Sam.preprocess (sam.py:163-173)."""
+        return run_steps(self.forward_steps(img_u8_chw))
+
+    def forward_steps(self, img_u8_chw: torch.Tensor):
+        """forward() as a generator that yields after every transformer block (its launches are enqueued on the stream
+        that is current when the generator is resumed) and returns the result: lets a caller interleave the launches of
+        two independent encoders on two streams (`interleave_two_streams`)."""
         D, heads, hd, split = self.D, self.heads, self.hd, self.split
         patches = ops.patchify(img_u8_chw, 16, 64, 0, 768, split)
         x, _ = self.patch(patches, residual=self.pos, want_f32=True)
         for i, blk in enumerate(self.blocks):
+            yield
             is_glob = i in self.glob
             if is_glob:
                 _, y, _ = ops.layernorm(x, blk["n1w"], blk["n1b"], 1e-6, want_h16=True, split=split)
@@ -153,6 +212,10 @@ class DinoEncoder:
     def forward(self, img_u8_chw: torch.Tensor) -> Tuple[torch.Tensor, H16]:
         """-> (x_norm_patchtokens fp32 [5329, D], same as h16 pair).  predictor.py:104-106: the
         SAM-normalised zero-padded image is resized bilinearly to 1022x1022 inside patchify."""
+        return run_steps(self.forward_steps(img_u8_chw))
+
+    def forward_steps(self, img_u8_chw: torch.Tensor):
+        """forward() as a generator yielding after every block (see SamEncoder.forward_steps)."""
         D, heads, hd, split = self.D, self.heads, self.hd, self.split
         n = 73 * 73
         patches = ops.patchify(img_u8_chw, 14, 73, 1022, 592, split)
@@ -160,6 +223,7 @@ class DinoEncoder:
         x[:1].copy_(self.cls_row)
         self.patch(patches, residual=self.pos_patch, out_f32=x[1:])
         for blk in self.blocks:
+            yield
             _, y, _ = ops.layernorm(x, blk["n1w"], blk["n1b"], 1e-6, want_h16=True, split=split)
             _, qkv = blk["qkv"](y, want_h16=True)
             a = ops.vit_attention(qkv, 1, n + 1, heads, hd, hd ** -0.5)

@@ -15,8 +15,10 @@ ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 # GEMM / attention implementation switches (validation only): 0 = tcgen05, 1 = SIMT
 GEMM_IMPL = int(os.environ.get("CSAM_GEMM_IMPL", "0"))
 ATTN_IMPL = int(os.environ.get("CSAM_ATTN_IMPL", "0"))
-# 1: softmax probabilities as hi+lo pair too (bit-for-bit closest to fp32, ~40% slower attention)
-ATTN_PSPLIT = int(os.environ.get("CSAM_ATTN_PSPLIT", "0"))
+# P V of the ViT attention: -1 (default) = probabilities and values each as ONE fp16 (one MMA per k-step; measured end to end
+# against the oracle: features 1.1e-5, class logits 1.3e-4 relative, the same as mode 0 to within 2e-6); 0 = values as hi+lo
+# pair (two MMAs); 1 = probabilities as hi+lo pair too (three MMAs, SS-mode kernel, ~40% slower attention)
+ATTN_PSPLIT = int(os.environ.get("CSAM_ATTN_PSPLIT", "-1"))
 
 
 class Profiler:

@@ -107,7 +107,7 @@ class CrowdSAM:
         self.image, self.downscale = resize_image(image[y0:y1, x0:x1, :], self.max_size)
 
     def _generate_masks(self, image) -> MaskData:
-        img_size = np.array(image).shape[:2]
+        img_size = np.asarray(image).shape[:2]          # (a view for ndarray input; the reference copies 3 MB here)
         crop_boxes, _ = amg.generate_crop_boxes(img_size, self.crop_n_layers, self.crop_overlap_ratio)
         data = MaskData()
         for crop_box in crop_boxes:

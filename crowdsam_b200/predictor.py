@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import numpy as np
 import torch
 
-from . import graphs, ops
+from . import engine, graphs, ops
 from .ops import H16
 from .transforms import ResizeLongestSide
 
@@ -52,11 +52,23 @@ class SamPredictor:
     def _encode_bind(enc, dino_eng, eng, img_u8: torch.Tensor):
         """Both encoders + the prompt-independent decoder work for one image: the region that is replayed as ONE
         CUDA graph (static shapes, ~380 launches, no host sync).  Returns (features, dino_feats, engine image state)."""
-        feats, feat_tok = enc.forward(img_u8)
         dino_feats, dino_h = None, None
-        if dino_eng is not None:
-            dino_f32, dino_h = dino_eng.forward(img_u8)
+        if dino_eng is not None and engine.two_streams_enabled() and not graphs.usable():
+            # two independent encoders on two streams (engine.two_streams_enabled); the DINOv2 outputs are allocated on
+            # the side stream and consumed on this one
+            (feats, feat_tok), (dino_f32, dino_h) = engine.interleave_two_streams(
+                enc.forward_steps(img_u8), dino_eng.forward_steps(img_u8), img_u8.device)
+            cur = torch.cuda.current_stream(img_u8.device)
+            for t in (dino_f32, dino_h.hi, dino_h.lo):
+                if t is not None:
+                    t.record_stream(cur)
+            img_u8.record_stream(engine._side_streams[img_u8.device.index])
             dino_feats = dino_f32.view(1, 73, 73, -1)
+        else:
+            feats, feat_tok = enc.forward(img_u8)
+            if dino_eng is not None:
+                dino_f32, dino_h = dino_eng.forward(img_u8)
+                dino_feats = dino_f32.view(1, 73, 73, -1)
         eng.set_image(feat_tok, dino_h)
         return feats, dino_feats, eng.img
 

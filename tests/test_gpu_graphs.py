@@ -114,3 +114,30 @@ def test_two_predictors_sharing_a_model():
         for x, y in zip(got, want):
             assert (x - y).abs().max() <= 1e-4 * y.abs().max()
         a.set_image(im_a)
+
+
+def test_two_stream_encoders_equal_one_stream(monkeypatch):
+    """SAM encoder and DINOv2 on two streams (engine.interleave_two_streams, the default) give bit-identical features,
+    DINOv2 tokens and decoder outputs to the single-stream launch order, image after image (the side stream's buffers
+    are recycled between images)."""
+    from crowdsam_b200 import engine, graphs
+
+    graphs.ENABLED = False
+    pred = _fresh_predictor()
+    imgs = [weights.synthetic_image(40 + i) for i in range(3)]
+    runs = {}
+    for mode in ("0", "1", "0"):
+        monkeypatch.setenv("CSAM_TWO_STREAMS", mode)
+        assert engine.two_streams_enabled() == (mode == "1")
+        out = []
+        for im in imgs:
+            pred.set_image(im)
+            c, l = _prompts(pred)
+            low, iou, cls = pred.decode_low_res(c, l)
+            out.append((pred.features.clone(), pred.dino_feats.clone(), low.clone(), iou.clone(), cls.clone()))
+        runs.setdefault(mode, []).append(out)
+    torch.cuda.synchronize()
+    for other in (runs["1"][0], runs["0"][1]):
+        for got, want in zip(other, runs["0"][0]):
+            for a, b in zip(got, want):
+                assert torch.equal(a, b)
