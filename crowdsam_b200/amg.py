@@ -222,17 +222,29 @@ def _coco_string(counts: Sequence[int]) -> str:
     return out.tobytes().decode("ascii")
 
 
+_PYCOCO = None
+
+
+def _have_pycocotools() -> bool:
+    """Probed once: a failing `import pycocotools` walks every sys.path entry again on each attempt (~0.2 ms per image)."""
+    global _PYCOCO
+    if _PYCOCO is None:
+        try:
+            from pycocotools import mask as mask_utils  # type: ignore  # noqa: F401
+
+            _PYCOCO = True
+        except ImportError:
+            _PYCOCO = False
+    return _PYCOCO
+
+
 def coco_encode_rles(rles: List[Dict[str, Any]]) -> List[Dict[str, Any]]:
     """coco_encode_rle for a whole list in ONE library call (csam_coco_rle_strings, host C): the per-mask interpreter
     overhead of hundreds of instances per crowd image disappears.  Same strings as `_coco_string` / pycocotools."""
     if not rles:
         return []
-    try:
-        from pycocotools import mask as mask_utils  # type: ignore  # noqa: F401
-
+    if _have_pycocotools():
         return [coco_encode_rle(r) for r in rles]       # the reference's own dependency, when it is installed
-    except ImportError:
-        pass
     import ctypes as C
 
     from . import lib as L

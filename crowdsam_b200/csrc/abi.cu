@@ -36,6 +36,10 @@ extern "C" int csam_coco_rle_strings(const int* counts, const long long* offsets
     for (long long i = 0; i < n; ++i) {
       long long x = c[i];
       if (i > 2) x -= c[i - 2];
+      if ((unsigned long long)(x + 16) < 32ull) {       // one character: the common case (|delta| < 16)
+        out[p++] = (char)((x & 0x1f) + 48);
+        continue;
+      }
       bool more = true;
       while (more) {
         char ch = (char)(x & 0x1f);

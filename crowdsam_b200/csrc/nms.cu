@@ -139,72 +139,119 @@ __global__ void points_occupied_kernel(const uint8_t* __restrict__ masks, int n_
 }
 
 // ---- RLE (column-major) -----------------------------------------------------------------------
-// element t of the Fortran-order flattening is mask[t % h][t / h]
-__device__ __forceinline__ uint8_t fval(const uint8_t* m, int h, int w, int t) { return m[(size_t)(t % h) * w + t / h]; }
+// Element t of the Fortran-order flattening is mask[t % h][t / h]; a "change" is a position t >= 1 whose value differs
+// from position t - 1.  Work item = (column c, row segment s) with RLE_NSEG segments per column, numbered c * NSEG + s
+// (= the order of the flattening), so one 1024 x 1024 mask is 8192 items spread over the whole GPU instead of one block
+// walking it (the kept masks of an image are often few: one block per mask left 147 SMs idle for ~0.3 ms per pass).
+// Threads of a block take adjacent columns of the same segment: every row read is a coalesced byte row.
+//   count: changes per item            -> item_cnt[n][w * NSEG]
+//   scan : exclusive scan per mask (in place) + n_runs[i] = changes + 1 + (mask starts with 1)
+//   fill : change positions            -> pos[offsets[i] + first_one + 1 + k]
+//   diff : run lengths = successive differences of {0, positions..., h * w}
+constexpr int RLE_NSEG = 8;
 
-// changes[t] (t >= 1) = flat[t] != flat[t-1]; block handles one mask; thread handles a contiguous chunk
-__global__ void __launch_bounds__(1024) rle_kernel(const uint8_t* __restrict__ masks, int h, int w,
-                                                   const long long* __restrict__ offsets, int* __restrict__ runs,
-                                                   int* __restrict__ n_runs) {
-  __shared__ int s_cnt[1024];
-  const uint8_t* m = masks + (size_t)blockIdx.x * h * w;
-  const int total = h * w;
-  const int chunk = (total + 1023) / 1024;
-  const int t0 = threadIdx.x * chunk, t1 = min(t0 + chunk, total);
+__device__ __forceinline__ uint8_t rle_pred(const uint8_t* m, int h, int w, int c, int r0) {
+  // the value in front of element (r0, c) in column-major order; the very first element is its own predecessor
+  if (r0 > 0) return m[(size_t)(r0 - 1) * w + c];
+  if (c > 0) return m[(size_t)(h - 1) * w + c - 1];
+  return m[0];
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) rle_items_kernel(const uint8_t* __restrict__ masks, int h, int w, int seg_rows,
+                                                        int* __restrict__ item_cnt, const long long* __restrict__ offsets,
+                                                        int* __restrict__ pos) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= w * RLE_NSEG) return;
+  const int c = tid % w, sgm = tid / w;
+  const uint8_t* m = masks + (size_t)blockIdx.y * h * w;
+  int* ic = item_cnt + (size_t)blockIdx.y * w * RLE_NSEG;
+  const int r0 = sgm * seg_rows, r1 = min(h, r0 + seg_rows);
   int cnt = 0;
-  if (t0 < t1) {
-    uint8_t prev = t0 > 0 ? fval(m, h, w, t0 - 1) : fval(m, h, w, 0);
-    for (int t = t0; t < t1; ++t) {
-      const uint8_t v = fval(m, h, w, t);
-      cnt += (v != prev);
+  int* out = nullptr;
+  if (FILL) out = pos + offsets[blockIdx.y] + (m[0] ? 1 : 0) + 1 + ic[c * RLE_NSEG + sgm];
+  if (r0 < r1) {
+    uint8_t prev = rle_pred(m, h, w, c, r0);
+    const uint8_t* col = m + c;
+    int r = r0;
+    for (; r + 8 <= r1; r += 8) {               // eight independent loads in flight
+      uint8_t v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = col[(size_t)(r + u) * w];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (v[u] != prev) {
+          if (FILL) out[cnt] = c * h + r + u;
+          ++cnt;
+        }
+        prev = v[u];
+      }
+    }
+    for (; r < r1; ++r) {
+      const uint8_t v = col[(size_t)r * w];
+      if (v != prev) {
+        if (FILL) out[cnt] = c * h + r;
+        ++cnt;
+      }
       prev = v;
     }
   }
-  s_cnt[threadIdx.x] = cnt;
+  if (!FILL) ic[c * RLE_NSEG + sgm] = cnt;
+}
+
+// one block per mask: exclusive scan of its item counts in place, n_runs
+__global__ void __launch_bounds__(1024) rle_scan_kernel(const uint8_t* __restrict__ masks, int h, int w,
+                                                        int* __restrict__ item_cnt, int* __restrict__ n_runs) {
+  __shared__ int s_warp[32];
+  const int items = w * RLE_NSEG;
+  int* ic = item_cnt + (size_t)blockIdx.x * items;
+  const int chunk = (items + 1023) / 1024;
+  const int i0 = min(threadIdx.x * chunk, items), i1 = min(i0 + chunk, items);
+  int sum = 0;
+  for (int i = i0; i < i1; ++i) sum += ic[i];
+  // block-wide exclusive scan of the 1024 partial sums
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = sum;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) s_warp[wid] = inc;
   __syncthreads();
-  // exclusive scan (Hillis-Steele on 1024 entries)
-  for (int o = 1; o < 1024; o <<= 1) {
-    const int v = threadIdx.x >= o ? s_cnt[threadIdx.x - o] : 0;
-    __syncthreads();
-    s_cnt[threadIdx.x] += v;
-    __syncthreads();
-  }
-  const int changes = s_cnt[1023];
-  const int first_one = m[0] ? 1 : 0;              // counts start with the number of zeros
-  const int nr = changes + 1 + first_one;
-  if (!runs) {                                     // counting pass
-    if (threadIdx.x == 0) n_runs[blockIdx.x] = nr;
-    return;
-  }
-  // second pass: write change positions, then turn them into run lengths in place
-  int* out = runs + offsets[blockIdx.x];
-  int k = s_cnt[threadIdx.x] - cnt + first_one;    // index of this thread's first change position
-  if (threadIdx.x == 0 && first_one) out[0] = 0;
-  if (t0 < t1) {
-    uint8_t prev = t0 > 0 ? fval(m, h, w, t0 - 1) : fval(m, h, w, 0);
-    for (int t = t0; t < t1; ++t) {
-      const uint8_t v = fval(m, h, w, t);
-      if (v != prev) out[k++ + 1] = t;             // slot j+1 holds the start of run j+1
-      prev = v;
+  if (wid == 0) {
+    int ws = s_warp[lane];
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, ws, o);
+      if (lane >= o) ws += v;
     }
+    s_warp[lane] = ws;
   }
-  __threadfence_block();
   __syncthreads();
-  // out[first_one + 1 + c] = position of change c; run lengths = successive differences
-  // work backwards-safe: each thread computes its lengths into registers first
-  const int base = first_one;                      // runs[base + r] for r = 0..changes
-  for (int r0 = 0; r0 <= changes; r0 += 1024) {
-    const int r = r0 + threadIdx.x;
-    int len = 0;
-    if (r <= changes) {
-      const int start = r == 0 ? 0 : out[base + r];
-      const int end = r == changes ? total : out[base + r + 1];
-      len = end - start;
-    }
-    __syncthreads();
-    if (r <= changes) out[base + r] = len;
-    __syncthreads();
+  int run = inc - sum + (wid > 0 ? s_warp[wid - 1] : 0);
+  for (int i = i0; i < i1; ++i) {
+    const int v = ic[i];
+    ic[i] = run;
+    run += v;
   }
+  if (threadIdx.x == 1023) {
+    const uint8_t first = masks[(size_t)blockIdx.x * h * w];
+    n_runs[blockIdx.x] = s_warp[31] + 1 + (first ? 1 : 0);      // counts start with the number of zeros
+  }
+}
+
+__global__ void __launch_bounds__(256) rle_diff_kernel(const uint8_t* __restrict__ masks, int h, int w,
+                                                       const long long* __restrict__ offsets, const int* __restrict__ n_runs,
+                                                       const int* __restrict__ pos, int* __restrict__ runs) {
+  const int b = blockIdx.y;
+  const int first_one = masks[(size_t)b * h * w] ? 1 : 0;
+  const int changes = n_runs[b] - 1 - first_one;
+  const long long off = offsets[b];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r == 0 && first_one) runs[off] = 0;
+  if (r > changes) return;
+  const int start = r == 0 ? 0 : pos[off + first_one + r];           // slot first_one + 1 + k = position of change k
+  const int end = r == changes ? h * w : pos[off + first_one + r + 1];
+  runs[off + first_one + r] = end - start;
 }
 
 }  // namespace csam
@@ -262,15 +309,34 @@ extern "C" int csam_points_occupied(const uint8_t* masks, int n_masks, int h, in
   return check_launch("points_occupied_kernel");
 }
 
-extern "C" int csam_rle_count(const uint8_t* masks, int n, int h, int w, int* n_runs, void* stream) {
-  CSAM_REQUIRE(masks && n_runs && n > 0 && h > 0 && w > 0, "csam_rle_count: bad args");
-  rle_kernel<<<n, 1024, 0, (cudaStream_t)stream>>>(masks, h, w, nullptr, nullptr, n_runs);
-  return check_launch("rle_kernel(count)");
+extern "C" long long csam_rle_scratch_bytes(int n, int h, int w) {
+  (void)h;
+  return (long long)sizeof(int) * (long long)(n > 0 ? n : 0) * (w > 0 ? w : 0) * RLE_NSEG;
 }
 
-extern "C" int csam_rle_fill(const uint8_t* masks, int n, int h, int w, const long long* offsets, int* runs,
-                             void* stream) {
-  CSAM_REQUIRE(masks && offsets && runs && n > 0 && h > 0 && w > 0, "csam_rle_fill: bad args");
-  rle_kernel<<<n, 1024, 0, (cudaStream_t)stream>>>(masks, h, w, offsets, runs, nullptr);
-  return check_launch("rle_kernel(fill)");
+extern "C" int csam_rle_count(const uint8_t* masks, int n, int h, int w, int* n_runs, void* scratch,
+                              long long scratch_bytes, void* stream) {
+  CSAM_REQUIRE(masks && n_runs && scratch && n > 0 && h > 0 && w > 0, "csam_rle_count: bad args");
+  CSAM_REQUIRE(n <= 65535 && (long long)h * w < (1ll << 31), "csam_rle_count: at most 65535 masks of less than 2^31 pixels");
+  CSAM_REQUIRE(scratch_bytes >= csam_rle_scratch_bytes(n, h, w), "csam_rle_count: scratch too small");
+  const int seg_rows = (h + RLE_NSEG - 1) / RLE_NSEG;
+  dim3 grid((w * RLE_NSEG + 255) / 256, n);
+  rle_items_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(masks, h, w, seg_rows, (int*)scratch, nullptr, nullptr);
+  if (check_launch("rle_items_kernel(count)")) return 1;
+  rle_scan_kernel<<<n, 1024, 0, (cudaStream_t)stream>>>(masks, h, w, (int*)scratch, n_runs);
+  return check_launch("rle_scan_kernel");
+}
+
+extern "C" int csam_rle_fill(const uint8_t* masks, int n, int h, int w, const long long* offsets, const int* n_runs,
+                             int max_runs, int* pos, int* runs, const void* scratch, void* stream) {
+  CSAM_REQUIRE(masks && offsets && n_runs && pos && runs && scratch && n > 0 && h > 0 && w > 0 && max_runs > 0,
+               "csam_rle_fill: bad args");
+  CSAM_REQUIRE(n <= 65535, "csam_rle_fill: at most 65535 masks");
+  const int seg_rows = (h + RLE_NSEG - 1) / RLE_NSEG;
+  dim3 grid((w * RLE_NSEG + 255) / 256, n);
+  rle_items_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(masks, h, w, seg_rows, (int*)scratch, offsets, pos);
+  if (check_launch("rle_items_kernel(fill)")) return 1;
+  dim3 grid2((max_runs + 255) / 256, n);
+  rle_diff_kernel<<<grid2, 256, 0, (cudaStream_t)stream>>>(masks, h, w, offsets, n_runs, pos, runs);
+  return check_launch("rle_diff_kernel");
 }

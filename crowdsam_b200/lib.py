@@ -112,8 +112,9 @@ _SIGS = {
     "csam_points_occupied": (ci, [vp, ci, ci, ci, vp, vp, ci, vp, vp]),
     "csam_small_regions_scratch_bytes": (cll, [ci, ci, ci]),
     "csam_remove_small_regions": (ci, [vp, ci, ci, ci, ci, ci, vp, vp, cll, vp]),
-    "csam_rle_count": (ci, [vp, ci, ci, ci, vp, vp]),
-    "csam_rle_fill": (ci, [vp, ci, ci, ci, vp, vp, vp]),
+    "csam_rle_scratch_bytes": (cll, [ci, ci, ci]),
+    "csam_rle_count": (ci, [vp, ci, ci, ci, vp, vp, cll, vp]),
+    "csam_rle_fill": (ci, [vp, ci, ci, ci, vp, vp, ci, vp, vp, vp, vp]),
     "csam_coco_rle_strings": (ci, [vp, vp, ci, vp, cll, vp]),
 }
 
@@ -145,7 +146,7 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.csam_abi_version() != 9:
+    if lib.csam_abi_version() != 10:
         raise RuntimeError("libcsam_sm100.so ABI version mismatch")
     _lib = lib
     return lib

@@ -6,6 +6,7 @@ import ctypes as C
 import os
 from typing import Optional
 
+import numpy as np
 import torch
 
 from . import lib as L
@@ -517,23 +518,26 @@ def points_occupied(masks: torch.Tensor, flag: torch.Tensor, pts_xy: torch.Tenso
 
 
 def rle_encode(masks: torch.Tensor):
-    """Column-major uncompressed RLE of bool masks [n,h,w] -> list of python int lists."""
+    """Column-major uncompressed RLE of bool masks [n,h,w] -> list of int32 numpy arrays (run lengths)."""
     n, h, w = masks.shape
     if n == 0:
         return []
     masks = masks.contiguous()
     dev = masks.device
+    lib = L.load()
     cnt = torch.empty((n,), dtype=torch.int32, device=dev)
-    L.check(L.load().csam_rle_count(_p(masks), n, h, w, _p(cnt), _stream()), "csam_rle_count")
-    cnt_h = cnt.cpu().long()
-    offs = torch.zeros((n + 1,), dtype=torch.int64)
-    offs[1:] = torch.cumsum(cnt_h, 0)
-    total = int(offs[-1])
-    runs = torch.empty((total,), dtype=torch.int32, device=dev)
-    offs_d = offs[:-1].to(dev)
-    L.check(L.load().csam_rle_fill(_p(masks), n, h, w, _p(offs_d), _p(runs), _stream()), "csam_rle_fill")
-    runs_h = runs.cpu().numpy()
-    o = offs.numpy()
+    need = lib.csam_rle_scratch_bytes(n, h, w)
+    scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+    L.check(lib.csam_rle_count(_p(masks), n, h, w, _p(cnt), _p(scratch), need, _stream()), "csam_rle_count")
+    o = np.zeros((n + 1,), dtype=np.int64)
+    cnt_h = cnt.cpu().numpy()                       # host decision: the size of the run buffer
+    np.cumsum(cnt_h, out=o[1:])
+    total = int(o[-1])
+    buf = torch.empty((2, total), dtype=torch.int32, device=dev)            # change positions | run lengths
+    offs_d = torch.from_numpy(o[:-1]).to(dev)
+    L.check(lib.csam_rle_fill(_p(masks), n, h, w, _p(offs_d), _p(cnt), int(cnt_h.max()), _p(buf[0]), _p(buf[1]),
+                              _p(scratch), _stream()), "csam_rle_fill")
+    runs_h = buf[1].cpu().numpy()
     return [runs_h[o[i]:o[i + 1]] for i in range(n)]
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSAM_ABI_VERSION 9
+#define CSAM_ABI_VERSION 10
 #if defined(__GNUC__)
 #define CSAM_API __attribute__((visibility("default")))
 #else
@@ -312,12 +312,19 @@ CSAM_API long long csam_small_regions_scratch_bytes(int n, int h, int w);
 CSAM_API int csam_remove_small_regions(uint8_t* masks, int n, int h, int w, int area_thresh, int mode, uint8_t* changed,
                               void* scratch, long long scratch_bytes, void* stream);
 
-/* Column-major run-length encoding of bool masks (amg.py:107-135), two passes:
- * count: n_runs[i] = number of runs of mask i (the first run counts zeros; 0 if the mask starts
- * with 1).  fill: runs[offsets[i] .. offsets[i]+n_runs[i]) = the run lengths (offsets = exclusive
- * prefix sum of n_runs, computed by the caller). */
-CSAM_API int csam_rle_count(const uint8_t* masks, int n, int h, int w, int* n_runs, void* stream);
-CSAM_API int csam_rle_fill(const uint8_t* masks, int n, int h, int w, const long long* offsets, int* runs, void* stream);
+/* Column-major run-length encoding of bool masks (amg.py:107-135), two passes with a host decision in between (the
+ * caller allocates `runs` from the counts):
+ * count: n_runs[i] = number of runs of mask i (the first run counts zeros; 0 if the mask starts with 1); leaves the
+ *        per-(column, row segment) change offsets of every mask in scratch (>= csam_rle_scratch_bytes(n,h,w)).
+ * fill : runs[offsets[i] .. offsets[i]+n_runs[i]) = the run lengths (offsets = exclusive prefix sum of n_runs, computed
+ *        by the caller; max_runs = max n_runs[i]); `pos` = int32 scratch of the same size as `runs` (change positions),
+ *        `scratch` and `n_runs` as left by csam_rle_count on the same masks.
+ * A mask is split into w * 8 work items, so a single kept mask occupies the whole GPU. */
+CSAM_API long long csam_rle_scratch_bytes(int n, int h, int w);
+CSAM_API int csam_rle_count(const uint8_t* masks, int n, int h, int w, int* n_runs, void* scratch, long long scratch_bytes,
+                            void* stream);
+CSAM_API int csam_rle_fill(const uint8_t* masks, int n, int h, int w, const long long* offsets, const int* n_runs,
+                           int max_runs, int* pos, int* runs, const void* scratch, void* stream);
 
 /* HOST function (no device work): COCO compressed RLE strings of n_masks run-length lists, replacing the per-mask
  * `coco_encode_rle` -> pycocotools `frPyObjects` call of amg.py:294-300 / model.py:184-185 (pycocotools' rleToString:
