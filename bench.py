@@ -468,7 +468,11 @@ def main():
             "dtype": "f16x3(fp32-accurate hi/lo split), fp32 accumulate" if os.environ.get("CSAM_PRECISION", "x3") != "x1" else "f16, fp32 accumulate",
             "data": "synthetic",
             "config": bench_config(arch, world),
-            "run": {"points_per_batch": args.points_per_batch, "masks_into_nms": nk[0], "detections": nk[1]},
+            "run": {"points_per_batch": args.points_per_batch, "masks_into_nms": nk[0], "detections": nk[1],
+                    # timed legs: SAM encoder and DINOv2 on two streams (engine.two_streams_enabled); the per-class
+                    # roofline pass below times every launch serialised on one stream
+                    "encoder_streams": 2 if os.environ.get("CSAM_TWO_STREAMS", "1") != "0" and not graphs.usable() else 1,
+                    "attn_pv_mmas": {1: 3, 0: 2}.get(ops.ATTN_PSPLIT, 1)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(imgs_np[0].nbytes),
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "graph_captures": int(graphs.captures), "setup_steps_before_warmup": int(priming), "clocks": clocks, "roofline": dominant, "rooflines": roofs,

@@ -88,9 +88,31 @@ class MaskData:
         return out
 
     def to_numpy(self) -> None:
+        dev = [k for k, v in self._stats.items() if isinstance(v, torch.Tensor) and v.is_cuda]
+        if len(dev) > 1:
+            # one device-to-host read for all device columns instead of one synchronising copy per column
+            for k, a in zip(dev, tensors_to_numpy_packed([self._stats[k] for k in dev])):
+                self._stats[k] = a
         for k, v in self._stats.items():
             if isinstance(v, torch.Tensor):
                 self._stats[k] = v.detach().cpu().numpy()
+
+
+def tensors_to_numpy_packed(tensors: List[torch.Tensor]) -> List[np.ndarray]:
+    """[t.cpu().numpy() for t in tensors] through ONE transfer: the tensors' bytes are concatenated on their device
+    (each padded to 8 bytes), copied once and cut up again on the host.  Same dtypes, shapes and values."""
+    parts, meta, off = [], [], 0
+    for t in tensors:
+        t = t.detach().contiguous()
+        b = t.reshape(-1).view(torch.uint8)
+        pad = (-b.numel()) % 8
+        parts.append(b)
+        if pad:
+            parts.append(torch.zeros(pad, dtype=torch.uint8, device=t.device))
+        meta.append((off, b.numel(), tuple(t.shape), torch.empty(0, dtype=t.dtype).numpy().dtype))
+        off += b.numel() + pad
+    flat = torch.cat(parts).cpu().numpy() if off else np.zeros(0, dtype=np.uint8)
+    return [flat[o:o + n].copy().view(dt).reshape(shape) for o, n, shape, dt in meta]
 
 
 def batch_iterator(batch_size: int, *args) -> Iterator[List[Any]]:

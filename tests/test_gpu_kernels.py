@@ -595,6 +595,22 @@ def test_rle_occupancy_overlap(golden_dir):
     assert torch.equal(inter.cpu().long(), ref_i) and torch.equal(area.cpu().long(), small.flatten(1).sum(1))
 
 
+@pytest.mark.parametrize("h,w", [(1, 1), (1, 9), (7, 1), (3, 5), (8, 8), (9, 1030), (1031, 13), (600, 900)])
+def test_rle_ragged_shapes(h, w):
+    """RLE work items are (column, row segment) pairs, 8 segments per column: fewer rows than segments, one row, one
+    column, sizes that are no multiple of anything, masks that start with a 1 / are constant."""
+    o = ops()
+    rng = np.random.default_rng(h * 131 + w)
+    mm = rng.random((5, h, w)) > 0.6
+    mm[1] = True
+    mm[2] = False
+    mm[3, 0, 0] = True
+    mm[4, :, : w // 2] = False          # long runs across column boundaries
+    runs = o.rle_encode(torch.as_tensor(mm).to(DEV))
+    for i in range(mm.shape[0]):
+        assert runs[i].tolist() == restate.mask_to_rle(mm[i])["counts"], (h, w, i)
+
+
 # ----------------------------------------------------------------- fused decoder GEMM epilogues
 @pytest.mark.skipif(0 not in IMPLS, reason="tcgen05 only")
 @pytest.mark.parametrize("split", [True, False])

@@ -1,5 +1,6 @@
 """CPU checks of host-side logic that the GPU tests rely on but that needs no device."""
 import numpy as np
+import torch
 
 from crowdsam_b200 import amg
 
@@ -58,3 +59,16 @@ def test_coco_string_batched_library_call_matches_scalar():
     assert [g["counts"] for g in got] == [_coco_string_scalar(list(r["counts"])) for r in rles]
     assert [g["size"] for g in got] == [list(r["size"]) for r in rles]
     assert amg.coco_encode_rles([]) == []
+
+
+def test_tensors_to_numpy_packed_equals_per_tensor_copies():
+    """MaskData.to_numpy reads all device columns back in one transfer: same dtypes, shapes, values (any device)."""
+    from crowdsam_b200.amg import tensors_to_numpy_packed
+
+    ts = [torch.randn(5, 4), torch.arange(7), torch.zeros(0, 4), torch.tensor([True, False, True]),
+          torch.randn(3).double(), torch.arange(3, dtype=torch.int32), torch.randn(0), torch.randn(2, 3, 5)[:, :, 1]]
+    for t, a in zip(ts, tensors_to_numpy_packed(ts)):
+        r = t.numpy()
+        assert a.dtype == r.dtype and a.shape == r.shape and np.array_equal(a, r)
+    assert tensors_to_numpy_packed([]) == []
+    assert tensors_to_numpy_packed([torch.zeros(0)])[0].shape == (0,)
