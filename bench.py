@@ -74,19 +74,20 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
-        sm, smax, reasons = [], None, set()
+        sm, smax, reasons, pw = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 smax = float(r[1])
+                pw.append(float(r[2]))
                 for n, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w": statistics.median(pw) if pw else None}
 
 
 def test_cfg(points_per_batch: int):
@@ -472,7 +473,9 @@ def main():
                     # timed legs: SAM encoder and DINOv2 on two streams (engine.two_streams_enabled); the per-class
                     # roofline pass below times every launch serialised on one stream
                     "encoder_streams": 2 if os.environ.get("CSAM_TWO_STREAMS", "1") != "0" and not graphs.usable() else 1,
-                    "attn_pv_mmas": {1: 3, 0: 2}.get(ops.ATTN_PSPLIT, 1)},
+                    "attn_pv_mmas": {1: 3, 0: 2}.get(ops.ATTN_PSPLIT, 1),
+                    # encoder GEMMs: 2 = cta_group::2 kernel with 256x128 pair tiles (library default), 0 = single-CTA
+                    "gemm_pair_mode": int(os.environ.get("CSAM_GEMM_PAIR", "2"))},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(imgs_np[0].nbytes),
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "graph_captures": int(graphs.captures), "setup_steps_before_warmup": int(priming), "clocks": clocks, "roofline": dominant, "rooflines": roofs,

@@ -924,8 +924,8 @@ extern "C" int csam_gemm(const csam_gemm_args* a, void* stream) {
     return split ? launch_tc<128, 3, true>(a, e, st) : launch_tc<128, 1, true>(a, e, st);
   }
   if (small_n) return split ? launch_tc<64, 3, false>(a, e, st) : launch_tc<64, 1, false>(a, e, st);
-  if (!wres_ok(128) || a->impl == CSAM_GEMM_TC_PAIR) {
-    // big encoder / DINOv2 shapes: 256 x 256 tiles on CTA pairs where the wave model favours them (gemm_pair.cu)
+  if ((!wres_ok(128) && a->impl != CSAM_GEMM_TC_SINGLE) || a->impl == CSAM_GEMM_TC_PAIR || a->impl == CSAM_GEMM_TC_PAIR128) {
+    // big encoder / DINOv2 shapes: pair tiles on CTA pairs (gemm_pair.cu; 256 x 128 by default, see CSAM_GEMM_PAIR)
     const int rc = launch_gemm_pair(a, e, st);
     if (rc >= 0) return rc;
   }

@@ -281,14 +281,18 @@ static int launch_pair_t(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t
 }
 
 int launch_gemm_pair(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st) {
-  // CSAM_GEMM_PAIR: unset / 0 = never (default), 1 = 256-wide pair tiles whenever the problem qualifies, 2 = 128-wide
-  // pair tiles whenever it qualifies (experiment), 3 = 256-wide where the wave model below favours them (the default
+  // CSAM_GEMM_PAIR: 0 = never, 1 = 256-wide pair tiles whenever the problem qualifies, 2 (default since the third session
+  // of round 2) = 256 x 128 pair tiles whenever it qualifies: the granularity of the single-CTA kernel with half the
+  // L2 -> shared-memory traffic per flop for the W operand.  Measured with the encoders on two streams under the power
+  // cap (three alternating runs on one box): GEMM class 16.0 against 16.6 ms serialised, step 41.2 against 41.5 ms, end
+  // to end 23.85 against 23.56 images/s, SM clock no lower.  3 = 256-wide where the wave model below favours them (the default
   // until the MMA-issue fix of round 2: with `elect.sync` role branches the single-CTA kernel issues its MMAs back to
   // back and the whole step measured 45.2 ms without pair tiles, 45.7 ms with the wave model, 46.2 ms with pair tiles
   // everywhere -- and CUDA-graph replay no longer pays the cluster-launch penalty).
   // impl == CSAM_GEMM_TC_PAIR in the arguments forces the 256-wide kernel (tests, A/B measurements).
-  static const int mode = getenv("CSAM_GEMM_PAIR") ? atoi(getenv("CSAM_GEMM_PAIR")) : 0;
-  const bool forced = a->impl == CSAM_GEMM_TC_PAIR;
+  static const int mode = getenv("CSAM_GEMM_PAIR") ? atoi(getenv("CSAM_GEMM_PAIR")) : 2;
+  const bool forced128 = a->impl == CSAM_GEMM_TC_PAIR128;
+  const bool forced = a->impl == CSAM_GEMM_TC_PAIR || forced128;
   if (mode == 0 && !forced) return -1;
   // qualifies: hi/lo split operands, K-major W, standard row-per-lane epilogue, whole k-blocks and pair tiles in N
   const int sms = num_sms();
@@ -301,6 +305,7 @@ int launch_gemm_pair(const csam_gemm_args* a, const GemmEpi& e, cudaStream_t st)
                                   "K >= 256 and 32-byte aligned outputs");
     return -1;
   }
+  if (forced128) return launch_pair_t<128>(a, e, st, tiles_m);
   if (!forced && mode == 2) {
     if ((long long)tiles_m * (a->N / 128) * 2 < sms) return -1;
     return launch_pair_t<128>(a, e, st, tiles_m);

@@ -51,9 +51,11 @@ CSAM_API long long csam_launch_count(void);
  *           out row = row_map ? row_map[r] : r  (negative = row dropped: window un-partition).
  * ------------------------------------------------------------------------------------------ */
 enum { CSAM_ACT_NONE = 0, CSAM_ACT_GELU = 1, CSAM_ACT_RELU = 2 };
-/* TCGEN05 = tensor-core kernels, tile shape / CTA-pair mode chosen by the library; SIMT = slow validation kernel;
- * TC_PAIR = force the 2-CTA (tcgen05 cta_group::2, 256x256 pair tiles) kernel, error if the problem does not qualify */
-enum { CSAM_GEMM_TCGEN05 = 0, CSAM_GEMM_SIMT = 1, CSAM_GEMM_TC_PAIR = 2 };
+/* TCGEN05 = tensor-core kernels, tile shape / CTA-pair mode chosen by the library (big split-operand problems run on
+ * CTA pairs with 256x128 pair tiles, the rest on the single-CTA kernel); SIMT = slow validation kernel;
+ * TC_PAIR / TC_PAIR128 = force the 2-CTA (tcgen05 cta_group::2) kernel with 256x256 / 256x128 pair tiles, error if the
+ * problem does not qualify; TC_SINGLE = force the single-CTA kernel (tests, A/B measurements) */
+enum { CSAM_GEMM_TCGEN05 = 0, CSAM_GEMM_SIMT = 1, CSAM_GEMM_TC_PAIR = 2, CSAM_GEMM_TC_SINGLE = 3, CSAM_GEMM_TC_PAIR128 = 4 };
 /* fused epilogues of the mask decoder (tcgen05 only):
  *  CSAM_EPI_LN   N == 256: y = LayerNorm(acc + bias + residual) * gamma + beta over the whole row;
  *                outputs (each optional): out_f32 = y, h16 pair (out_hi/lo) = y, h16 pair (out2_hi/lo) =
@@ -76,7 +78,7 @@ typedef struct {
   const int* row_map;                     /* [M] or NULL */
   float* out_f32; int ldo;                /* optional fp32 output */
   void* out_hi; void* out_lo; int ldh;    /* optional h16-pair output */
-  int impl;                               /* CSAM_GEMM_TCGEN05 / CSAM_GEMM_SIMT / CSAM_GEMM_TC_PAIR */
+  int impl;                               /* CSAM_GEMM_TCGEN05 / _SIMT / _TC_PAIR / _TC_SINGLE / _TC_PAIR128 */
   int b_mn_major;                         /* 1: W given as [K,N] row-major (ldw = N stride) */
   int epi;                                /* CSAM_EPI_* */
   const float* gamma; const float* beta; float eps;          /* EPI_LN / EPI_UP1 */

@@ -15,7 +15,7 @@ from oracle import fixtures, restate  # noqa: E402
 
 DEV = "cuda"
 # which GEMM / attention implementations to exercise: 0 = tcgen05, 1 = SIMT validation kernels
-IMPLS = [int(x) for x in os.environ.get("CSAM_TEST_IMPLS", "1,0").split(",")]
+IMPLS = [int(x) for x in os.environ.get("CSAM_TEST_IMPLS", "1,0,3").split(",")]      # SIMT, library choice, forced single-CTA
 ATTN_IMPLS = [int(x) for x in os.environ.get("CSAM_TEST_ATTN_IMPLS", "1,0").split(",")]
 
 
@@ -114,11 +114,13 @@ def test_gemm_epilogue(impl):
 
 
 @pytest.mark.skipif(0 not in IMPLS, reason="tcgen05 only")
+@pytest.mark.parametrize("pair_impl", [2, 4])
 @pytest.mark.parametrize("M,N,K", [(4096, 1024, 1024), (4900, 3072, 1024), (5330, 1024, 4096), (5330, 4096, 1024), (700, 2048, 256)])
-def test_gemm_pair_tiles_encoder_shapes(M, N, K):
-    """The 2-CTA (cta_group::2) 256x256 pair-tile kernel on the encoder / DINOv2 shapes, incl. ragged M (last pair tile
-    partly or wholly beyond M for one CTA of the pair), with the epilogue options the encoders use: bias + GELU +
-    LayerScale + in-place fp32 residual through a row scatter map, and fp32 + h16-pair outputs.  fp64 reference."""
+def test_gemm_pair_tiles_encoder_shapes(M, N, K, pair_impl):
+    """The 2-CTA (cta_group::2) kernel with 256x256 (impl 2) and 256x128 (impl 4, what the library picks by default for these
+    shapes) pair tiles on the encoder / DINOv2 shapes, incl. ragged M (last pair tile partly or wholly beyond M for one CTA
+    of the pair), with the epilogue options the encoders use: bias + GELU + LayerScale + in-place fp32 residual through a
+    row scatter map, and fp32 + h16-pair outputs.  fp64 reference; compared with the single-CTA kernel (impl 3) too."""
     o = ops()
     g = torch.Generator().manual_seed(M + N + K)
     a = torch.randn(M, K, generator=g)
@@ -127,7 +129,7 @@ def test_gemm_pair_tiles_encoder_shapes(M, N, K):
     ah, wh = _h16(a, True), _h16(w, True)
     acc = ah.float().cpu().double() @ wh.float().cpu().double().T
     # (1) plain: bias, fp32 + h16 outputs
-    PAIR = 2                                               # CSAM_GEMM_TC_PAIR: force the cta_group::2 kernel
+    PAIR = pair_impl                                       # CSAM_GEMM_TC_PAIR / _PAIR128: force the cta_group::2 kernel
     if N % 256 != 0 or K < 256:
         PAIR = 0
     l0 = lib_launches()
@@ -148,9 +150,10 @@ def test_gemm_pair_tiles_encoder_shapes(M, N, K):
     want[perm[keep].long()] += val[keep]
     assert _rel(x, want) < 2e-5, _rel(x, want)
     # (3) agrees with the single-CTA tcgen05 kernel and the SIMT kernel to accumulation order
-    out0, _ = o.gemm(ah, wh, bias=bias.to(DEV), want_f32=True, impl=0)
+    out0, _ = o.gemm(ah, wh, bias=bias.to(DEV), want_f32=True, impl=3)           # CSAM_GEMM_TC_SINGLE
     out1, _ = o.gemm(ah, wh, bias=bias.to(DEV), want_f32=True, impl=1)
-    assert _rel(out, out0) < 2e-5 and _rel(out, out1) < 2e-5
+    outd, _ = o.gemm(ah, wh, bias=bias.to(DEV), want_f32=True, impl=0)           # the library's own choice
+    assert _rel(out, out0) < 2e-5 and _rel(out, out1) < 2e-5 and _rel(out, outd) < 2e-5
 
 
 def test_gemm_pair_refuses_unqualified_problems():
