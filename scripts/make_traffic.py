@@ -4,7 +4,8 @@ usage: python scripts/make_traffic.py profiles/ncu_summary_r01.csv > profiles/tr
 import csv, json, sys
 
 CLASSES = {   # bench.py roofline name -> (report file prefix, kernel-name substring)
-    "gemm_tensor": ("prof_gemm_enc", "gemm_tc_kernel<128, 3, 0, 0, 0"),
+    # encoder / DINOv2 GEMMs: cta_group::2 kernel with 256x128 pair tiles since r04 (single-CTA kernel before)
+    "gemm_tensor": ("prof_gemm_enc", "gemm_"),
     "gemm_pair": ("prof_gemm_pair", "gemm_pair_kernel"),
     "mask_post_p1024": ("prof_post_p1024", "post_"),
     "gemm_hbm": ("prof_gemm_up", "gemm_tc_kernel"),
