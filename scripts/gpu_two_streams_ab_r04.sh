@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B on one box: encoders on two streams (CSAM_TWO_STREAMS) x P V with V as one fp16 (CSAM_ATTN_PSPLIT=-1).
-# usage: gpurun -- bash scripts/gpu_ab_r04.sh
+# usage: gpurun -- bash scripts/gpu_two_streams_ab_r04.sh
 mkdir -p gpurun_out
 export PYTHONPATH=$PWD
 timeout 300 python scripts/bench_overlap.py 2>&1 | tail -2
