@@ -378,22 +378,30 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
 //   P(j): fp16 pairs written over the first 32 columns of S(j) after S(j) has been read (no shared memory, no proxy
 //         fence); S(j+2) may only be issued once P V(j) has retired.
 // Shared memory holds nothing but the K/V ring (6-7 stages).
-template <int SPLIT, int BIAS, int NQ, int HD = 64>
+// G2 (global blocks, head dim 64, V as one fp16): the 64 per-query column terms of the decomposed rel-pos bias live in
+// shared memory instead of 64 registers per thread, the stage holds K hi | K lo | V hi only (24 KB, 3 stages), and TWO
+// CTAs share an SM (<= 128 registers, 256 TMEM columns, ~108 KB each): one CTA's load -> S -> softmax -> P V chain runs
+// under the other's, which is what the two query tiles per CTA do for the bias-free kernel (the round-1 review asked for
+// the bias out of the registers: one tile per CTA at 186 registers ran at 32-39 % tensor pipe).
+template <int SPLIT, int BIAS, int NQ, int HD = 64, int G2 = 0>
 struct AttnTsCfg {
   static constexpr int NOPS = (SPLIT == 3) ? 2 : 1;
   static constexpr int THREADS = 128 + 128 * NQ;
   static_assert(HD == 64 || (HD == 80 && NQ == 1), "head dim 64, or 80 with one query tile per CTA");
+  static_assert(G2 == 0 || (BIAS == 2 && NQ == 1 && HD == 64 && SPLIT == 3), "G2: split global blocks, head dim 64");
   static constexpr int NA = (HD + 63) / 64;                  // 64-wide swizzle atoms per K / V tile (80 -> 2, the second 1/4 used)
   static constexpr int KV_TILE = NA * AT_BN * 64 * 2;        // 8 KB per atom
-  static constexpr int STAGE_BYTES = NOPS * 2 * KV_TILE;
-  static constexpr int REL_BYTES = (BIAS == 1) ? NQ * AT_BM * AT_REL_LD * 4 : 0;
+  static constexpr int V_OPS = G2 ? 1 : NOPS;                // V tiles per stage (hi | lo, or hi only)
+  static constexpr int STAGE_BYTES = (NOPS + V_OPS) * KV_TILE;
+  static constexpr int REL_LD = G2 ? 68 : AT_REL_LD;         // 68 floats = 272 B: 16-byte aligned rows, conflict-free LDS.128
+  static constexpr int REL_BYTES = (BIAS == 1 || G2) ? NQ * AT_BM * REL_LD * 4 : 0;
   // window blocks, head dim 64: the decomposed rel-pos terms q . Rh[qh - kh + 13], q . Rw[qw - kw + 13] are computed IN the
   // kernel, as one small TS-mode MMA per query tile against both tables (27 + 27 rows of 64, hi | lo, K-major SW128)
   static constexpr int TAB_BYTES = (BIAS == 1 && HD == 64) ? 2 * 8192 : 0;
   static constexpr int STAGES_FIT = (227 * 1024 - REL_BYTES - TAB_BYTES - 512 - 1024) / STAGE_BYTES;
   // window blocks with ONE query tile per CTA (the default, see use_nq2): 4 key tiles in all, so a 2-stage ring is
   // enough and two CTAs (256 TMEM columns, ~82 KB, <= 128 registers each) share an SM
-  static constexpr int STAGES = (BIAS == 1 && NQ == 1 && HD == 64) ? 2 : (STAGES_FIT > 8 ? 8 : STAGES_FIT);
+  static constexpr int STAGES = (BIAS == 1 && NQ == 1 && HD == 64) ? 2 : G2 ? 3 : (STAGES_FIT > 8 ? 8 : STAGES_FIT);
   static constexpr int OFF_TAB = STAGES * STAGE_BYTES;        // 1024-byte aligned (stages are multiples of 16 KB)
   static constexpr int OFF_REL = OFF_TAB + TAB_BYTES;
   static constexpr int OFF_BAR = OFF_REL + REL_BYTES;
@@ -411,11 +419,11 @@ struct AttnTsBars {
   uint32_t tmem_slot;
 };
 
-template <int SPLIT, int BIAS, int NQ, int HD>
-__global__ void __launch_bounds__(128 + 128 * NQ, (BIAS == 1 && NQ == 1 && HD == 64) ? 2 : 1)
+template <int SPLIT, int BIAS, int NQ, int HD, int G2>
+__global__ void __launch_bounds__(128 + 128 * NQ, ((BIAS == 1 && NQ == 1 && HD == 64) || G2) ? 2 : 1)
 vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_constant__ CUtensorMap t_lo,
                         csam_attn_args a, const float* __restrict__ rel, int n_full, int n_single) {
-  using Cfg = AttnTsCfg<SPLIT, BIAS, NQ, HD>;
+  using Cfg = AttnTsCfg<SPLIT, BIAS, NQ, HD, G2>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int TS = Cfg::TSTRIDE;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -465,7 +473,7 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
   const bool rel_inkernel = (BIAS == 1) && Cfg::TAB_BYTES > 0 && rel == nullptr;
   // p_split < 0: V enters P V as ONE fp16 (no V_lo load, one MMA per k-step instead of two).  P is a single fp16 already,
   // so the product carries 2^-12 relative per factor instead of per probability only
-  const bool v_lo = (SPLIT == 3) && a.p_split >= 0;
+  const bool v_lo = (SPLIT == 3) && a.p_split >= 0 && !G2;      // (G2 stages have no room for V_lo)
   if (rel_inkernel) {
     // B operand [64 rows = 27 of Rh | 27 of Rw | 10 zero][K = 64], hi then lo, 128B-swizzled K-major
     uint8_t* tab = smem + Cfg::OFF_TAB;
@@ -495,7 +503,7 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
         mbar_wait(&bars->kv_empty[st], ((j / STAGES) & 1) ^ 1);
         uint8_t* sk = smem + st * Cfg::STAGE_BYTES;
         uint8_t* sv = sk + Cfg::NOPS * Cfg::KV_TILE;
-        mbar_expect_tx(&bars->kv_full[st], v_lo ? Cfg::STAGE_BYTES : Cfg::STAGE_BYTES - (Cfg::NOPS - 1) * Cfg::KV_TILE);
+        mbar_expect_tx(&bars->kv_full[st], (Cfg::NOPS + (v_lo ? Cfg::NOPS : 1)) * Cfg::KV_TILE);
         const int row = row_base + j * AT_BN;
 #pragma unroll
         for (int at = 0; at < Cfg::NA; ++at) {      // head dim 80: a second 64-wide box of which 16 columns are used
@@ -622,11 +630,18 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->q_ready[qt]);
     }
-    float relw[BIAS == 2 ? 64 : 1];
+    float relw[(BIAS == 2 && !G2) ? 64 : 1];
     const float* relq = nullptr;
-    float* rel_r = rel_s + (qt * AT_BM + r) * AT_REL_LD;
+    float* rel_r = rel_s + (qt * AT_BM + r) * Cfg::REL_LD;
     if (BIAS != 0 && !rel_inkernel) relq = rel + (((size_t)g * a.heads + h) * a.tokens + qc) * 2 * a.S;
-    if (BIAS == 2) {
+    if (BIAS == 2 && G2) {
+      // this row's 64 column terms -> its own shared-memory row (read back by the same thread: no barrier needed)
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) {
+        const float4 t4 = *reinterpret_cast<const float4*>(relq + 64 + c);
+        *reinterpret_cast<float4*>(rel_r + c) = make_float4(t4.x * LOG2E, t4.y * LOG2E, t4.z * LOG2E, t4.w * LOG2E);
+      }
+    } else if (BIAS == 2) {
 #pragma unroll
       for (int c = 0; c < 64; ++c) relw[c] = relq[64 + c] * LOG2E;
     }
@@ -682,7 +697,7 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
       if (BIAS == 2) {
         const float bh = relq[j] * LOG2E;
 #pragma unroll
-        for (int c = 0; c < 64; ++c) s[c] = fmaf(__uint_as_float(raw[c]), scale2, bh + relw[c]);
+        for (int c = 0; c < 64; ++c) s[c] = fmaf(__uint_as_float(raw[c]), scale2, bh + (G2 ? rel_r[c] : relw[c]));
       } else if (BIAS == 1) {
         int kh = key0 / 14, kw = key0 % 14;
 #pragma unroll
@@ -780,16 +795,16 @@ vit_attention_ts_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_c
   if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
-template <int SPLIT, int BIAS, int NQ, int HD = 64>
+template <int SPLIT, int BIAS, int NQ, int HD = 64, int G2 = 0>
 static int launch_attn_ts(const csam_attn_args* a, const float* rel, cudaStream_t st) {
-  using Cfg = AttnTsCfg<SPLIT, BIAS, NQ, HD>;
+  using Cfg = AttnTsCfg<SPLIT, BIAS, NQ, HD, G2>;
   CUtensorMap t_hi, t_lo;
   const uint64_t rows = (uint64_t)a->groups * a->tokens;
   const uint64_t cols = 3ull * a->heads * a->hd;
   if (make_tmap_2d_f16(&t_hi, a->qkv_hi, rows, cols, a->ld_qkv, 64, 64)) return 1;
   t_lo = t_hi;
   if (SPLIT == 3 && make_tmap_2d_f16(&t_lo, a->qkv_lo, rows, cols, a->ld_qkv, 64, 64)) return 1;
-  auto kern = vit_attention_ts_kernel<SPLIT, BIAS, NQ, HD>;
+  auto kern = vit_attention_ts_kernel<SPLIT, BIAS, NQ, HD, G2>;
   CSAM_DYN_SMEM(kern, Cfg::SMEM_BYTES, "vit_attention_ts_kernel");
   // query tiles -> n_full items of NQ tiles + n_single items of one tile (per head and group)
   const int tiles = (a->tokens + AT_BM - 1) / AT_BM;
@@ -883,6 +898,9 @@ int vit_attention_tc(const csam_attn_args* a, cudaStream_t st) {
       if (split) {
         if (bias == 0) return nq2 ? launch_attn_ts<3, 0, 2>(a, rel, st) : launch_attn_ts<3, 0, 1>(a, rel, st);
         if (bias == 1) return nq2 ? launch_attn_ts<3, 1, 2>(a, rel, st) : launch_attn_ts<3, 1, 1>(a, rel, st);
+        // global blocks with V as one fp16 (the default): two CTAs per SM, column bias terms in shared memory
+        static const int g2_env = getenv("CSAM_ATTN_G2") ? atoi(getenv("CSAM_ATTN_G2")) : 1;
+        if (g2_env && a->p_split < 0 && a->S == 64) return launch_attn_ts<3, 2, 1, 64, 1>(a, rel, st);
         return launch_attn_ts<3, 2, 1>(a, rel, st);
       }
       if (bias == 0) return nq2 ? launch_attn_ts<1, 0, 2>(a, rel, st) : launch_attn_ts<1, 0, 1>(a, rel, st);
