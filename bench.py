@@ -80,7 +80,10 @@ class ClockSampler:
             try:
                 sm.append(float(r[0]))
                 smax = float(r[1])
-                pw.append(float(r[2]))
+                try:
+                    pw.append(float(r[2]))
+                except ValueError:
+                    pass                                   # power.draw can read "[N/A]"; the clocks / reasons still count
                 for n, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
