@@ -72,3 +72,58 @@ def test_tensors_to_numpy_packed_equals_per_tensor_copies():
         assert a.dtype == r.dtype and a.shape == r.shape and np.array_equal(a, r)
     assert tensors_to_numpy_packed([]) == []
     assert tensors_to_numpy_packed([torch.zeros(0)])[0].shape == (0,)
+
+
+def test_interleave_two_streams_protocol(monkeypatch):
+    """engine.interleave_two_streams (host logic of the two-stream encoders) with fake streams: the side generator is only
+    ever resumed inside the side-stream context, the main one outside, block by block in alternation; the side stream first
+    waits for the main stream and the main stream waits for the side stream at the end; both results come back."""
+    import contextlib
+
+    from crowdsam_b200 import engine
+
+    log = []
+
+    class FakeStream:
+        def __init__(self, name="side", **kw):
+            self.name = name
+
+        def wait_stream(self, other):
+            log.append(("wait", self.name, other.name))
+
+    main = FakeStream("main")
+    current = [main]
+
+    @contextlib.contextmanager
+    def fake_ctx(s):
+        current.append(s)
+        try:
+            yield
+        finally:
+            current.pop()
+
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: main)
+    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+    monkeypatch.setattr(torch.cuda, "stream", fake_ctx)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(engine, "_side_streams", {})
+
+    def gen(tag, blocks):
+        log.append((tag, "prologue", current[-1].name))
+        for b in range(blocks):
+            yield
+            log.append((tag, b, current[-1].name))
+        return tag + "-result"
+
+    res = engine.interleave_two_streams(gen("sam", 3), gen("dino", 5), "cuda:0")
+    assert res == ("sam-result", "dino-result")
+    assert log[0] == ("wait", "side", "main") and log[-1] == ("wait", "main", "side")
+    steps = [e for e in log if e[0] in ("sam", "dino")]
+    assert all(e[2] == ("main" if e[0] == "sam" else "side") for e in steps)
+    assert [e[1] for e in steps if e[0] == "sam"] == ["prologue", 0, 1, 2]
+    assert [e[1] for e in steps if e[0] == "dino"] == ["prologue", 0, 1, 2, 3, 4]
+    # alternation while both are live: dino k, sam k, dino k+1, ...
+    order = [e[0] for e in steps[:8]]
+    assert order == ["dino", "sam"] * 4
+    # run_steps: the single-stream driver of the same generators
+    assert engine.run_steps(gen("sam", 2)) == "sam-result"
